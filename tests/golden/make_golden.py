@@ -1,0 +1,202 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (discsim/frank 1.2.3).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Inputs are seeded synthetic visibilities (generated with NumPy only, stored in the
+fixture so tests never need the reference) plus the 196-row AS 209 subsample shipped in
+the reference's docs (docs/tutorials/test_datafile.txt, data not source).  Outputs are
+whatever the reference's public API returns for them:
+
+  j0_golden.npz      scipy.special.j0 on sample arguments (the reference's J0, hankel.py:23)
+  dht.npz            DiscreteHankelTransform tables / coefficients / transform (hankel.py)
+  mapping.npz        VisibilityMapping.map_visibilities M, j, H0 for opt_thick / opt_thin /
+                     debris / multi-channel (statistical_models.py:109-237)
+  fit_normal.npz     FrankFitter(method='Normal').fit  MAP, power spectrum, iterations
+  fit_lognormal.npz  FrankFitter(method='LogNormal').fit
+  fit_as209sub.npz   FrankFitter on the 196-visibility AS 209 subsample, N=20
+  uvbin.npz          UVDataBinner bin indices, counts, means, errors (utilities.py:180-400)
+  gauss_kat.npz      the reference's analytic Gaussian Hankel-pair test inputs (tests.py:37-130)
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+REF = '/root/reference'
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+warnings.filterwarnings('ignore')
+
+import scipy.special  # noqa: E402
+import frank  # noqa: E402
+from frank.constants import rad_to_arcsec, deg_to_rad  # noqa: E402
+from frank.geometry import FixedGeometry  # noqa: E402
+from frank.hankel import DiscreteHankelTransform  # noqa: E402
+from frank.radial_fitters import FrankFitter, FourierBesselFitter  # noqa: E402
+from frank.debris_fitters import FrankDebrisFitter  # noqa: E402
+from frank.statistical_models import VisibilityMapping  # noqa: E402
+from frank.utilities import UVDataBinner  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+assert frank.__version__ == '1.2.3', frank.__version__
+
+
+def synthetic(n_vis, N, Rmax=1.6, seed=12345, geom=(30., 40., 1e-3, -2e-3)):
+    """Seeded Gaussian-ring disc of SURVEY.md section 8(d), built through the reference."""
+    rng = np.random.default_rng(seed)
+    g = FixedGeometry(*geom)
+    dht = DiscreteHankelTransform(Rmax / rad_to_arcsec, N)
+    vm = VisibilityMapping(dht, g, verbose=False)
+    q = 0.98 * dht.q[-1] * np.sqrt(rng.uniform(1e-5, 1, n_vis))
+    th = rng.uniform(0, 2 * np.pi, n_vis)
+    ud, vd = q * np.cos(th), q * np.sin(th)
+    u, v = g.reproject(ud, vd)
+    r = dht.r * rad_to_arcsec
+    I = 1e10 * np.exp(-0.5 * ((r - 0.6) / 0.08) ** 2) + 3e9 * np.exp(-0.5 * (r / 0.3) ** 2)
+    Vd = vm.predict_visibilities(I, q, k=None)
+    _, _, V = g.undo_correction(ud, vd, Vd.astype(complex))
+    w = 1e4 * rng.uniform(0.5, 2, n_vis)
+    V = V + (rng.standard_normal(n_vis) + 1j * rng.standard_normal(n_vis)) / np.sqrt(w)
+    return u, v, V, w, g
+
+
+def main():
+    # ---- J0 -------------------------------------------------------------------------------
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(0, 1e-5, 200), rng.uniform(0, 5, 3000), rng.uniform(5, 30, 3000),
+                        rng.uniform(30, 950, 6000), rng.uniform(950, 6300, 3000),
+                        scipy.special.jn_zeros(0, 300), [0.0, 5.0, 1e-5]])
+    np.savez_compressed(os.path.join(OUT, 'j0_golden.npz'), x=x, j0=scipy.special.j0(x))
+
+    # ---- DHT ------------------------------------------------------------------------------
+    N = 64
+    dht = DiscreteHankelTransform(1.6 / rad_to_arcsec, N)
+    qs = np.random.default_rng(3).uniform(0, dht.q[-1], 40)
+    f = np.exp(-0.5 * (dht.r * rad_to_arcsec / 0.4) ** 2)
+    np.savez_compressed(os.path.join(OUT, 'dht.npz'), Rmax=dht.Rmax, N=N, r=dht.r, q=dht.q, Qmax=dht.Qmax,
+                        Ykm=dht._Ykm, scale_factor=dht._scale_factor, j_nk=dht._j_nk, j_nN=dht._j_nN,
+                        coeff=dht.coefficients(), qs=qs, coeff_qs=dht.coefficients(qs),
+                        f=f, Hf=dht.transform(f), Hf_qs=dht.transform(f, qs))
+
+    # ---- mapping --------------------------------------------------------------------------
+    n_vis, N = 6000, 60
+    u, v, V, w, g = synthetic(n_vis, N)
+    dht = DiscreteHankelTransform(1.6 / rad_to_arcsec, N)
+    out = dict(u=u, v=v, V=V, w=w, N=N, Rmax=1.6, geom=np.array([g.inc, g.PA, g.dRA, g.dDec]))
+    for model in ['opt_thick', 'opt_thin']:
+        vm = VisibilityMapping(dht, g, vis_model=model, verbose=False)
+        m = vm.map_visibilities(u, v, V, w)
+        out.update({f'M_{model}': m['M'], f'j_{model}': m['j'], f'H0_{model}': m['null_likelihood']})
+    up, vp, wp, Vp = g.apply_correction(u, v, V, use3D=True)
+    out.update(up=up, vp=vp, wp=wp, Vp=Vp, q=np.hypot(up, vp))
+    vm = VisibilityMapping(dht, g, vis_model='debris', scale_height=lambda r: 0.05 * r, verbose=False)
+    m = vm.map_visibilities(u, v, V, w)
+    out.update(M_debris=m['M'], j_debris=m['j'], H0_debris=m['null_likelihood'], H2_debris=vm._H2)
+    freqs = np.random.default_rng(5).choice(np.array([2.1e11, 2.3e11, 3.4e11]), n_vis)
+    vm = VisibilityMapping(dht, g, verbose=False)
+    m = vm.map_visibilities(u, v, V, w, frequencies=freqs)
+    out.update(freqs=freqs, M_multi=m['M'], j_multi=m['j'], H0_multi=m['null_likelihood'], channels=m['channels'])
+    m = vm.map_visibilities(u, v, V, 2.5)       # scalar weights (radial_fitters.py:544)
+    out.update(M_scalar_w=m['M'], j_scalar_w=m['j'], H0_scalar_w=m['null_likelihood'])
+    Itest = 1e10 * np.exp(-0.5 * ((dht.r * rad_to_arcsec - 0.6) / 0.08) ** 2)
+    out.update(I_pred=Itest, V_pred=vm.predict_visibilities(Itest, out['q'], wp))
+    np.savez_compressed(os.path.join(OUT, 'mapping.npz'), **out)
+
+    # ---- Normal fit -----------------------------------------------------------------------
+    FF = FrankFitter(1.6, N, g, alpha=1.05, weights_smooth=1e-4, verbose=False,
+                     store_iteration_diagnostics=True)
+    sol = FF.fit(u, v, V, w)
+    diag = FF.iteration_diagnostics
+    uu = np.random.default_rng(11).uniform(-2e6, 2e6, 50)
+    vv = np.random.default_rng(12).uniform(-2e6, 2e6, 50)
+    np.savez_compressed(os.path.join(OUT, 'fit_normal.npz'), MAP=sol.MAP, power_spectrum=sol.power_spectrum,
+                        num_iterations=diag['num_iterations'], p_first=np.array(diag['power_spectrum'][:3]),
+                        MAP_first=np.array(diag['MAP'][:3]), r=sol.r, q=sol.q, covariance=sol.covariance,
+                        log_evidence=FF.log_evidence_laplace(), log_like=sol.log_likelihood(),
+                        upred=uu, vpred=vv, Vpred=sol.predict(uu, vv),
+                        Vpred_deproj=sol.predict_deprojected(sol.q))
+    # alpha / wsmooth variation (config 4 grid points)
+    sweep = []
+    for alpha, ws in [(1.3, 1e-2), (1.01, 1e-1)]:
+        FF2 = FrankFitter(1.6, N, g, alpha=alpha, weights_smooth=ws, verbose=False,
+                          store_iteration_diagnostics=True)
+        s2 = FF2.fit(u, v, V, w)
+        sweep.append((alpha, ws, FF2.iteration_diagnostics['num_iterations'], s2.MAP, s2.power_spectrum))
+    np.savez_compressed(os.path.join(OUT, 'fit_sweep.npz'), alpha=[s[0] for s in sweep], ws=[s[1] for s in sweep],
+                        num_iterations=[s[2] for s in sweep], MAP=np.array([s[3] for s in sweep]),
+                        power_spectrum=np.array([s[4] for s in sweep]))
+    # non-parametric (no prior) fit
+    FB = FourierBesselFitter(1.6, 20, g, verbose=False)
+    sb = FB.fit(u, v, V, w)
+    np.savez_compressed(os.path.join(OUT, 'fit_fourier_bessel.npz'), MAP=sb.MAP)
+
+    # ---- LogNormal fit --------------------------------------------------------------------
+    Nl = 40
+    ul, vl, Vl, wl, _ = synthetic(4000, Nl, seed=777)
+    FL = FrankFitter(1.6, Nl, g, alpha=1.3, weights_smooth=1e-2, method='LogNormal', verbose=False,
+                     store_iteration_diagnostics=True)
+    sl = FL.fit(ul, vl, Vl, wl)
+    dl = FL.iteration_diagnostics
+    np.savez_compressed(os.path.join(OUT, 'fit_lognormal.npz'), N=Nl, u=ul, v=vl, V=Vl, w=wl, M=FL._M, j=FL._j, MAP=sl.MAP, power_spectrum=sl.power_spectrum,
+                        num_iterations=dl['num_iterations'], s_MAP=sl._fit.MAP,
+                        p_first=np.array(dl['power_spectrum'][:3]), MAP_first=np.array(dl['MAP'][:3]))
+
+    # ---- debris Normal fit ----------------------------------------------------------------
+    FD = FrankDebrisFitter(1.6, 40, g, lambda r: 0.05 * r, alpha=1.3, weights_smooth=1e-2, verbose=False,
+                           store_iteration_diagnostics=True)
+    sd = FD.fit(ul, vl, Vl, wl)
+    np.savez_compressed(os.path.join(OUT, 'fit_debris.npz'), N=40, MAP=sd.MAP, power_spectrum=sd.power_spectrum,
+                        num_iterations=FD.iteration_diagnostics['num_iterations'])
+
+    # ---- AS 209 subsample (196 visibilities), N=20 -------------------------------------
+    ua, va, re, im, wa = np.genfromtxt(os.path.join(REF, 'docs/tutorials/test_datafile.txt')).T
+    Va = re + 1j * im
+    ga = FixedGeometry(34.97, 85.76, dRA=1.9e-3, dDec=-2.5e-3)      # AS 209 geometry, frank/tests.py:150-151
+    FA = FrankFitter(1.6, 20, ga, alpha=1.05, weights_smooth=1e-2, verbose=False,
+                     store_iteration_diagnostics=True, check_qbounds=False, convergence_failure='warn')
+    sa = FA.fit(ua, va, Va, wa)
+    np.savez_compressed(os.path.join(OUT, 'fit_as209sub.npz'), u=ua, v=va, V=Va, w=wa,
+                        geom=np.array([ga.inc, ga.PA, ga.dRA, ga.dDec]), MAP=sa.MAP,
+                        power_spectrum=sa.power_spectrum, M=FA._M, j=FA._j, H0=FA._H0,
+                        num_iterations=FA.iteration_diagnostics['num_iterations'])
+
+    # ---- UV binner ------------------------------------------------------------------------
+    uvd = out['q']
+    for tag, width in [('a', 5e4), ('b', 1e3)]:
+        b = UVDataBinner(uvd, out['Vp'], w, width)
+        np.savez_compressed(os.path.join(OUT, f'uvbin_{tag}.npz'), uv_in=uvd, V_in=out['Vp'], w_in=w, width=width,
+                            idx=b.determine_uv_bin(uvd), uv=b.uv.filled(0), V=b.V.filled(0),
+                            weights=b.weights.filled(0), counts=b.bin_counts.filled(0),
+                            error=b.error.filled(np.nan), mask=np.ma.getmaskarray(b.uv),
+                            left=b.bin_edges[0].filled(0), right=b.bin_edges[1].filled(0))
+    # real-valued V and boundary-exact points
+    uvx = np.concatenate([np.arange(0, 11) * 1e3, [9999.999999999998, 1e4 * (1 - 1e-16), 3e3 + 1e-9]])
+    Vx = np.linspace(-1, 1, len(uvx))
+    wx = np.linspace(1, 2, len(uvx))
+    b = UVDataBinner(uvx, Vx, wx, 1e3)
+    np.savez_compressed(os.path.join(OUT, 'uvbin_edge.npz'), uv_in=uvx, V_in=Vx, w_in=wx, width=1e3,
+                        idx=b.determine_uv_bin(uvx), uv=b.uv.filled(0), V=b.V.filled(0),
+                        weights=b.weights.filled(0), counts=b.bin_counts.filled(0),
+                        error=b.error.filled(np.nan), mask=np.ma.getmaskarray(b.uv))
+
+    # ---- analytic Gaussian pair (frank/tests.py:37-130) --------------------------------------
+    def gauss_vis(q, inc):
+        return np.cos(inc * deg_to_rad) * 2 * np.pi * np.exp(-0.5 * (2 * np.pi * q) ** 2)
+    dht = DiscreteHankelTransform(5.0, 100)
+    gk = FixedGeometry(60, 0)
+    vm = VisibilityMapping(dht, gk, verbose=False)
+    Ig = np.exp(-0.5 * (dht.r) ** 2)
+    np.savez_compressed(os.path.join(OUT, 'gauss_kat.npz'), r=dht.r, q=dht.q, I=Ig,
+                        V_model=vm.predict_visibilities(Ig, dht.q), V_exact=gauss_vis(dht.q, 60.))
+    print('golden fixtures written to', OUT)
+    for fn in sorted(os.listdir(OUT)):
+        if fn.endswith('.npz'):
+            print(f'  {fn:24s} {os.path.getsize(os.path.join(OUT, fn)) / 1024:8.1f} KB')
+
+
+if __name__ == '__main__':
+    main()
