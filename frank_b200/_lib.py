@@ -1,0 +1,166 @@
+"""ctypes binding of libfrankb200.so (the C ABI in include/frankb200.h).
+
+There is no CPU fallback: importing this module without the compiled library, or creating a
+context without a CUDA device, raises.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libfrankb200.so')
+
+FB_E_QRANGE, FB_E_NOTPD, FB_E_BADP = 1, 2, 3
+MODEL_CODE = {'opt_thick': 0, 'opt_thin': 1, 'debris': 2}
+
+
+class FBGeometry(ctypes.Structure):
+    _fields_ = [('a_ra', ctypes.c_double), ('a_dec', ctypes.c_double),
+                ('cos_pa', ctypes.c_double), ('sin_pa', ctypes.c_double),
+                ('cos_inc', ctypes.c_double), ('sin_inc', ctypes.c_double)]
+
+
+_c_p = ctypes.c_void_p
+_c_i = ctypes.c_int
+_c_l = ctypes.c_int64
+_c_d = ctypes.c_double
+
+_SIGNATURES = {
+    'fb_version': ([], _c_i),
+    'fb_ctx_create': ([ctypes.POINTER(_c_p), _c_i], _c_i),
+    'fb_ctx_destroy': ([_c_p], _c_i),
+    'fb_last_error': ([_c_p], ctypes.c_char_p),
+    'fb_dht_setup': ([_c_p, _c_i, _c_d, _c_p, _c_p, _c_p, _c_d], _c_i),
+    'fb_map_visibilities_dev': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_i, _c_p, _c_i, ctypes.POINTER(FBGeometry),
+                                 _c_i, _c_d, _c_p, _c_i, _c_d, _c_p, _c_p, _c_p, _c_p], _c_i),
+    'fb_map_visibilities_host': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_i, _c_p, _c_i, ctypes.POINTER(FBGeometry),
+                                  _c_i, _c_d, _c_p, _c_i, _c_d, _c_p, _c_p, _c_p, _c_p], _c_i),
+    'fb_last_map_timing': ([_c_p, _c_p], _c_i),
+    'fb_debug_prepped': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p], _c_i),
+    'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libfrankb200.so (built by `make -C frank_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"frank_b200: compiled CUDA library not found at {LIB_PATH}. Build it with "
+                    "`make -C frank_b200/csrc` (needs nvcc, sm_100a). There is no CPU fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (args, res) in _SIGNATURES.items():
+                fn = getattr(lib, name)     # AttributeError if the ABI and the header drifted apart
+                fn.argtypes = args
+                fn.restype = res
+            _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def _ptr(x):
+    """Raw pointer of a torch tensor / numpy array / None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data_as(_c_p)
+    return _c_p(x.data_ptr())          # torch.Tensor
+
+
+class Context(object):
+    """One fb_ctx: a CUDA stream, workspaces and DHT tables on one device."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        h = _c_p()
+        rc = self._lib.fb_ctx_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            raise RuntimeError(f"frank_b200: fb_ctx_create(device={device}) failed with status {rc} "
+                               "(no CUDA device, or not an sm_100 part). There is no CPU fallback.")
+        self._h = h
+        self.device = int(device)
+        self._dht_key = None
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.fb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def error(self):
+        return self._lib.fb_last_error(self._h).decode()
+
+    def check(self, rc, what):
+        if rc < 0:
+            raise RuntimeError(f"frank_b200: {what} failed ({rc}): {self.error()}")
+        return rc
+
+    # -- DHT ---------------------------------------------------------------------------------
+    def dht_setup(self, dht, x_max=0.0):
+        key = (dht.Rmax, dht.size, dht.order)
+        if self._dht_key == key:
+            return
+        j_nk = np.ascontiguousarray(dht._j_nk, dtype=np.float64)
+        coef = np.ascontiguousarray((1 / (np.pi * dht.Qmax ** 2)) * dht._scale_factor, dtype=np.float64)
+        Y = np.ascontiguousarray(dht.coefficients(), dtype=np.float64)
+        self.check(self._lib.fb_dht_setup(self._h, dht.size, float(dht.Qmax), _ptr(j_nk), _ptr(coef), _ptr(Y),
+                                          float(x_max)), 'fb_dht_setup')
+        self._dht_key = key
+
+    # -- mapping -----------------------------------------------------------------------------
+    def map_visibilities(self, n, u, v, V, w, w_stride, geom, vis_model, model_scale, H2, check_qbounds,
+                         q_last, M, j, H0, host=False):
+        """Thin call into fb_map_visibilities_{dev,host}.  Returns (status, qmin, qmax)."""
+        qmm = np.zeros(2)
+        fn = self._lib.fb_map_visibilities_host if host else self._lib.fb_map_visibilities_dev
+        H2p = None if H2 is None else np.ascontiguousarray(H2, dtype=np.float64)
+        rc = fn(self._h, int(n), _ptr(u), _ptr(v), _ptr(V), _ptr(w), int(w_stride), None, 1, ctypes.byref(geom),
+                int(vis_model), float(model_scale), _ptr(H2p), int(bool(check_qbounds)), float(q_last),
+                _ptr(M), _ptr(j), _ptr(H0), _ptr(qmm))
+        self.check(rc, 'fb_map_visibilities')
+        return rc, qmm[0], qmm[1]
+
+    def last_map_timing(self):
+        t = np.zeros(4)
+        self._lib.fb_last_map_timing(self._h, _ptr(t))
+        return {'prep_ms': t[0], 'gram_ms': t[1], 'finalize_ms': t[2], 'copy_ms': t[3]}
+
+    def debug_prepped(self, n):
+        a, kz, Vre, perm = np.empty(n), np.empty(n), np.empty(n), np.empty(n, dtype=np.uint32)
+        self.check(self._lib.fb_debug_prepped(self._h, int(n), _ptr(a), _ptr(kz), _ptr(Vre), _ptr(perm)),
+                   'fb_debug_prepped')
+        return a, kz, Vre, perm
+
+    def debug_j0(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self.check(self._lib.fb_debug_j0(self._h, x.size, _ptr(x), _ptr(out)), 'fb_debug_j0')
+        return out
+
+
+_contexts = {}
+
+
+def get_context(device=None):
+    """Process-wide context per device (one process per GPU is the deployment model)."""
+    if device is None:
+        device = int(os.environ.get('LOCAL_RANK', '0')) if 'FRANK_B200_DEVICE' not in os.environ \
+            else int(os.environ['FRANK_B200_DEVICE'])
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]

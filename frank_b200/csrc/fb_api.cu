@@ -1,0 +1,261 @@
+// C ABI of libfrankb200 (see include/frankb200.h): context, DHT setup, map_visibilities entry points.
+#include "fb_common.cuh"
+
+#include <cmath>
+#include <cstring>
+
+extern "C" {
+
+int fb_version(void) { return 100; }
+
+int fb_ctx_create(fb_ctx **out, int device)
+{
+    if (!out) return -1;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return -2;   // no CUDA device: fail loudly
+    if (device < 0 || device >= count) return -3;
+    fb_ctx *ctx = new fb_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return -4; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return -5; }
+    if (prop.major < 10) { delete ctx; return -6; }                            // sm_100a only
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -7; }
+    for (auto &e : ctx->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return -8; }
+    *out = ctx;
+    return 0;
+}
+
+int fb_ctx_destroy(fb_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void *p : {(void *)ctx->d_jk, (void *)ctx->d_ck, (void *)ctx->d_Y, (void *)ctx->d_tab, (void *)ctx->d_types,
+                    (void *)ctx->d_tile_panel, (void *)ctx->d_panel_t0, (void *)ctx->d_panel_nt, (void *)ctx->d_pair_code,
+                    (void *)ctx->d_a, (void *)ctx->d_sw, (void *)ctx->d_swV, (void *)ctx->d_kz, (void *)ctx->d_red,
+                    (void *)ctx->d_partial, (void *)ctx->d_H2, (void *)ctx->d_in, (void *)ctx->d_out,
+                    (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist})
+        if (p) cudaFree(p);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+const char *fb_last_error(fb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int fb_dht_setup(fb_ctx *ctx, int N, double Qmax, const double *host_j_nk, const double *host_coef,
+                 const double *host_Ycoef, double x_max)
+{
+    if (!ctx) return -1;
+    if (N < 1 || !host_j_nk || !host_coef || !(Qmax > 0)) FB_FAIL(-10, "fb_dht_setup: bad arguments");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->N = N;
+    ctx->NT = (N + 1 + 7) / 8;
+    ctx->NC = ctx->NT * 8;
+    ctx->Qmax = Qmax;
+    ctx->invQmax = 1.0 / Qmax;                    // hankel.py:189  k = 1. / self._Qmax
+    ctx->h_jk.assign(ctx->NC, 0.0);
+    ctx->h_ck.assign(ctx->NC, 0.0);
+    for (int k = 0; k < N; k++) { ctx->h_jk[k] = host_j_nk[k]; ctx->h_ck[k] = host_coef[k]; }
+    for (double **p : {&ctx->d_jk, &ctx->d_ck, &ctx->d_Y, &ctx->d_H2}) {
+        if (*p) FB_CUDA(cudaFree(*p));
+        *p = nullptr;
+    }
+    FB_CUDA(cudaMalloc(&ctx->d_jk, sizeof(double) * ctx->NC));
+    FB_CUDA(cudaMalloc(&ctx->d_ck, sizeof(double) * ctx->NC));
+    FB_CUDA(cudaMalloc(&ctx->d_H2, sizeof(double) * ctx->NC));
+    FB_CUDA(cudaMemset(ctx->d_H2, 0, sizeof(double) * ctx->NC));
+    FB_CUDA(cudaMemcpy(ctx->d_jk, ctx->h_jk.data(), sizeof(double) * ctx->NC, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_ck, ctx->h_ck.data(), sizeof(double) * ctx->NC, cudaMemcpyHostToDevice));
+    if (host_Ycoef) {
+        FB_CUDA(cudaMalloc(&ctx->d_Y, sizeof(double) * (size_t)N * N));
+        FB_CUDA(cudaMemcpy(ctx->d_Y, host_Ycoef, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice));
+    }
+
+    // panel decomposition of the NT x NT tile grid
+    const int NT = ctx->NT;
+    const int P = (NT + FB_PT - 1) / FB_PT;
+    ctx->P = P;
+    std::vector<int> panel_t0(P), panel_nt(P), tile_panel(NT), pair_code((size_t)P * P, -1);
+    {
+        const int base = NT / P, rem = NT % P;
+        int t = 0;
+        for (int p = 0; p < P; p++) {
+            panel_t0[p] = t;
+            panel_nt[p] = base + (p < rem ? 1 : 0);
+            for (int i = 0; i < panel_nt[p]; i++) tile_panel[t + i] = p;
+            t += panel_nt[p];
+        }
+    }
+    ctx->h_types.clear();
+    for (int pa = 0; pa < P; pa++)
+        for (int pb = pa + 1; pb < P; pb++) {
+            pair_code[(size_t)pa * P + pb] = (int)ctx->h_types.size();
+            ctx->h_types.push_back({FB_KIND_OFF, panel_t0[pa], panel_nt[pa], panel_t0[pb], panel_nt[pb]});
+        }
+    for (int p = 0; p < P; p += 2) {
+        const int id = (int)ctx->h_types.size();
+        FbGramType t{FB_KIND_DIAG2, panel_t0[p], panel_nt[p], 0, 0};
+        pair_code[(size_t)p * P + p] = (id << 1) | 0;
+        if (p + 1 < P) {
+            t.b_t0 = panel_t0[p + 1];
+            t.b_nt = panel_nt[p + 1];
+            pair_code[(size_t)(p + 1) * P + (p + 1)] = (id << 1) | 1;
+        }
+        ctx->h_types.push_back(t);
+    }
+    ctx->ntypes = (int)ctx->h_types.size();
+    for (void **p : {(void **)&ctx->d_types, (void **)&ctx->d_tile_panel, (void **)&ctx->d_panel_t0,
+                     (void **)&ctx->d_panel_nt, (void **)&ctx->d_pair_code}) {
+        if (*p) FB_CUDA(cudaFree(*p));
+        *p = nullptr;
+    }
+    FB_CUDA(cudaMalloc(&ctx->d_types, sizeof(FbGramType) * ctx->ntypes));
+    FB_CUDA(cudaMalloc(&ctx->d_tile_panel, sizeof(int) * NT));
+    FB_CUDA(cudaMalloc(&ctx->d_panel_t0, sizeof(int) * P));
+    FB_CUDA(cudaMalloc(&ctx->d_panel_nt, sizeof(int) * P));
+    FB_CUDA(cudaMalloc(&ctx->d_pair_code, sizeof(int) * P * P));
+    FB_CUDA(cudaMemcpy(ctx->d_types, ctx->h_types.data(), sizeof(FbGramType) * ctx->ntypes, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_tile_panel, tile_panel.data(), sizeof(int) * NT, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_panel_t0, panel_t0.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_panel_nt, panel_nt.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_pair_code, pair_code.data(), sizeof(int) * P * P, cudaMemcpyHostToDevice));
+
+    if (!(x_max > 0)) x_max = host_j_nk[N - 1];
+    return fb_build_j0_table(ctx, x_max);
+}
+
+static int map_dev_impl(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
+                        int w_stride, const int32_t *chan, int nchan, const fb_geometry *geom, int vis_model,
+                        double model_scale, const double *host_H2, int check_qbounds, double q_last, double *dev_M,
+                        double *dev_j, double *dev_H0, double *host_qminmax)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0) FB_FAIL(-11, "fb_map_visibilities: fb_dht_setup has not been called");
+    if (n < 0 || !geom || !dev_M || !dev_j || !dev_H0 || !host_qminmax) FB_FAIL(-12, "fb_map_visibilities: bad arguments");
+    if (nchan != 1 || chan != nullptr) FB_FAIL(-13, "fb_map_visibilities: multi-channel input must be split by the caller");
+    if (vis_model < 0 || vis_model > 2) FB_FAIL(-14, "fb_map_visibilities: vis_model must be 0, 1 or 2");
+    if (vis_model == FB_MODEL_DEBRIS) {
+        if (!host_H2) FB_FAIL(-15, "fb_map_visibilities: debris model needs H2");
+        std::vector<double> h2(ctx->NC, 0.0);
+        for (int k = 0; k < ctx->N; k++) h2[k] = host_H2[k];
+        FB_CUDA(cudaMemcpyAsync(ctx->d_H2, h2.data(), sizeof(double) * ctx->NC, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    FB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = fb_launch_prep(ctx, n, u, v, V, w, w_stride, geom, dev_H0, host_qminmax);
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (n > 0) {
+        // statistical_models.py:526: raise when the last collocation point is inside the data
+        if (check_qbounds && q_last < host_qminmax[1]) FB_FAIL(FB_E_QRANGE, "last collocation point is at a shorter baseline than the longest deprojected baseline");
+        // make sure the J0 table reaches the largest argument a_max * j_{N-1}
+        const double xneed = host_qminmax[1] * ctx->invQmax * ctx->h_jk[ctx->N - 1];
+        if (xneed * 4.0 + 2.0 > (double)ctx->tab_rows) {
+            rc = fb_build_j0_table(ctx, xneed * 1.05);
+            if (rc) return rc;
+        }
+    }
+    rc = fb_launch_gram(ctx, n, vis_model, model_scale, dev_M, dev_j);
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float t01 = 0, t12 = 0, t23 = 0;
+    cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[3]);
+    ctx->timing[0] = t01; ctx->timing[1] = t12; ctx->timing[2] = t23; ctx->timing[3] = 0;
+    return 0;
+}
+
+int fb_map_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v, const double *dev_V_reim,
+                            const double *dev_w, int w_stride, const int32_t *dev_chan, int nchan, const fb_geometry *geom,
+                            int vis_model, double model_scale, const double *host_H2, int check_qbounds, double q_last,
+                            double *dev_M, double *dev_j, double *dev_H0, double *host_qminmax)
+{
+    if (!ctx) return -1;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    return map_dev_impl(ctx, n, dev_u, dev_v, dev_V_reim, dev_w, w_stride, dev_chan, nchan, geom, vis_model, model_scale,
+                        host_H2, check_qbounds, q_last, dev_M, dev_j, dev_H0, host_qminmax);
+}
+
+int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const double *host_v, const double *host_V_reim,
+                             const double *host_w, int w_stride, const int32_t *host_chan, int nchan, const fb_geometry *geom,
+                             int vis_model, double model_scale, const double *host_H2, int check_qbounds, double q_last,
+                             double *host_M, double *host_j, double *host_H0, double *host_qminmax)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0) FB_FAIL(-11, "fb_map_visibilities: fb_dht_setup has not been called");
+    if (host_chan != nullptr || nchan != 1) FB_FAIL(-13, "fb_map_visibilities: multi-channel input must be split by the caller");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t nw = w_stride ? n : 1;
+    const int64_t need = 4 * n + nw + 8;
+    if (need > ctx->in_cap) {
+        if (ctx->d_in) FB_CUDA(cudaFree(ctx->d_in));
+        ctx->d_in = nullptr;
+        FB_CUDA(cudaMalloc(&ctx->d_in, sizeof(double) * need));
+        ctx->in_cap = need;
+    }
+    const size_t N = ctx->N, nout = N * N + N + 1;
+    if (nout > ctx->out_cap) {
+        if (ctx->d_out) FB_CUDA(cudaFree(ctx->d_out));
+        ctx->d_out = nullptr;
+        FB_CUDA(cudaMalloc(&ctx->d_out, sizeof(double) * nout));
+        ctx->out_cap = nout;
+    }
+    double *du = ctx->d_in, *dv = du + n, *dV = dv + n, *dw = dV + 2 * n;
+    FB_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(du, host_u, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(dv, host_v, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(dV, host_V_reim, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(dw, host_w, sizeof(double) * nw, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    double *dM = ctx->d_out, *dj = dM + N * N, *dH0 = dj + N;
+    int rc = map_dev_impl(ctx, n, du, dv, dV, dw, w_stride, nullptr, 1, geom, vis_model, model_scale, host_H2, check_qbounds,
+                          q_last, dM, dj, dH0, host_qminmax);
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(host_M, dM, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(host_j, dj, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(host_H0, dH0, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float h2d = 0, d2h = 0;
+    cudaEventElapsedTime(&h2d, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&d2h, ctx->ev[6], ctx->ev[7]);
+    ctx->timing[3] = h2d + d2h;
+    return 0;
+}
+
+int fb_last_map_timing(fb_ctx *ctx, double *out4)
+{
+    if (!ctx || !out4) return -1;
+    for (int i = 0; i < 4; i++) out4[i] = ctx->timing[i];
+    return 0;
+}
+
+int fb_debug_prepped(fb_ctx *ctx, int64_t n, double *host_q, double *host_kz, double *host_Vre, uint32_t *host_perm)
+{
+    if (!ctx) return -1;
+    if (n > ctx->last_n) FB_FAIL(-20, "fb_debug_prepped: n exceeds the last mapped size");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<double> a(n), sw(n), swV(n);
+    FB_CUDA(cudaMemcpy(a.data(), ctx->d_a, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    FB_CUDA(cudaMemcpy(sw.data(), ctx->d_sw, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    FB_CUDA(cudaMemcpy(swV.data(), ctx->d_swV, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    FB_CUDA(cudaMemcpy(host_kz, ctx->d_kz, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (host_perm) FB_CUDA(cudaMemcpy(host_perm, ctx->d_perm, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    // the pre-pass stores a = q * (1/Qmax) and sqrt(w) * Re V; hand back a (callers compare a against
+    // np.hypot(u', v') * (1/Qmax)) and Re V recovered by the division (exact only to rounding)
+    for (int64_t i = 0; i < n; i++) { host_q[i] = a[i]; host_Vre[i] = sw[i] != 0.0 ? swV[i] / sw[i] : 0.0; }
+    return 0;
+}
+
+}  // extern "C"

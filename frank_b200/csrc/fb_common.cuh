@@ -1,0 +1,97 @@
+// Shared declarations for libfrankb200 (sm_100a).  Internal; the public surface is include/frankb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/frankb200.h"
+
+// ---- geometry of the fused J0 + Gram kernel -------------------------------------------------
+// One tile = TV visibilities.  The design-matrix tile G[mode][vis] lives in shared memory with a
+// leading dimension LDV = TV + 4 doubles so that the m8n8k4 fragment pattern (8 modes x 4 vis)
+// touches all 32 banks exactly once per half-warp.
+constexpr int FB_TV = 64;
+constexpr int FB_LDV = FB_TV + 4;
+constexpr int FB_PT = 19;              // max 8-column tiles per panel (152 modes)
+constexpr int FB_PCOLS = FB_PT * 8;
+constexpr int FB_DH = 10;              // skew offsets per triangle: floor(PT/2) + 1
+constexpr int FB_PSZ = 2 * FB_PT * FB_DH * 64;   // doubles per work-item partial (>= PT*PT*64)
+constexpr int FB_GRAM_THREADS = 512;
+constexpr int FB_J0_ROWLEN = 10;       // Taylor degree 9, rows centred on multiples of 1/4
+
+constexpr int FB_KIND_OFF = 0;         // rectangular block  panel A x panel B
+constexpr int FB_KIND_DIAG2 = 1;       // upper triangles of panel A and of panel B
+
+struct FbGramType {
+    int kind;
+    int a_t0, a_nt;   // first tile / number of tiles of panel A
+    int b_t0, b_nt;   // panel B (b_nt == 0 when a DIAG2 item carries a single triangle)
+};
+
+struct fb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // DHT
+    int N = 0, NT = 0, NC = 0;
+    double Qmax = 0, invQmax = 0;
+    std::vector<double> h_jk, h_ck;
+    double *d_jk = nullptr, *d_ck = nullptr, *d_Y = nullptr;
+    // J0 table
+    double2 *d_tab = nullptr;
+    int tab_rows = 0;
+    // panel decomposition
+    int P = 0, ntypes = 0;
+    std::vector<FbGramType> h_types;
+    FbGramType *d_types = nullptr;
+    int *d_tile_panel = nullptr, *d_panel_t0 = nullptr, *d_panel_nt = nullptr, *d_pair_code = nullptr;
+    // workspaces
+    int64_t cap = 0;
+    double *d_a = nullptr, *d_sw = nullptr, *d_swV = nullptr, *d_kz = nullptr;   // sorted, padded, SoA
+    double *d_rec = nullptr;       // unsorted records (a, sqrt w, sqrt w * Re V, kz), 32 B each
+    uint64_t *d_items = nullptr;   // 2 x cap sort buffers of (key << 32 | index)
+    uint32_t *d_perm = nullptr;    // sorted position -> original index
+    uint32_t *d_hist = nullptr;
+    size_t hist_cap = 0;
+    double *d_red = nullptr;     // pre-pass block reductions
+    int red_cap = 0;
+    double *d_partial = nullptr;
+    size_t partial_cap = 0;
+    double *d_H2 = nullptr;
+    // staging for the host entry point
+    double *d_in = nullptr;
+    int64_t in_cap = 0;
+    double *d_out = nullptr;
+    size_t out_cap = 0;
+    cudaEvent_t ev[8] = {};
+    double timing[4] = {0, 0, 0, 0};
+    int num_sms = 148;
+    int64_t last_n = 0;
+};
+
+#define FB_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            char buf__[512];                                                                 \
+            snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #call,                    \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                           \
+            ctx->err = buf__;                                                                \
+            return -(int)e__ - 1000;                                                         \
+        }                                                                                    \
+    } while (0)
+
+#define FB_FAIL(code, msg)      \
+    do {                        \
+        ctx->err = (msg);       \
+        return (code);          \
+    } while (0)
+
+// kernels / launchers implemented in the .cu files
+int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
+                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax);
+int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, double *dev_M, double *dev_j);
+int fb_build_j0_table(fb_ctx *ctx, double x_max);
+int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max);

@@ -1,0 +1,240 @@
+"""Statistical models of the fit: visibility mapping (data -> normal equations) and the
+Gaussian / log-normal posterior solves.
+
+API mirror of frank.statistical_models (frank/statistical_models.py).  The arithmetic runs in
+libfrankb200 (hand-written sm_100a CUDA, reached through ctypes); NumPy only carries the O(N^2)
+results.  There is no CPU path: constructing these objects without a CUDA device raises.
+"""
+import logging
+
+import numpy as np
+
+from frank_b200 import _lib
+from frank_b200.constants import rad_to_arcsec, deg_to_rad
+
+__all__ = ['VisibilityMapping']
+
+
+def _is_cuda_tensor(x):
+    return hasattr(x, 'data_ptr') and hasattr(x, 'is_cuda') and x.is_cuda
+
+
+class VisibilityMapping(object):
+    r"""Mapping between the visibility plane and the brightness at the DHT collocation points.
+
+    Same constructor and results as frank.statistical_models.VisibilityMapping
+    (frank/statistical_models.py:29-107).  ``block_data`` / ``block_size`` are accepted for
+    compatibility; the GPU kernel tiles the visibility axis itself (64 visibilities per
+    shared-memory tile), so they do not change the result beyond round-off.
+
+    Parameters
+    ----------
+    DHT : DiscreteHankelTransform
+    geometry : SourceGeometry
+    vis_model : {'opt_thick', 'opt_thin', 'debris'}
+    scale_height : callable H(R) in arcsec, required for 'debris'
+    block_data, block_size : ignored (see above)
+    check_qbounds : bool
+        Raise when the data extend beyond the last collocation point.
+    verbose : bool
+    device : int, optional
+        CUDA device ordinal (default: LOCAL_RANK, else 0).
+    """
+
+    def __init__(self, DHT, geometry, vis_model='opt_thick', scale_height=None, block_data=True,
+                 block_size=10 ** 5, check_qbounds=True, verbose=True, device=None):
+        models = ['opt_thick', 'opt_thin', 'debris']
+        if vis_model not in models:
+            raise ValueError(f"vis_model must be one of {models}")
+        self._vis_model = vis_model
+        self.check_qbounds = check_qbounds
+        self._verbose = verbose
+        self._chunking = block_data
+        self._chunk_size = block_size
+        self._DHT = DHT
+        self._geometry = geometry
+        self._device = device
+        self._scale_height = None
+        self._H2 = None
+        if vis_model == 'debris':
+            if scale_height is None:
+                raise ValueError('You requested a model with a non-zero scale height'
+                                 ' but did not specify H(R) (scale_height=None)')
+            self._scale_height = scale_height(self.r)
+            self._H2 = 0.5 * (2 * np.pi * self._scale_height / rad_to_arcsec) ** 2     # :101-102
+        if verbose:
+            logging.info('  Visibility model: %s', vis_model)
+        self._timing = None
+
+    # -- the hot path ----------------------------------------------------------------------------
+    def _context(self):
+        ctx = _lib.get_context(self._device)
+        ctx.dht_setup(self._DHT)
+        return ctx
+
+    def _model_scale(self, geometry=None):
+        if self._vis_model == 'opt_thick':
+            g = self._geometry if geometry is None else geometry
+            return float(np.cos(g.inc * deg_to_rad))                                   # :486-490
+        return 1.0
+
+    def _map_one(self, ctx, u, v, V, w, w_stride):
+        """One channel through fb_map_visibilities_{host,dev}: returns M, j, H0, qmin, qmax."""
+        import torch
+        N = self.size
+        n = int(u.shape[0])
+        geom = self._geometry.device_scalars()
+        q_last = float(self.q[-1])
+        on_device = _is_cuda_tensor(u)
+        if on_device:
+            dev = u.device
+            out = torch.empty(N * N + N + 1, dtype=torch.float64, device=dev)
+            M, j, H0 = out[:N * N], out[N * N:N * N + N], out[N * N + N:]
+            Vr = torch.view_as_real(V) if V.is_complex() else torch.stack([V, torch.zeros_like(V)], dim=-1)
+            Vr = Vr.contiguous()
+            rc, qmin, qmax = ctx.map_visibilities(n, u.contiguous(), v.contiguous(), Vr, w, w_stride, geom,
+                                                  _lib.MODEL_CODE[self._vis_model], self._model_scale(), self._H2,
+                                                  self.check_qbounds, q_last, M, j, H0, host=False)
+            if rc == 0:
+                host = out.cpu().numpy()
+        else:
+            host = np.empty(N * N + N + 1)
+            M, j, H0 = host[:N * N], host[N * N:N * N + N], host[N * N + N:]
+            rc, qmin, qmax = ctx.map_visibilities(n, u, v, V, w, w_stride, geom, _lib.MODEL_CODE[self._vis_model],
+                                                  self._model_scale(), self._H2, self.check_qbounds, q_last,
+                                                  M, j, H0, host=True)
+        self._timing = ctx.last_map_timing()
+        if rc == _lib.FB_E_QRANGE:
+            self._raise_qrange(qmax)
+        return host[:N * N].reshape(N, N).copy(), host[N * N:N * N + N].copy(), float(host[N * N + N]), qmin, qmax
+
+    def map_visibilities(self, u, v, V, weights, frequencies=None, geometry=None):
+        r"""Compute M = H^T w H, j = H^T w V and the null likelihood H0 from the visibilities
+        (frank/statistical_models.py:109-237).
+
+        u, v, V, weights may be NumPy arrays (host memory; copied to the GPU inside the call) or
+        torch CUDA tensors (used in place).  Returns the reference's dict:
+        ``mult_freq, channels, M, j, null_likelihood, hash``.
+
+        As in the reference the deprojection always uses the geometry given at construction;
+        a `geometry` argument only lands in the returned hash (statistical_models.py:158-165, 227).
+        """
+        if geometry is None:
+            geometry = self._geometry
+        if self._verbose:
+            logging.info('    Building visibility matrices M and j')
+        ctx = self._context()
+        on_device = _is_cuda_tensor(u)
+        if on_device:
+            import torch
+            w_stride = 1
+            if not hasattr(weights, 'data_ptr'):
+                weights = torch.full((1,), float(weights), dtype=torch.float64, device=u.device)
+                w_stride = 0
+            elif weights.numel() == 1:
+                weights = weights.reshape(1).to(torch.float64)
+                w_stride = 0
+            V = V if V.is_complex() else V.to(torch.float64)
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64)
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            V = np.ascontiguousarray(V, dtype=np.complex128)
+            weights = np.asarray(weights, dtype=np.float64)
+            w_stride = 1
+            if weights.ndim == 0 or weights.size == 1:
+                weights = weights.reshape(1).copy()
+                w_stride = 0
+            else:
+                weights = np.ascontiguousarray(weights)
+
+        multi_freq = frequencies is not None
+        if not multi_freq:
+            M, j, H0, qmin, qmax = self._map_one(ctx, u, v, V, weights, w_stride)
+            self._warn_qmin(qmin)
+            return {'mult_freq': False, 'channels': None, 'M': M, 'j': j, 'null_likelihood': H0,
+                    'hash': [False, self._DHT, geometry, self._vis_model, self._scale_height]}
+
+        # multi-frequency: one Gram per channel (statistical_models.py:180-214); H0 over all data
+        if on_device:
+            import torch
+            channels = torch.unique(frequencies)
+            sel = [frequencies == f for f in channels]
+            channels = channels.cpu().numpy()
+        else:
+            frequencies = np.asarray(frequencies)
+            channels = np.unique(frequencies)
+            sel = [frequencies == f for f in channels]
+        N = self.size
+        Ms, js, H0 = np.zeros([len(channels), N, N]), np.zeros([len(channels), N]), 0.0
+        qlo, qhi = np.inf, -np.inf
+        for c, idx in enumerate(sel):
+            wc = weights if w_stride == 0 else weights[idx]
+            Ms[c], js[c], h0c, qmin, qmax = self._map_one(ctx, u[idx], v[idx], V[idx], wc, w_stride)
+            H0 += h0c
+            qlo, qhi = min(qlo, qmin), max(qhi, qmax)
+        self._warn_qmin(qlo)
+        return {'mult_freq': True, 'channels': channels, 'M': Ms, 'j': js, 'null_likelihood': H0,
+                'hash': [True, self._DHT, geometry, self._vis_model, self._scale_height]}
+
+    def _warn_qmin(self, qmin):
+        if self.check_qbounds and self.q[0] < qmin:                                     # :519-525
+            logging.warning(r"WARNING: First collocation point, q[0] = {:.3e} \lambda,"
+                            " is at a baseline shorter than the"
+                            " shortest deprojected baseline in the dataset,"
+                            r" min(uv) = {:.3e} \lambda. For q[0] << min(uv),"
+                            " the fit's total flux may be biased"
+                            " low.".format(self.q[0], qmin))
+
+    def _raise_qrange(self, qmax):
+        raise ValueError(r"ERROR: Last collocation point, {:.3e} \lambda, is at"                # :526-535
+                         " a shorter baseline than the longest deprojected"
+                         r" baseline in the dataset, {:.3e} \lambda. Please"
+                         " increase N (this is `hyperparameters: n` if you're using a parameter"
+                         " file). Or if you'd like to fit to shorter maximum baseline,"
+                         " cut the (u, v) distribution before fitting"
+                         " (`modify_data: baseline_range` in the"
+                         " parameter file).".format(self.q[-1], qmax))
+
+    @property
+    def last_timing(self):
+        """CUDA-event timings (ms) of the most recent map_visibilities call."""
+        return self._timing
+
+    def check_hash(self, hash, multi_freq=False, geometry=None):
+        """Compatibility test of mapped visibilities with this mapping (statistical_models.py:239-276)."""
+        if geometry is None:
+            geometry = self._geometry
+        same = (multi_freq == hash[0]
+                and all(getattr(self._DHT, k) == getattr(hash[1], k) for k in ('Rmax', 'size', 'order'))
+                and all(getattr(geometry, k) == getattr(hash[2], k) for k in ('inc', 'PA', 'dRA', 'dDec'))
+                and self._vis_model == hash[3])
+        if not same:
+            return False
+        if self._scale_height is None:
+            return hash[4] is None
+        return False if hash[4] is None else bool(np.all(self._scale_height == hash[4]))
+
+    # -- small host-side helpers kept for API compatibility -----------------------------------
+    def transform(self, f, q=None, direction='forward'):
+        if direction == 'backward' and q is not None:
+            q = q / rad_to_arcsec
+        return self._DHT.transform(f, q, direction)
+
+    def DHT_coefficients(self, direction='forward'):
+        return self._DHT.coefficients(direction=direction)
+
+    def interpolate(self, f, r, space='Real'):
+        if space == 'Real':
+            r = r / rad_to_arcsec
+        r = np.array(r)
+        return self._DHT.interpolate(f, r.reshape(-1), space).reshape(*r.shape)
+
+    r = property(lambda self: self._DHT.r * rad_to_arcsec, doc="Radius points, arcsec")
+    Rmax = property(lambda self: self._DHT.Rmax * rad_to_arcsec, doc="Maximum radius, arcsec")
+    q = property(lambda self: self._DHT.q, doc="Frequency points, lambda")
+    Qmax = property(lambda self: self._DHT.Qmax, doc="Maximum frequency, lambda")
+    size = property(lambda self: self._DHT.size, doc="Number of points in reconstruction")
+
+    @property
+    def scale_height(self):
+        return self._scale_height

@@ -1,0 +1,107 @@
+/*
+ * frankb200.h -- C ABI of libfrankb200.so: B200 (sm_100a) implementation of discsim/frank's
+ * visibility -> Gaussian-process normal-equations path and of the dense FP64 solves that consume it.
+ *
+ * Every entry point names the reference interface it replaces (paths are into discsim/frank 1.2.3).
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function returns an int status
+ *   0            success
+ *   < 0          CUDA / argument error (text from fb_last_error)
+ *   FB_E_QRANGE  data reach beyond the last collocation point (reference raises ValueError,
+ *                frank/statistical_models.py:526-535)
+ *   FB_E_NOTPD   Cholesky hit a non-positive pivot (reference: numpy.linalg.LinAlgError -> SVD fallback,
+ *                frank/statistical_models.py:747)
+ *   FB_E_BADP    non-positive / NaN power spectrum (reference ValueError, statistical_models.py:688-698)
+ * Nothing throws or aborts across the ABI.  A context is bound to one device; calls on one context are
+ * serialised on its stream and are complete (host-visible) when the function returns unless stated.
+ * "dev" pointers are device memory on the context's device, "host" pointers are host memory.
+ */
+#ifndef FRANKB200_H
+#define FRANKB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_E_QRANGE 1
+#define FB_E_NOTPD 2
+#define FB_E_BADP 3
+
+#define FB_MODEL_OPT_THICK 0
+#define FB_MODEL_OPT_THIN 1
+#define FB_MODEL_DEBRIS 2
+
+typedef struct fb_ctx fb_ctx;
+
+/* Geometry scalars exactly as the reference forms them on the host before touching the arrays
+ * (frank/geometry.py:69-70, 111-115): a_ra = dRA * 2pi/rad_to_arcsec, a_dec likewise,
+ * cos/sin of PA*deg_to_rad and inc*deg_to_rad. */
+typedef struct fb_geometry {
+    double a_ra, a_dec;
+    double cos_pa, sin_pa;
+    double cos_inc, sin_inc;
+} fb_geometry;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int fb_ctx_create(fb_ctx **ctx, int device);
+int fb_ctx_destroy(fb_ctx *ctx);
+const char *fb_last_error(fb_ctx *ctx);
+int fb_version(void);
+
+/* ---- DiscreteHankelTransform tables (frank/hankel.py:55-93) ---------------------------------
+ * Host-side tables are O(N^2) setup and are passed in; the library builds the device-side J0
+ * interpolation table covering arguments up to x_max (= a_max * j_nk[N-1]).
+ *   j_nk[N]     first N zeros of J0                (hankel.py:72-73)
+ *   coef[N]     norm * scale_factor = 1/(pi Qmax^2) / J1(j_nk)^2   (hankel.py:188, 201)
+ *   Qmax        j_{N+1} / (2 pi Rmax)              (hankel.py:75)
+ *   Ycoef[N*N]  coefficients(q=None) = 0.5 j_{N+1} norm Ykm, row-major (hankel.py:198-199), may be NULL
+ *               when only the mapping is used. */
+int fb_dht_setup(fb_ctx *ctx, int N, double Qmax, const double *host_j_nk, const double *host_coef,
+                 const double *host_Ycoef, double x_max);
+
+/* ---- VisibilityMapping.map_visibilities (frank/statistical_models.py:109-237) -----------------
+ * Replaces: SourceGeometry.apply_correction (geometry.py:202-236), q = hypot (statistical_models.py:166),
+ * _check_uv_range (:512-535), the chunk loop X = H(q); M += (X^T w) X; j += (X^T w) V (:192-214) and
+ * H0 (:218).
+ *   n            visibilities on this rank
+ *   u, v         [n]      baselines / lambda
+ *   V_reim       [2n]     complex visibilities, interleaved (re, im)  (numpy complex128 layout)
+ *   w, w_stride  weights; w_stride = 1 for an array, 0 for a broadcast scalar (radial_fitters.py:544)
+ *   chan, nchan  optional int32 channel index per visibility in [0, nchan) (np.unique order,
+ *                statistical_models.py:180-189); NULL / 1 for a single channel
+ *   kz2_H2       debris model only: H2[N] = 0.5 (2 pi h(r)/rad_to_arcsec)^2 (statistical_models.py:101-102)
+ *   model_scale  cos(inc*deg_to_rad) for opt_thick, 1 otherwise (statistical_models.py:486-493)
+ *   check_qbounds nonzero: return FB_E_QRANGE (outputs untouched except qminmax) when q_last < max(q)
+ *   q_last       last collocation frequency q[N-1]
+ * Outputs (dev or host according to the entry point):
+ *   M [nchan*N*N] row-major, j [nchan*N], H0 [1] null likelihood, qminmax [2] = min(q), max(q).
+ * In a multi-GPU job each rank passes its slice and sums (M, j, H0) / min-maxes qminmax across ranks
+ * afterwards (the sums are over independent visibilities). */
+int fb_map_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v,
+                            const double *dev_V_reim, const double *dev_w, int w_stride,
+                            const int32_t *dev_chan, int nchan, const fb_geometry *geom, int vis_model,
+                            double model_scale, const double *host_H2, int check_qbounds, double q_last,
+                            double *dev_M, double *dev_j, double *dev_H0, double *host_qminmax);
+
+int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const double *host_v,
+                             const double *host_V_reim, const double *host_w, int w_stride,
+                             const int32_t *host_chan, int nchan, const fb_geometry *geom, int vis_model,
+                             double model_scale, const double *host_H2, int check_qbounds, double q_last,
+                             double *host_M, double *host_j, double *host_H0, double *host_qminmax);
+
+/* Timing of the most recent map call, milliseconds by CUDA events on the context's stream:
+ * out[0] prepass (deproject / phase shift / hypot / H0 / min-max), out[1] J0+Gram kernel,
+ * out[2] split-K reduction + scaling, out[3] host<->device copies (host entry point only). */
+int fb_last_map_timing(fb_ctx *ctx, double *out4);
+
+/* Pre-passed visibilities of the most recent map call in the (baseline-sorted) order the Gram kernel reads
+ * them, for parity tests of the geometry pre-pass (geometry.py:202-236): a = q * (1/Qmax) [n], kz [n],
+ * Re V' [n] and perm [n] (sorted position -> index into the caller's arrays), device -> host. */
+int fb_debug_prepped(fb_ctx *ctx, int64_t n, double *host_a, double *host_kz, double *host_Vre, uint32_t *host_perm);
+
+/* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]). */
+int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
