@@ -18,6 +18,7 @@
 #include "fb_common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -31,6 +32,7 @@ struct GramArgs {
     const FbGramType *types;
     const double *H2;
     double *partial;
+    int debug_mode;   // 0 normal | 1 skip the DMMA phase | 2 skip J0 evaluation (profiling aid, FB_GRAM_DEBUG)
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
@@ -63,30 +65,142 @@ __device__ __forceinline__ double j0_tab(double x, const double2 *__restrict__ t
 
 __device__ __forceinline__ int clamp5(int x) { return x < 0 ? 0 : (x > 5 ? 5 : x); }
 
+constexpr int GT = FB_TV;              // visibilities per tile (64)
+constexpr int GLD = FB_LDV;            // 68 = 4 mod 16: conflict-free m8n8k4 fragments
+constexpr int GKS = GT / 4;            // k-steps per tile
+constexpr int GCOLS = 2 * FB_PCOLS;    // columns held per tile (panel A | panel B)
+
+// shared-memory carve-up (doubles unless noted)
+constexpr int SM_G = 0;                                   // [GCOLS][GLD]        design-matrix tile
+constexpr int SM_JK = SM_G + GCOLS * GLD;                 // [GCOLS]             j_k (>= 0), -1 data column, -2 padding
+constexpr int SM_H2 = SM_JK + GCOLS;                      // [GCOLS]             debris H2_k
+constexpr int SM_ROW = SM_H2 + GCOLS;                     // [GCOLS][10]         staged J0 table rows
+constexpr int SM_ROWM = SM_ROW + GCOLS * FB_J0_ROWLEN;    // [GCOLS] int         staged row index
+constexpr int SM_CFG = SM_ROWM + GCOLS / 2;                   // [16 warps][8] int  per-warp register-block description
+constexpr int SM_DOUBLES = SM_CFG + 16 * 8 / 2;
+constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * SM_DOUBLES;
+
+// rectangular register block: acc[r][c] += G_A[r0+r]^T G_B[c0+c] over one tile
+template <int NR, int NC>
+__device__ __forceinline__ void mma_off(double (&acc)[5][5][2], const double *__restrict__ ap, const double *__restrict__ bp)
+{
+#pragma unroll 2
+    for (int ks = 0; ks < GKS; ks++) {
+        double af[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) af[r] = ap[r * 8 * GLD + ks * 4];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const double b = bp[c * 8 * GLD + ks * 4];
+#pragma unroll
+            for (int r = 0; r < NR; r++) dmma(acc[r][c], af[r], b);
+        }
+    }
+}
+
+// skewed strip of a triangle: acc[r][d] += G[r0+r]^T G[(r0+r + d0+d) mod n] over one tile;
+// boff[s] = shared-memory offset of tile column (r0 + d0 + s) mod n
+template <int NR, int ND>
+__device__ __forceinline__ void mma_diag(double (&acc)[5][5][2], const double *__restrict__ ap, const double *__restrict__ tp,
+                                         int cbase, int nmod)
+{
+#pragma unroll 2
+    for (int ks = 0; ks < GKS; ks++) {
+        double af[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) af[r] = ap[r * 8 * GLD + ks * 4];
+#pragma unroll
+        for (int s = 0; s < NR + ND - 1; s++) {
+            int ct = cbase + s;
+            ct = ct >= nmod ? ct - nmod : ct;
+            const double b = tp[ct * 8 * GLD + ks * 4];
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                const int d = s - r;
+                if (d >= 0 && d < ND) dmma(acc[r][d], af[r], b);
+            }
+        }
+    }
+}
+
+template <int NR>
+__device__ __forceinline__ void mma_off_nc(double (&acc)[5][5][2], const double *ap, const double *bp, int nc)
+{
+    switch (nc) {
+        case 5: mma_off<NR, 5>(acc, ap, bp); break;
+        case 4: mma_off<NR, 4>(acc, ap, bp); break;
+        case 3: mma_off<NR, 3>(acc, ap, bp); break;
+        case 2: mma_off<NR, 2>(acc, ap, bp); break;
+        case 1: mma_off<NR, 1>(acc, ap, bp); break;
+        default: break;
+    }
+}
+template <int NR>
+__device__ __forceinline__ void mma_diag_nd(double (&acc)[5][5][2], const double *ap, const double *tp, int cbase, int nmod, int nd)
+{
+    switch (nd) {
+        case 5: mma_diag<NR, 5>(acc, ap, tp, cbase, nmod); break;
+        case 4: mma_diag<NR, 4>(acc, ap, tp, cbase, nmod); break;
+        case 3: mma_diag<NR, 3>(acc, ap, tp, cbase, nmod); break;
+        case 2: mma_diag<NR, 2>(acc, ap, tp, cbase, nmod); break;
+        case 1: mma_diag<NR, 1>(acc, ap, tp, cbase, nmod); break;
+        default: break;
+    }
+}
+
+// Evaluate the staged polynomial for two visibilities of one column (shared coefficient loads).
+__device__ __forceinline__ void horner2(const double2 *__restrict__ rb, double t0, double t1, double &g0, double &g1)
+{
+    double2 c = rb[4];
+    g0 = fma(c.y, t0, c.x);           g1 = fma(c.y, t1, c.x);
+    c = rb[3];
+    g0 = fma(g0, t0, c.y);            g1 = fma(g1, t1, c.y);
+    g0 = fma(g0, t0, c.x);            g1 = fma(g1, t1, c.x);
+    c = rb[2];
+    g0 = fma(g0, t0, c.y);            g1 = fma(g1, t1, c.y);
+    g0 = fma(g0, t0, c.x);            g1 = fma(g1, t1, c.x);
+    c = rb[1];
+    g0 = fma(g0, t0, c.y);            g1 = fma(g1, t1, c.y);
+    g0 = fma(g0, t0, c.x);            g1 = fma(g1, t1, c.x);
+    c = rb[0];
+    g0 = fma(g0, t0, c.y);            g1 = fma(g1, t1, c.y);
+    g0 = fma(g0, t0, c.x);            g1 = fma(g1, t1, c.x);
+}
+
+// The persistent J0 + Gram kernel: per tile of 64 visibilities
+//   (1) 304 threads stage, per column, the J0 table row the tile's first visibility needs (the visibilities
+//       are sorted by baseline, so nearly always every lane needs that same row);
+//   (2) all 16 warps evaluate J0 for their columns (two visibilities per lane share the coefficient loads)
+//       into G[column][vis] in shared memory;
+//   (3) all 16 warps run the DMMAs of their register block over the tile.
 template <bool DEBRIS>
 __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(GramArgs p)
 {
     extern __shared__ double smem[];
-    double *G = smem;                                  // [2*PCOLS][LDV]
-    double *col_jk = G + 2 * FB_PCOLS * FB_LDV;        // [2*PCOLS]  j_k, or -1 (data column), -2 (padding)
-    double *col_h2 = col_jk + 2 * FB_PCOLS;            // [2*PCOLS]  debris H2_k
+    double *G = smem + SM_G;
+    double *col_jk = smem + SM_JK;
+    double *col_h2 = smem + SM_H2;
+    double *rowbuf = smem + SM_ROW;
+    int *rowm = reinterpret_cast<int *>(smem + SM_ROWM);
+    int *cfg = reinterpret_cast<int *>(smem + SM_CFG);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int smsp = warp & 3, slot = warp >> 2;
     const int last_row = p.tab_rows - 1;
-    const int frag = (lane >> 2) * FB_LDV + (lane & 3);   // fragment offset inside an 8-mode x 4-vis brick
+    const double MAGIC = 6755399441055744.0;
 
     for (int item = blockIdx.x; item < p.ntypes * p.C; item += gridDim.x) {
         const int type = item % p.ntypes, chunk = item / p.ntypes;
         const FbGramType ty = p.types[type];
-        const long long t0 = (p.n_tiles * chunk) / p.C, t1 = (p.n_tiles * (chunk + 1)) / p.C;
+        const int t0 = (int)((p.n_tiles * chunk) / p.C), t1 = (int)((p.n_tiles * (chunk + 1)) / p.C);
         const int ncolA = ty.a_nt * 8, ncol = (ty.a_nt + ty.b_nt) * 8;
 
         __syncthreads();
         for (int lc = tid; lc < ncol; lc += FB_GRAM_THREADS) {
-            int g = lc < ncolA ? ty.a_t0 * 8 + lc : ty.b_t0 * 8 + (lc - ncolA);
-            col_jk[lc] = g < p.N ? p.jk[g] : (g == p.N ? -1.0 : -2.0);
-            if (DEBRIS) col_h2[lc] = g < p.N ? p.H2[g] : 0.0;
+            const bool inA = lc < ncolA;
+            const int g = inA ? ty.a_t0 * 8 + lc : ty.b_t0 * 8 + (lc - ncolA);
+            const int sc = inA ? lc : FB_PCOLS + (lc - ncolA);
+            col_jk[sc] = g < p.N ? p.jk[g] : (g == p.N ? -1.0 : -2.0);
+            if (DEBRIS) col_h2[sc] = g < p.N ? p.H2[g] : 0.0;
         }
 
         double acc[5][5][2];
@@ -95,128 +209,140 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(GramArgs p)
 #pragma unroll
             for (int c = 0; c < 5; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
 
-        // warp's register block
-        int r0, c0, nr, nc, nmod = 1, base_cols = 0;
-        if (ty.kind == FB_KIND_OFF) {
-            r0 = 5 * slot;
-            c0 = 5 * ((slot + smsp) & 3);
-            nr = clamp5(ty.a_nt - r0);
-            nc = clamp5(ty.b_nt - c0);
-        } else {
-            const int tri = slot >> 1;
-            nmod = tri ? ty.b_nt : ty.a_nt;
-            base_cols = tri ? FB_PCOLS : 0;
-            r0 = 5 * ((smsp + slot) & 3);
-            c0 = 5 * (slot & 1);                       // first skew offset d
-            nr = clamp5(nmod - r0);
-            nc = nmod > 0 ? clamp5(nmod / 2 + 1 - c0) : 0;
-            if (nmod == 0) nmod = 1;
-        }
-        __syncthreads();
-
-        for (long long tile = t0; tile < t1; ++tile) {
-            // ---------------- phase 1: design-matrix tile into shared memory ----------------------
-            const long long v0 = tile * FB_TV;
-            const double a0 = p.a[v0 + lane], a1 = p.a[v0 + lane + 32];
-            const double s0 = p.sw[v0 + lane], s1 = p.sw[v0 + lane + 32];
-            double k0 = 0.0, k1 = 0.0;
-            if (DEBRIS) {
-                k0 = p.kz[v0 + lane]; k1 = p.kz[v0 + lane + 32];
-                k0 = -k0 * k0; k1 = -k1 * k1;
-            }
-            for (int lc = warp; lc < ncol; lc += FB_GRAM_THREADS / 32) {
-                const double jk = col_jk[lc];
-                const int sc = lc < ncolA ? lc : FB_PCOLS + (lc - ncolA);
-                double g0, g1;
-                if (jk >= 0.0) {
-                    g0 = j0_tab(__dmul_rn(a0, jk), p.tab, last_row);
-                    g1 = j0_tab(__dmul_rn(a1, jk), p.tab, last_row);
-                    if (DEBRIS) {
-                        const double h2 = col_h2[lc];
-                        g0 *= exp(k0 * h2);
-                        g1 *= exp(k1 * h2);
-                    }
-                    g0 *= s0;
-                    g1 *= s1;
-                } else if (jk == -1.0) {
-                    g0 = p.swV[v0 + lane];
-                    g1 = p.swV[v0 + lane + 32];
-                } else {
-                    g0 = 0.0;
-                    g1 = 0.0;
-                }
-                G[sc * FB_LDV + lane] = g0;
-                G[sc * FB_LDV + lane + 32] = g1;
-            }
-            __syncthreads();
-
-            // ---------------- phase 2: DMMA over the tile -----------------------------------------
+        // this warp's register block (all warp-uniform).  Kept in shared memory and re-read at the start of
+        // every DMMA phase so that it does not occupy registers (next to 100 accumulator registers) while
+        // the J0 loop runs.
+        const int smsp = warp & 3, slot = warp >> 2;
+        if (lane == 0) {
+            int r0, c0, nr, nc, nmod = 1, base_cols = 0;
             if (ty.kind == FB_KIND_OFF) {
-                const double *ap = G + (r0 * 8) * FB_LDV + frag;
-                const double *bp = G + (FB_PCOLS + c0 * 8) * FB_LDV + frag;
-                if (nr == 5 && nc == 5) {
-#pragma unroll 2
-                    for (int ks = 0; ks < FB_TV / 4; ks++) {
-                        double af[5];
+                r0 = 5 * slot;
+                c0 = 5 * ((slot + smsp) & 3);
+                nr = clamp5(ty.a_nt - r0);
+                nc = clamp5(ty.b_nt - c0);
+            } else {
+                const int tri = slot >> 1;
+                nmod = tri ? ty.b_nt : ty.a_nt;
+                base_cols = tri ? FB_PCOLS : 0;
+                r0 = 5 * ((smsp + slot) & 3);
+                c0 = 5 * (slot & 1);                       // first skew offset d
+                nr = clamp5(nmod - r0);
+                nc = nmod > 0 ? clamp5(nmod / 2 + 1 - c0) : 0;
+                if (nmod == 0) nmod = 1;
+            }
+            if (nr == 0 || nc == 0) { nr = 0; nc = 0; }
+            int *cf = cfg + warp * 8;
+            cf[0] = nr; cf[1] = nc; cf[2] = r0; cf[3] = c0; cf[4] = nmod;
+            cf[5] = (base_cols + r0 * 8) * GLD;                                                      // A fragment base
+            cf[6] = ty.kind == FB_KIND_OFF ? (FB_PCOLS + c0 * 8) * GLD : base_cols * GLD;            // B fragment base
+            cf[7] = (r0 + c0) % nmod;
+        }
+        const int kind = ty.kind;
+        const int ncolB = ncol - ncolA;
+        // staging role: thread tid < ncol stages the row of shared column sc_stage
+        const int sc_stage = tid < ncolA ? tid : FB_PCOLS + (tid - ncolA);
+
+        for (int tile = t0; tile < t1; ++tile) {
+            const size_t v0 = (size_t)tile * GT;
+            // ---- (1) stage table rows -------------------------------------------------------------
+            if (p.debug_mode != 2 || tile == t0) {
+                if (tid < ncol) {
+                    const double jk = col_jk[sc_stage];
+                    int m = 0;
+                    if (jk >= 0.0) m = min(__double2loint(fma(__dmul_rn(p.a[v0], jk), 4.0, MAGIC)), last_row);
+                    rowm[sc_stage] = m;
+                    const double2 *row = p.tab + (size_t)m * (FB_J0_ROWLEN / 2);
+                    double2 *dst = reinterpret_cast<double2 *>(rowbuf + sc_stage * FB_J0_ROWLEN);
 #pragma unroll
-                        for (int r = 0; r < 5; r++) af[r] = ap[r * 8 * FB_LDV + ks * 4];
-#pragma unroll
-                        for (int c = 0; c < 5; c++) {
-                            const double b = bp[c * 8 * FB_LDV + ks * 4];
-#pragma unroll
-                            for (int r = 0; r < 5; r++) dmma(acc[r][c], af[r], b);
-                        }
-                    }
-                } else if (nr > 0 && nc > 0) {
-                    for (int ks = 0; ks < FB_TV / 4; ks++) {
-                        double af[5];
-#pragma unroll
-                        for (int r = 0; r < 5; r++) af[r] = r < nr ? ap[r * 8 * FB_LDV + ks * 4] : 0.0;
-#pragma unroll
-                        for (int c = 0; c < 5; c++) {
-                            if (c < nc) {
-                                const double b = bp[c * 8 * FB_LDV + ks * 4];
-#pragma unroll
-                                for (int r = 0; r < 5; r++)
-                                    if (r < nr) dmma(acc[r][c], af[r], b);
-                            }
-                        }
-                    }
+                    for (int k = 0; k < FB_J0_ROWLEN / 2; k++) dst[k] = __ldg(row + k);
                 }
-            } else if (nr > 0 && nc > 0) {
-                // skewed strip of a triangle: acc[r][d] += G_{r0+r}^T G_{(r0+r + c0+d) mod n}
-                const double *ap = G + (base_cols + r0 * 8) * FB_LDV + frag;
-                const double *tp = G + base_cols * FB_LDV + frag;
-                int boff[9];
-#pragma unroll
-                for (int s = 0; s < 9; s++) boff[s] = ((r0 + c0 + s) % nmod) * 8 * FB_LDV;
-                const bool full = (nr == 5 && nc == 5);
+            }
+            __syncthreads();          // rows staged; every warp is done with the previous tile's DMMAs
+            // ---- (2) J0 evaluation ------------------------------------------------------------------
+            if (p.debug_mode != 2 || tile == t0) {
+                const double a0 = p.a[v0 + lane], a1 = p.a[v0 + lane + 32];
+                const double w0 = p.sw[v0 + lane], w1 = p.sw[v0 + lane + 32];
+                double k0 = 0.0, k1 = 0.0;
+                if (DEBRIS) {
+                    k0 = p.kz[v0 + lane]; k1 = p.kz[v0 + lane + 32];
+                    k0 = -k0 * k0; k1 = -k1 * k1;
+                }
+                // panel A columns then panel B columns; the start of the second sweep is rotated by 8 warps
+                // so that an odd column count per 16 warps balances out
 #pragma unroll 1
-                for (int ks = 0; ks < FB_TV / 4; ks++) {
-                    double af[5];
-#pragma unroll
-                    for (int r = 0; r < 5; r++) af[r] = r < nr ? ap[r * 8 * FB_LDV + ks * 4] : 0.0;
-#pragma unroll
-                    for (int s = 0; s < 9; s++) {
-                        if (full || s < nr + nc - 1) {
-                            const double b = tp[boff[s] + ks * 4];
-#pragma unroll
-                            for (int r = 0; r < 5; r++) {
-                                const int d = s - r;
-                                if (d >= 0 && d < 5) {
-                                    if (full || (r < nr && d < nc)) dmma(acc[r][d], af[r], b);
-                                }
+                for (int half = 0; half < 2; half++) {
+                    const int nh = half ? ncolB : ncolA;
+                    const int base = half ? FB_PCOLS : 0;
+#pragma unroll 1
+                    for (int lc = half ? ((warp + 8) & 15) : warp; lc < nh; lc += FB_GRAM_THREADS / 32) {
+                        const int sc = base + lc;
+                        const double jk = col_jk[sc];
+                        double g0, g1;
+                        if (jk >= 0.0) {
+                            const double x0 = __dmul_rn(a0, jk), x1 = __dmul_rn(a1, jk);
+                            const double s0 = fma(x0, 4.0, MAGIC), s1 = fma(x1, 4.0, MAGIC);
+                            const int mref = rowm[sc];
+                            const bool same = (min(__double2loint(s0), last_row) == mref) & (min(__double2loint(s1), last_row) == mref);
+                            if (__all_sync(0xffffffffu, same)) {
+                                horner2(reinterpret_cast<const double2 *>(rowbuf + sc * FB_J0_ROWLEN),
+                                        fma(s0 - MAGIC, -0.25, x0), fma(s1 - MAGIC, -0.25, x1), g0, g1);
+                            } else {
+                                g0 = j0_tab(x0, p.tab, last_row);
+                                g1 = j0_tab(x1, p.tab, last_row);
                             }
+                            if (DEBRIS) {
+                                const double h2 = col_h2[sc];
+                                g0 *= exp(k0 * h2);
+                                g1 *= exp(k1 * h2);
+                            }
+                            g0 *= w0;
+                            g1 *= w1;
+                        } else if (jk == -1.0) {
+                            g0 = p.swV[v0 + lane];
+                            g1 = p.swV[v0 + lane + 32];
+                        } else {
+                            g0 = 0.0;
+                            g1 = 0.0;
                         }
+                        G[sc * GLD + lane] = g0;
+                        G[sc * GLD + lane + 32] = g1;
                     }
                 }
             }
             __syncthreads();
+            // ---- (3) DMMA over the tile -----------------------------------------------------------
+            if (p.debug_mode != 1) {
+                const int *cf = cfg + warp * 8;
+                const int nr = cf[0], nc = cf[1], nmod = cf[4], cbase = cf[7];
+                const int frag = (lane >> 2) * GLD + (lane & 3);
+                const double *ap = G + cf[5] + frag;
+                const double *bp = G + cf[6] + frag;
+                if (nr > 0) {
+                    if (kind == FB_KIND_OFF) {
+                        switch (nr) {
+                            case 5: mma_off_nc<5>(acc, ap, bp, nc); break;
+                            case 4: mma_off_nc<4>(acc, ap, bp, nc); break;
+                            case 3: mma_off_nc<3>(acc, ap, bp, nc); break;
+                            case 2: mma_off_nc<2>(acc, ap, bp, nc); break;
+                            default: mma_off_nc<1>(acc, ap, bp, nc); break;
+                        }
+                    } else {
+                        switch (nr) {
+                            case 5: mma_diag_nd<5>(acc, ap, bp, cbase, nmod, nc); break;
+                            case 4: mma_diag_nd<4>(acc, ap, bp, cbase, nmod, nc); break;
+                            case 3: mma_diag_nd<3>(acc, ap, bp, cbase, nmod, nc); break;
+                            case 2: mma_diag_nd<2>(acc, ap, bp, cbase, nmod, nc); break;
+                            default: mma_diag_nd<1>(acc, ap, bp, cbase, nmod, nc); break;
+                        }
+                    }
+                }
+            }
         }
 
         // ---------------- write the partial block ------------------------------------------------
         double *out = p.partial + (size_t)item * FB_PSZ;
-        if (ty.kind == FB_KIND_OFF) {
+        const int nr = cfg[warp * 8 + 0], nc = cfg[warp * 8 + 1], r0 = cfg[warp * 8 + 2], c0 = cfg[warp * 8 + 3];
+        if (kind == FB_KIND_OFF) {
 #pragma unroll
             for (int r = 0; r < 5; r++)
 #pragma unroll
@@ -350,8 +476,12 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
     args.jk = ctx->d_jk; args.tab = ctx->d_tab; args.tab_rows = ctx->tab_rows;
     args.N = ctx->N; args.ntypes = ctx->ntypes; args.C = C;
     args.types = ctx->d_types; args.H2 = ctx->d_H2; args.partial = ctx->d_partial;
+    {
+        const char *dbg = getenv("FB_GRAM_DEBUG");
+        args.debug_mode = dbg ? atoi(dbg) : 0;
+    }
 
-    const size_t smem = sizeof(double) * (2 * FB_PCOLS * FB_LDV + 4 * FB_PCOLS);
+    const size_t smem = GRAM_SMEM_BYTES;
     int grid = ctx->ntypes * C;
     if (grid > ctx->num_sms) grid = ctx->num_sms;
     if (n_tiles > 0) {
