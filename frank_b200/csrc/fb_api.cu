@@ -38,7 +38,7 @@ int fb_ctx_destroy(fb_ctx *ctx)
                     (void *)ctx->d_tile_panel, (void *)ctx->d_panel_t0, (void *)ctx->d_panel_nt, (void *)ctx->d_pair_code,
                     (void *)ctx->d_a, (void *)ctx->d_sw, (void *)ctx->d_swV, (void *)ctx->d_kz, (void *)ctx->d_red,
                     (void *)ctx->d_partial, (void *)ctx->d_H2, (void *)ctx->d_in, (void *)ctx->d_out,
-                    (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist})
+                    (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist, (void *)ctx->d_work})
         if (p) cudaFree(p);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -94,22 +94,23 @@ int fb_dht_setup(fb_ctx *ctx, int N, double Qmax, const double *host_j_nk, const
             t += panel_nt[p];
         }
     }
+    // pair_code[(pa * P + pb) * 2 + half] = OFF type of that half of the rows of panel pa against panel pb (pa < pb);
+    // pair_code[(p * P + p) * 2] = DIAG type of panel p
+    pair_code.assign((size_t)P * P * 2, -1);
     ctx->h_types.clear();
     for (int pa = 0; pa < P; pa++)
         for (int pb = pa + 1; pb < P; pb++) {
-            pair_code[(size_t)pa * P + pb] = (int)ctx->h_types.size();
-            ctx->h_types.push_back({FB_KIND_OFF, panel_t0[pa], panel_nt[pa], panel_t0[pb], panel_nt[pb]});
+            const int h0 = (panel_nt[pa] + 1) / 2;
+            pair_code[((size_t)pa * P + pb) * 2 + 0] = (int)ctx->h_types.size();
+            ctx->h_types.push_back({FB_KIND_OFF, panel_t0[pa], h0, panel_t0[pb], panel_nt[pb]});
+            if (panel_nt[pa] - h0 > 0) {
+                pair_code[((size_t)pa * P + pb) * 2 + 1] = (int)ctx->h_types.size();
+                ctx->h_types.push_back({FB_KIND_OFF, panel_t0[pa] + h0, panel_nt[pa] - h0, panel_t0[pb], panel_nt[pb]});
+            }
         }
-    for (int p = 0; p < P; p += 2) {
-        const int id = (int)ctx->h_types.size();
-        FbGramType t{FB_KIND_DIAG2, panel_t0[p], panel_nt[p], 0, 0};
-        pair_code[(size_t)p * P + p] = (id << 1) | 0;
-        if (p + 1 < P) {
-            t.b_t0 = panel_t0[p + 1];
-            t.b_nt = panel_nt[p + 1];
-            pair_code[(size_t)(p + 1) * P + (p + 1)] = (id << 1) | 1;
-        }
-        ctx->h_types.push_back(t);
+    for (int p = 0; p < P; p++) {
+        pair_code[((size_t)p * P + p) * 2] = (int)ctx->h_types.size();
+        ctx->h_types.push_back({FB_KIND_DIAG, panel_t0[p], panel_nt[p], 0, 0});
     }
     ctx->ntypes = (int)ctx->h_types.size();
     for (void **p : {(void **)&ctx->d_types, (void **)&ctx->d_tile_panel, (void **)&ctx->d_panel_t0,
@@ -121,12 +122,12 @@ int fb_dht_setup(fb_ctx *ctx, int N, double Qmax, const double *host_j_nk, const
     FB_CUDA(cudaMalloc(&ctx->d_tile_panel, sizeof(int) * NT));
     FB_CUDA(cudaMalloc(&ctx->d_panel_t0, sizeof(int) * P));
     FB_CUDA(cudaMalloc(&ctx->d_panel_nt, sizeof(int) * P));
-    FB_CUDA(cudaMalloc(&ctx->d_pair_code, sizeof(int) * P * P));
+    FB_CUDA(cudaMalloc(&ctx->d_pair_code, sizeof(int) * P * P * 2));
     FB_CUDA(cudaMemcpy(ctx->d_types, ctx->h_types.data(), sizeof(FbGramType) * ctx->ntypes, cudaMemcpyHostToDevice));
     FB_CUDA(cudaMemcpy(ctx->d_tile_panel, tile_panel.data(), sizeof(int) * NT, cudaMemcpyHostToDevice));
     FB_CUDA(cudaMemcpy(ctx->d_panel_t0, panel_t0.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
     FB_CUDA(cudaMemcpy(ctx->d_panel_nt, panel_nt.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
-    FB_CUDA(cudaMemcpy(ctx->d_pair_code, pair_code.data(), sizeof(int) * P * P, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_pair_code, pair_code.data(), sizeof(int) * P * P * 2, cudaMemcpyHostToDevice));
 
     if (!(x_max > 0)) x_max = host_j_nk[N - 1];
     return fb_build_j0_table(ctx, x_max);

@@ -9,25 +9,34 @@
 #include "../../include/frankb200.h"
 
 // ---- geometry of the fused J0 + Gram kernel -------------------------------------------------
-// One tile = TV visibilities.  The design-matrix tile G[mode][vis] lives in shared memory with a
-// leading dimension LDV = TV + 4 doubles so that the m8n8k4 fragment pattern (8 modes x 4 vis)
+// One tile = FB_TV visibilities.  The design-matrix tile G[mode][vis] lives in shared memory with a
+// leading dimension FB_LDV = FB_TV + 4 doubles so that the m8n8k4 fragment pattern (8 modes x 4 vis)
 // touches all 32 banks exactly once per half-warp.
+//
+// The symmetric (N+1)x(N+1) Gram matrix is cut into 8x8 tiles, the tiles into panels of <= FB_PT tiles, and
+// the upper triangle of the panel grid into work-item types:
+//   OFF  : <= FB_HT tile rows of panel A  x  all tile columns of panel B   (A < B; two halves per panel pair)
+//   DIAG : the upper triangle of one panel, executed as the skewed strip (row r, offset d) -> column (r+d) mod n
+// so that every CTA holds <= 190 accumulator tiles (<= 15 per warp, 60 registers) and has to evaluate J0 only
+// for the <= 232 columns its block touches.
 constexpr int FB_TV = 64;
 constexpr int FB_LDV = FB_TV + 4;
 constexpr int FB_PT = 19;              // max 8-column tiles per panel (152 modes)
-constexpr int FB_PCOLS = FB_PT * 8;
-constexpr int FB_DH = 10;              // skew offsets per triangle: floor(PT/2) + 1
-constexpr int FB_PSZ = 2 * FB_PT * FB_DH * 64;   // doubles per work-item partial (>= PT*PT*64)
+constexpr int FB_HT = 10;              // max tile rows of an OFF item: ceil(FB_PT / 2)
+constexpr int FB_DH = 10;              // skew offsets per triangle: floor(FB_PT / 2) + 1
+constexpr int FB_GCOLS = (FB_HT + FB_PT) * 8;    // columns of G held per tile
+constexpr int FB_PSZ = FB_PT * 10 * 64;          // doubles per work-item partial
+constexpr int FB_ACC = 15;             // accumulator tiles per warp
 constexpr int FB_GRAM_THREADS = 512;
 constexpr int FB_J0_ROWLEN = 10;       // Taylor degree 9, rows centred on multiples of 1/4
 
-constexpr int FB_KIND_OFF = 0;         // rectangular block  panel A x panel B
-constexpr int FB_KIND_DIAG2 = 1;       // upper triangles of panel A and of panel B
+constexpr int FB_KIND_OFF = 0;
+constexpr int FB_KIND_DIAG = 1;
 
 struct FbGramType {
     int kind;
-    int a_t0, a_nt;   // first tile / number of tiles of panel A
-    int b_t0, b_nt;   // panel B (b_nt == 0 when a DIAG2 item carries a single triangle)
+    int a_t0, a_nt;   // OFF: tile rows [a_t0, a_t0 + a_nt)   DIAG: the panel
+    int b_t0, b_nt;   // OFF: tile columns                     DIAG: unused (b_nt = 0)
 };
 
 struct fb_ctx {
@@ -47,6 +56,8 @@ struct fb_ctx {
     std::vector<FbGramType> h_types;
     FbGramType *d_types = nullptr;
     int *d_tile_panel = nullptr, *d_panel_t0 = nullptr, *d_panel_nt = nullptr, *d_pair_code = nullptr;
+    int *d_work = nullptr;         // per launch: [3 * max_items] item -> (type, chunk, partial slot); then per type (C, first slot)
+    int work_cap = 0;
     // workspaces
     int64_t cap = 0;
     double *d_a = nullptr, *d_sw = nullptr, *d_swV = nullptr, *d_kz = nullptr;   // sorted, padded, SoA
