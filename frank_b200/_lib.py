@@ -40,6 +40,9 @@ _SIGNATURES = {
     'fb_last_map_timing': ([_c_p, _c_p], _c_i),
     'fb_debug_prepped': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
+    'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
+    'fb_frank_normal_loop': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p,
+                              _c_p, _c_p, _c_p, _c_p, _c_i], _c_i),
 }
 
 _lib = None
@@ -145,6 +148,48 @@ class Context(object):
         self.check(self._lib.fb_debug_prepped(self._h, int(n), _ptr(a), _ptr(kz), _ptr(Vre), _ptr(perm)),
                    'fb_debug_prepped')
         return a, kz, Vre, perm
+
+    # -- solver ------------------------------------------------------------------------------
+    def gaussian_fit(self, M, j, p=None, want_chol=True):
+        """fb_gaussian_fit for a batch of power spectra p [B, N] (or no prior).  Returns mu [B, N],
+        chol [B, N, N] (upper factor in the upper triangle), info [B], status."""
+        N = M.shape[0]
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        j = np.ascontiguousarray(j, dtype=np.float64)
+        if p is None:
+            B, pp = 1, None
+        else:
+            pp = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
+            B = pp.shape[0]
+        mu = np.empty((B, N))
+        chol = np.empty((B, N, N)) if want_chol else None
+        info = np.zeros(B, dtype=np.int32)
+        rc = self._lib.fb_gaussian_fit(self._h, B, _ptr(M), _ptr(j), _ptr(pp), int(p is not None), _ptr(mu), _ptr(chol),
+                                       _ptr(info))
+        self.check(rc, 'fb_gaussian_fit')
+        return mu, chol, info, rc
+
+    def frank_normal_loop(self, M, j, p_init, alpha, p0, ldl, tol, max_iter, want_chol=True, hist_cap=0):
+        """fb_frank_normal_loop for B hyper-parameter points.  Returns a dict."""
+        N = M.shape[0]
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        j = np.ascontiguousarray(j, dtype=np.float64)
+        p_init = np.ascontiguousarray(np.atleast_2d(p_init), dtype=np.float64)
+        B = p_init.shape[0]
+        alpha = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64), (B,)))
+        p0 = np.ascontiguousarray(np.broadcast_to(np.asarray(p0, dtype=np.float64), (B,)))
+        ldl = np.ascontiguousarray(np.broadcast_to(np.asarray(ldl, dtype=np.float64), (B, 3, N)))
+        p = np.empty((B, N)); mu = np.empty((B, N))
+        chol = np.empty((B, N, N)) if want_chol else None
+        niter = np.zeros(B, dtype=np.int32); conv = np.zeros(B, dtype=np.int32); info = np.zeros(B, dtype=np.int32)
+        hp = np.zeros((B, hist_cap, N)) if hist_cap > 0 else None
+        hm = np.zeros((B, hist_cap, N)) if hist_cap > 0 else None
+        rc = self._lib.fb_frank_normal_loop(self._h, B, _ptr(M), _ptr(j), _ptr(p_init), _ptr(alpha), _ptr(p0), _ptr(ldl),
+                                            float(tol), int(max_iter), _ptr(p), _ptr(mu), _ptr(chol), _ptr(niter),
+                                            _ptr(conv), _ptr(info), _ptr(hp), _ptr(hm), int(hist_cap))
+        self.check(rc, 'fb_frank_normal_loop')
+        return {'p': p, 'mu': mu, 'chol': chol, 'niter': niter, 'converged': conv, 'info': info, 'status': rc,
+                'hist_p': hp, 'hist_mu': hm}
 
     def debug_j0(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

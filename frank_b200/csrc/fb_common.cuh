@@ -76,6 +76,11 @@ struct fb_ctx {
     int64_t in_cap = 0;
     double *d_out = nullptr;
     size_t out_cap = 0;
+    // solver workspaces (fb_solve.cu)
+    int sv_B = 0, sv_N = 0;
+    double *sv_D = nullptr, *sv_p = nullptr, *sv_mu = nullptr, *sv_tr2 = nullptr, *sv_alpha = nullptr, *sv_p0 = nullptr;
+    double *sv_ldl = nullptr, *sv_M = nullptr, *sv_j = nullptr, *sv_Z = nullptr;
+    int *sv_flags = nullptr;
     cudaEvent_t ev[8] = {};
     double timing[4] = {0, 0, 0, 0};
     int num_sms = 148;

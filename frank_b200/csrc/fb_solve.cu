@@ -1,0 +1,619 @@
+// K4-K6: dense FP64 solves of the power-spectrum fixed-point iteration, batched over B problems
+// (hyper-parameter grid points).  Replaces, per iteration of FrankFitter._fit (frank/radial_fitters.py:769-785):
+//   GaussianModel.__init__/_fit      S^-1 = Y^T diag(1/p) Y ; D^-1 = M + S^-1 ; cho_factor ; mu = cho_solve(j)
+//                                    (frank/statistical_models.py:700-745)
+//   CriticalFilter.update_power_spectrum   Tr1 = (Y mu)^2 ; Tr2 = diag(Y D Y^T) ; beta ; (T + I) tau = beta + log p ;
+//                                    p = exp(tau)              (frank/filter.py:154-177)
+//   CriticalFilter.check_convergence all(|p_new - p_old| <= tol p_new)   (frank/filter.py:179-181)
+//
+// Matrices are row-major N x N, one after another per problem.  The Cholesky factor is the upper one,
+// D^-1 = U^T U (what scipy.linalg.cho_factor returns by default), computed in place by a right-looking blocked
+// algorithm with 64 x 64 blocks: per block row one "panel" kernel (diagonal block factorisation + triangular
+// solves of the block row) and one "update" kernel (symmetric rank-64 update of the trailing matrix).
+// Tr2_i = || U^-T Y[i, :]^T ||^2 needs only the forward substitution (same value as the reference's
+// einsum('ij,ji->i', Y, cho_solve(Y.T)) up to round-off).
+#include "fb_common.cuh"
+
+#include <cmath>
+
+namespace {
+
+constexpr int NB = 64;                 // block size of the blocked algorithms
+constexpr int SLD = NB + 1;            // padded leading dimension of 64 x 64 blocks in shared memory
+
+struct SolveDims {
+    int N, nb;                         // matrix size, number of 64-blocks
+};
+
+// ---- D^-1 = M + Y^T diag(1/p) Y  (upper blocks computed, mirrored) ------------------------------------------------
+// grid (nb*(nb+1)/2, B), 256 threads, 4x4 outputs per thread.
+__global__ void __launch_bounds__(256)
+k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restrict__ Y, const double *__restrict__ p_all,
+             const int *__restrict__ active, double *__restrict__ Dinv_all)
+{
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    int rem = blockIdx.x, bi = 0;
+    while (rem >= nb - bi) { rem -= nb - bi; bi++; }
+    const int bj = bi + rem;
+    const double *p = p_all + (size_t)b * N;
+    double *Dinv = Dinv_all + (size_t)b * N * N;
+    __shared__ double Ya[16][NB + 4], Yb[16][NB + 4];     // [k][i] slices of Y scaled / unscaled
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < N; k0 += 16) {
+        for (int e = threadIdx.x; e < 16 * NB; e += 256) {
+            const int kk = e / NB, c = e % NB, k = k0 + kk;
+            const int ia = bi * NB + c, ib = bj * NB + c;
+            const double ip = k < N ? 1.0 / p[k] : 0.0;
+            Ya[kk][c] = (k < N && ia < N) ? Y[(size_t)k * N + ia] * ip : 0.0;     // einsum order: (Y_ji * (1/p)_j) * Y_jk
+            Yb[kk][c] = (k < N && ib < N) ? Y[(size_t)k * N + ib] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            double a[4], bb[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) { a[r] = Ya[kk][ty * 4 + r]; bb[r] = Yb[kk][tx * 4 + r]; }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = fma(a[r], bb[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int i = bi * NB + ty * 4 + r, j = bj * NB + tx * 4 + c;
+            if (i < N && j < N) {
+                const double v = M[(size_t)i * N + j] + acc[r][c];
+                Dinv[(size_t)i * N + j] = v;
+                if (bi != bj) Dinv[(size_t)j * N + i] = M[(size_t)j * N + i] + acc[r][c];
+            }
+        }
+}
+
+// ---- Cholesky panel: factor A_kk, then U_kj = U_kk^-T A_kj for the block row ----------------------------------------
+// grid (nb - k, B): block x = 0 factors and stores the diagonal block, x > 0 solves block column k + x.
+__global__ void __launch_bounds__(256)
+k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active, int *__restrict__ info)
+{
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    double *A = A_all + (size_t)b * N * N;
+    extern __shared__ double dyn_sm[];
+    double (*D)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm);
+    double (*R)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm + NB * SLD);
+    const int tid = threadIdx.x;
+    const int j = k + blockIdx.x;
+    const int r0 = k * NB, c0 = j * NB;
+    const int nk = min(NB, N - r0), nj = min(NB, N - c0);
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        D[r][c] = (r < nk && c < nk && c >= r) ? A[(size_t)(r0 + r) * N + r0 + c] : (r == c ? 1.0 : 0.0);
+        if (blockIdx.x > 0) R[r][c] = (r < nk && c < nj) ? A[(size_t)(r0 + r) * N + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    // unblocked upper Cholesky of D in shared memory (every CTA of the panel repeats it: 64 short steps)
+    for (int c = 0; c < nk; c++) {
+        const double piv = D[c][c];
+        if (tid == 0 && blockIdx.x == 0 && !(piv > 0.0)) atomicCAS(&info[b], 0, r0 + c + 1);
+        const double d = sqrt(piv), inv = 1.0 / d;
+        __syncthreads();
+        if (tid == 0) D[c][c] = d;
+        for (int e = tid + c + 1; e < nk; e += 256) D[c][e] = D[c][e] * inv;
+        __syncthreads();
+        // trailing update of the upper triangle: D[i][jj] -= U[c][i] U[c][jj], c < i <= jj
+        const int m = nk - c - 1;
+        for (int e = tid; e < m * m; e += 256) {
+            const int i = c + 1 + e / m, jj = c + 1 + e % m;
+            if (jj >= i) D[i][jj] = fma(-D[c][i], D[c][jj], D[i][jj]);
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0) {
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int r = e / NB, c = e % NB;
+            if (r < nk && c < nk && c >= r) A[(size_t)(r0 + r) * N + r0 + c] = D[r][c];
+        }
+        return;
+    }
+    // forward substitution U_kk^T X = R, all 64 columns at once: 4 threads per column
+    const int col = tid & 63, part = tid >> 6;
+    for (int r = 0; r < nk; r++) {
+        if (part == 0) R[r][col] = R[r][col] / D[r][r];
+        __syncthreads();
+        const double x = R[r][col];
+        for (int rr = r + 1 + part; rr < nk; rr += 4) R[rr][col] = fma(-D[r][rr], x, R[rr][col]);
+        __syncthreads();
+    }
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        if (r < nk && c < nj) A[(size_t)(r0 + r) * N + c0 + c] = R[r][c];
+    }
+}
+
+// ---- trailing update A_ij -= U_ki^T U_kj, k < i <= j -----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_chol_update(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active)
+{
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    double *A = A_all + (size_t)b * N * N;
+    const int nt = nb - k - 1;
+    int rem = blockIdx.x, ii = 0;
+    while (rem >= nt - ii) { rem -= nt - ii; ii++; }
+    const int bi = k + 1 + ii, bj = bi + rem;
+    extern __shared__ double dyn_sm[];
+    double (*Ui)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm);
+    double (*Uj)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm + NB * SLD);
+    const int r0 = k * NB, nk = min(NB, N - r0);
+    for (int e = threadIdx.x; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        const int ci = bi * NB + c, cj = bj * NB + c;
+        Ui[r][c] = (r < nk && ci < N) ? A[(size_t)(r0 + r) * N + ci] : 0.0;
+        Uj[r][c] = (r < nk && cj < N) ? A[(size_t)(r0 + r) * N + cj] : 0.0;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4] = {};
+#pragma unroll 4
+    for (int kk = 0; kk < NB; kk++) {
+        double a[4], bb[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) { a[r] = Ui[kk][ty * 4 + r]; bb[r] = Uj[kk][tx * 4 + r]; }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[r][c] = fma(a[r], bb[c], acc[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int i = bi * NB + ty * 4 + r, j = bj * NB + tx * 4 + c;
+            if (i < N && j < N && j >= i) A[(size_t)i * N + j] -= acc[r][c];
+        }
+}
+
+// ---- Z = U^-T R for a slab of right-hand sides; returns column sums of squares ----------------------------------------
+// R = Y^T (columns = rows of Y).  grid (ceil(N / 32), B), 256 threads.  The slab of Z (N x 32) lives in shared
+// memory (N <= 512) or in a global scratch (larger N).
+constexpr int TS = 32;                 // right-hand sides per CTA
+
+__global__ void __launch_bounds__(256)
+k_trsm_tr2(int N, int nb, const double *__restrict__ U_all, const double *__restrict__ Y, const int *__restrict__ active,
+           double *__restrict__ Zscratch_all, double *__restrict__ tr2_all)
+{
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const double *U = U_all + (size_t)b * N * N;
+    extern __shared__ double sm[];
+    double *Ub = sm;                       // [NB][SLD]   current block of U
+    double *Zs = sm + NB * SLD;            // [N_pad][TS + 1] when it fits, else a [NB][TS+1] window
+    const bool in_smem = Zscratch_all == nullptr;
+    double *Zg = in_smem ? nullptr : Zscratch_all + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)nb * NB * TS;
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * TS;        // first right-hand side = row c0 of Y
+    const int col = tid & 31, part = tid >> 5;          // 8 threads per right-hand side
+    auto Z = [&](int r, int c) -> double & { return in_smem ? Zs[r * (TS + 1) + c] : Zg[(size_t)r * TS + c]; };
+
+    for (int kb = 0; kb < nb; kb++) {
+        const int r0 = kb * NB, nk = min(NB, N - r0);
+        // acc = R block: R[r0 + r][c0 + col] = Y[c0 + col][r0 + r]
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int r = part * 8 + q;
+            acc[q] = (r < nk && c0 + col < N) ? Y[(size_t)(c0 + col) * N + r0 + r] : 0.0;
+        }
+        // minus sum_{ib < kb} U_{ib,kb}^T Z_ib
+        for (int ib = 0; ib < kb; ib++) {
+            __syncthreads();
+            for (int e = tid; e < NB * NB; e += 256) {
+                const int r = e / NB, c = e % NB;
+                Ub[r * SLD + c] = (c < nk) ? U[(size_t)(ib * NB + r) * N + r0 + c] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int i = 0; i < NB; i++) {
+                const double z = Z(ib * NB + i, col);
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc[q] = fma(-Ub[i * SLD + part * 8 + q], z, acc[q]);
+            }
+        }
+        // diagonal block solve U_kk^T X = acc
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int r = e / NB, c = e % NB;
+            Ub[r * SLD + c] = (r < nk && c < nk && c >= r) ? U[(size_t)(r0 + r) * N + r0 + c] : (r == c ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) Z(r0 + part * 8 + q, col) = acc[q];
+        __syncthreads();
+        for (int r = 0; r < nk; r++) {
+            if (part == 0) Z(r0 + r, col) = Z(r0 + r, col) / Ub[r * SLD + r];
+            __syncthreads();
+            const double x = Z(r0 + r, col);
+            for (int rr = r + 1 + part; rr < nk; rr += 8) Z(r0 + rr, col) = fma(-Ub[r * SLD + rr], x, Z(r0 + rr, col));
+            __syncthreads();
+        }
+    }
+    // column sums of squares: Tr2[c0 + col]
+    double s = 0.0;
+    for (int r = part; r < N; r += 8) { const double z = Z(r, col); s = fma(z, z, s); }
+    __syncthreads();
+    double *red = Ub;
+    red[part * 32 + col] = s;
+    __syncthreads();
+    if (part == 0 && c0 + col < N) {
+        double t = 0.0;
+        for (int q = 0; q < 8; q++) t += red[q * 32 + col];
+        tr2_all[(size_t)b * N + c0 + col] = t;
+    }
+}
+
+// ---- mu = U^-1 U^-T j, one CTA (1024 threads) per problem ---------------------------------------------------------
+// Both sweeps walk U in panels of PR rows staged in shared memory (rows of the row-major upper factor are
+// contiguous): the PR x PR triangle is solved by one warp with shuffles, the rest of the panel is a
+// block update done by all threads.
+__global__ void __launch_bounds__(1024)
+k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__restrict__ jvec, int j_stride,
+           const int *__restrict__ active, double *__restrict__ mu_all)
+{
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    const double *U = U_all + (size_t)b * N * N;
+    extern __shared__ double shm[];
+    double *x = shm;                       // [N]  right-hand side / solution
+    double *zp = shm + N;                  // [32] panel solution
+    double *S = shm + N + 32;              // [PR][N] panel of U rows
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int i = tid; i < N; i += blockDim.x) x[i] = jvec[(size_t)b * j_stride + i];
+    // ---- forward: U^T z = j
+    for (int r1 = 0; r1 < N; r1 += PR) {
+        const int nk = min(PR, N - r1);
+        __syncthreads();
+        for (int e = tid; e < nk * (N - r1); e += blockDim.x) {
+            const int r = e / (N - r1), c = r1 + e % (N - r1);
+            S[r * N + c] = U[(size_t)(r1 + r) * N + c];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double xl = lane < nk ? x[r1 + lane] : 0.0;
+            for (int r = 0; r < nk; r++) {
+                double zr = 0.0;
+                if (lane == r) { xl = xl / S[r * N + r1 + r]; zr = xl; }
+                zr = __shfl_sync(0xffffffffu, zr, r);
+                if (lane > r && lane < nk) xl = fma(-S[r * N + r1 + lane], zr, xl);
+            }
+            if (lane < nk) { x[r1 + lane] = xl; zp[lane] = xl; }
+        }
+        __syncthreads();
+        for (int c = r1 + nk + tid; c < N; c += blockDim.x) {
+            double v = x[c];
+            for (int r = 0; r < nk; r++) v = fma(-S[r * N + c], zp[r], v);
+            x[c] = v;
+        }
+    }
+    // ---- backward: U mu = z
+    const int last = ((N - 1) / PR) * PR;
+    for (int r1 = last; r1 >= 0; r1 -= PR) {
+        const int nk = min(PR, N - r1);
+        __syncthreads();
+        for (int e = tid; e < nk * (N - r1); e += blockDim.x) {
+            const int r = e / (N - r1), c = r1 + e % (N - r1);
+            S[r * N + c] = U[(size_t)(r1 + r) * N + c];
+        }
+        __syncthreads();
+        // tail dot products with the already final part of mu: one warp per panel row
+        for (int r = warp; r < nk; r += nw) {
+            double sacc = 0.0;
+            for (int c = r1 + nk + lane; c < N; c += 32) sacc = fma(S[r * N + c], x[c], sacc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, o);
+            if (lane == 0) zp[r] = x[r1 + r] - sacc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double al = lane < nk ? zp[lane] : 0.0;
+            for (int r = nk - 1; r >= 0; r--) {
+                double mr = 0.0;
+                if (lane == r) { al = al / S[r * N + r1 + r]; mr = al; }
+                mr = __shfl_sync(0xffffffffu, mr, r);
+                if (lane < r) al = fma(-S[lane * N + r1 + r], mr, al);
+            }
+            if (lane < nk) x[r1 + lane] = al;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += blockDim.x) mu_all[(size_t)b * N + i] = x[i];
+}
+
+// ---- power-spectrum update, one CTA per problem -----------------------------------------------------------------
+// Tr1 = (Y mu)^2 ; beta = (p0 + 0.5 (Tr1 + Tr2)) / p - (alpha - 1 + 0.5) ; (T + I) tau = beta + log p ; p_new = exp(tau).
+// The SPD pentadiagonal matrix T + I is passed as its banded L D L^T factorisation (host, once per filter):
+// ldl[0] = D, ldl[1] = L sub-diagonal 1, ldl[2] = L sub-diagonal 2.
+__global__ void __launch_bounds__(256)
+k_ps_update(int N, const double *__restrict__ Y, const double *__restrict__ mu_all, const double *__restrict__ tr2_all,
+            const double *__restrict__ alpha_all, const double *__restrict__ p0_all, const double *__restrict__ ldl_all,
+            int ldl_stride, double tol, int max_iter, double *__restrict__ p_all, int *__restrict__ active,
+            int *__restrict__ count, int *__restrict__ converged, double *__restrict__ hist_p, int hist_cap)
+{
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    extern __shared__ double sh[];         // mu[N], rhs[N]
+    double *mu = sh, *rhs = sh + N;
+    __shared__ int not_conv;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *p = p_all + (size_t)b * N;
+    const double *ldl = ldl_all + (size_t)b * ldl_stride;
+    for (int i = tid; i < N; i += 256) mu[i] = mu_all[(size_t)b * N + i];
+    if (tid == 0) not_conv = 0;
+    __syncthreads();
+    const double alpha = alpha_all[b], p0 = p0_all[b];
+    for (int i = warp; i < N; i += 8) {
+        double s = 0.0;
+        for (int c = lane; c < N; c += 32) s = fma(Y[(size_t)i * N + c], mu[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const double tr1 = s * s, tr2 = tr2_all[(size_t)b * N + i], pi = p[i];
+            const double beta = (p0 + 0.5 * (tr1 + tr2)) / pi - (alpha - 1.0 + 0.5 * 1.0);
+            rhs[i] = beta + log(pi);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // L y = rhs ; D w = y ; L^T tau = w   (unit lower-triangular L with two sub-diagonals)
+        const double *Dd = ldl, *L1 = ldl + N, *L2 = ldl + 2 * N;
+        for (int i = 0; i < N; i++) {
+            double v = rhs[i];
+            if (i >= 1) v = fma(-L1[i], rhs[i - 1], v);
+            if (i >= 2) v = fma(-L2[i], rhs[i - 2], v);
+            rhs[i] = v;
+        }
+        for (int i = 0; i < N; i++) rhs[i] = rhs[i] / Dd[i];
+        for (int i = N - 1; i >= 0; i--) {
+            double v = rhs[i];
+            if (i + 1 < N) v = fma(-L1[i + 1], rhs[i + 1], v);
+            if (i + 2 < N) v = fma(-L2[i + 2], rhs[i + 2], v);
+            rhs[i] = v;
+        }
+    }
+    __syncthreads();
+    int bad = 0;
+    for (int i = tid; i < N; i += 256) {
+        const double pn = exp(rhs[i]), po = p[i];
+        if (!(fabs(pn - po) <= tol * pn)) bad = 1;
+        p_all[(size_t)b * N + i] = pn;
+        if (hist_p && count[b] < hist_cap) hist_p[((size_t)b * hist_cap + count[b]) * N + i] = pn;
+    }
+    if (bad) atomicOr(&not_conv, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const int c = count[b] + 1;
+        count[b] = c;
+        converged[b] = not_conv ? 0 : 1;
+        // while (not converged and count <= max_iter)          radial_fitters.py:769-770
+        // (the solve of the new p still runs in this iteration; `active` is cleared afterwards by k_loop_gate)
+    }
+}
+
+// clears `active` once the fit of the last power spectrum has been computed
+__global__ void k_loop_gate(int B, int max_iter, const int *__restrict__ count, const int *__restrict__ converged,
+                            int *__restrict__ active, int *__restrict__ n_active)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && active[b]) {
+        if (converged[b] || count[b] > max_iter) {
+            active[b] = 0;
+            atomicSub(n_active, 1);
+        }
+    }
+}
+
+__global__ void k_copy_hist_mu(int N, const double *__restrict__ mu_all, const int *__restrict__ count, const int *__restrict__ active_before,
+                               double *__restrict__ hist_mu, int hist_cap)
+{
+    const int b = blockIdx.x;
+    if (!active_before[b]) return;
+    const int c = count[b] - 1;
+    if (c < 0 || c >= hist_cap) return;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) hist_mu[((size_t)b * hist_cap + c) * N + i] = mu_all[(size_t)b * N + i];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host-side drivers
+// ---------------------------------------------------------------------------------------------
+static int ensure_solver_ws(fb_ctx *ctx, int B)
+{
+    const size_t N = ctx->N;
+    if (B <= ctx->sv_B && ctx->sv_N == (int)N) return 0;
+    for (void **p : {(void **)&ctx->sv_D, (void **)&ctx->sv_p, (void **)&ctx->sv_mu, (void **)&ctx->sv_tr2, (void **)&ctx->sv_alpha,
+                     (void **)&ctx->sv_p0, (void **)&ctx->sv_ldl, (void **)&ctx->sv_flags, (void **)&ctx->sv_M, (void **)&ctx->sv_j,
+                     (void **)&ctx->sv_Z}) {
+        if (*p) FB_CUDA(cudaFree(*p));
+        *p = nullptr;
+    }
+    FB_CUDA(cudaMalloc(&ctx->sv_D, sizeof(double) * B * N * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_p, sizeof(double) * B * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_mu, sizeof(double) * B * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_tr2, sizeof(double) * B * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_alpha, sizeof(double) * B));
+    FB_CUDA(cudaMalloc(&ctx->sv_p0, sizeof(double) * B));
+    FB_CUDA(cudaMalloc(&ctx->sv_ldl, sizeof(double) * B * 3 * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_flags, sizeof(int) * (4 * B + 8)));
+    FB_CUDA(cudaMalloc(&ctx->sv_M, sizeof(double) * N * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_j, sizeof(double) * N));
+    if (N > 512) {
+        const int nb = ((int)N + NB - 1) / NB, slabs = ((int)N + TS - 1) / TS;
+        FB_CUDA(cudaMalloc(&ctx->sv_Z, sizeof(double) * (size_t)B * slabs * nb * NB * TS));
+    }
+    ctx->sv_B = B;
+    ctx->sv_N = (int)N;
+    return 0;
+}
+
+// factor D^-1 (in ctx->sv_D) for all active problems and solve for mu
+static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_info)
+{
+    const int N = ctx->N, nb = (N + NB - 1) / NB;
+    const size_t blk2 = sizeof(double) * 2 * NB * SLD;
+    FB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
+    FB_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
+    for (int k = 0; k < nb; k++) {
+        k_chol_panel<<<dim3(nb - k, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info);
+        const int nt = nb - k - 1;
+        if (nt > 0) k_chol_update<<<dim3(nt * (nt + 1) / 2, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active);
+    }
+    int PR = 32;
+    while (PR > 1 && sizeof(double) * ((size_t)N + 32 + (size_t)PR * N) > 200 * 1024) PR /= 2;
+    const size_t smem = sizeof(double) * ((size_t)N + 32 + (size_t)PR * N);
+    FB_CUDA(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_mu<<<B, 1024, smem, ctx->stream>>>(N, PR, ctx->sv_D, ctx->sv_j, 0, d_active, ctx->sv_mu);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_tr2(fb_ctx *ctx, int B, const int *d_active)
+{
+    const int N = ctx->N, nb = (N + NB - 1) / NB, slabs = (N + TS - 1) / TS;
+    const bool in_smem = N <= 512;
+    const size_t smem = sizeof(double) * (NB * SLD + (in_smem ? (size_t)nb * NB * (TS + 1) : 0));
+    if (in_smem) FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_trsm_tr2<<<dim3(slabs, B), 256, smem, ctx->stream>>>(N, nb, ctx->sv_D, ctx->d_Y, d_active, in_smem ? nullptr : ctx->sv_Z,
+                                                         ctx->sv_tr2);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p, int has_prior,
+                    double *host_mu, double *host_chol, int *host_info)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0 || !ctx->d_Y) FB_FAIL(-30, "fb_gaussian_fit: fb_dht_setup (with Ycoef) has not been called");
+    if (B < 1 || !host_M || !host_j || !host_mu) FB_FAIL(-31, "fb_gaussian_fit: bad arguments");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    int rc = ensure_solver_ws(ctx, B);
+    if (rc) return rc;
+    int *d_info = ctx->sv_flags;          // [B]
+    FB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int) * B, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_M, host_M, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_j, host_j, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    const int nb = ((int)N + NB - 1) / NB;
+    if (has_prior) {
+        if (!host_p) FB_FAIL(-32, "fb_gaussian_fit: power spectrum missing");
+        for (size_t i = 0; i < (size_t)B * N; i++)
+            if (!(host_p[i] > 0.0)) FB_FAIL(FB_E_BADP, "bad value in power spectrum");        // statistical_models.py:688
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p, sizeof(double) * B * N, cudaMemcpyHostToDevice, ctx->stream));
+        k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, 0, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, nullptr, ctx->sv_D);
+    } else {
+        for (int b = 0; b < B; b++)
+            FB_CUDA(cudaMemcpyAsync(ctx->sv_D + (size_t)b * N * N, ctx->sv_M, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    rc = launch_factor_solve(ctx, B, nullptr, d_info);
+    if (rc) return rc;
+    FB_CUDA(cudaMemcpyAsync(host_mu, ctx->sv_mu, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_chol) FB_CUDA(cudaMemcpyAsync(host_chol, ctx->sv_D, sizeof(double) * B * N * N, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int> info(B);
+    FB_CUDA(cudaMemcpyAsync(info.data(), d_info, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    int worst = 0;
+    for (int b = 0; b < B; b++) {
+        if (host_info) host_info[b] = info[b];
+        if (info[b]) worst = FB_E_NOTPD;
+    }
+    if (worst) ctx->err = "Cholesky factorisation met a non-positive pivot";
+    return worst;
+}
+
+int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p_init,
+                         const double *host_alpha, const double *host_p0, const double *host_ldl, double tol, int max_iter,
+                         double *host_p, double *host_mu, double *host_chol, int *host_niter, int *host_converged,
+                         int *host_info, double *host_hist_p, double *host_hist_mu, int hist_cap)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0 || !ctx->d_Y) FB_FAIL(-30, "fb_frank_normal_loop: fb_dht_setup (with Ycoef) has not been called");
+    if (B < 1 || !host_M || !host_j || !host_p_init || !host_alpha || !host_p0 || !host_ldl || !host_p || !host_mu || !host_niter)
+        FB_FAIL(-31, "fb_frank_normal_loop: bad arguments");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    int rc = ensure_solver_ws(ctx, B);
+    if (rc) return rc;
+    for (size_t i = 0; i < (size_t)B * N; i++)
+        if (!(host_p_init[i] > 0.0)) FB_FAIL(FB_E_BADP, "bad value in power spectrum");
+    int *d_info = ctx->sv_flags, *d_active = d_info + B, *d_count = d_active + B, *d_conv = d_count + B, *d_nact = d_conv + B;
+    std::vector<int> ones(B, 1);
+    FB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int) * (4 * B + 8), ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(d_active, ones.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(d_nact, &B, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_M, host_M, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_j, host_j, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p_init, sizeof(double) * B * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_alpha, host_alpha, sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_p0, host_p0, sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_ldl, host_ldl, sizeof(double) * B * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
+    double *d_hist_p = nullptr, *d_hist_mu = nullptr;
+    if (hist_cap > 0 && host_hist_p && host_hist_mu) {
+        FB_CUDA(cudaMalloc(&d_hist_p, sizeof(double) * (size_t)B * hist_cap * N));
+        FB_CUDA(cudaMalloc(&d_hist_mu, sizeof(double) * (size_t)B * hist_cap * N));
+    }
+    const int nb = ((int)N + NB - 1) / NB;
+    // fit for the initial spectrum (the reference enters the loop with `fit` of p_init, radial_fitters.py:752-763)
+    k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, 0, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
+    rc = launch_factor_solve(ctx, B, d_active, d_info);
+    if (rc) return rc;
+    int *d_active_prev = nullptr;
+    if (d_hist_mu) FB_CUDA(cudaMalloc(&d_active_prev, sizeof(int) * B));
+
+    int n_active = B, it = 0;
+    const int poll = 8;
+    while (n_active > 0 && it <= max_iter + 1) {
+        for (int s = 0; s < poll; s++, it++) {
+            rc = launch_tr2(ctx, B, d_active);
+            if (rc) return rc;
+            if (d_active_prev) FB_CUDA(cudaMemcpyAsync(d_active_prev, d_active, sizeof(int) * B, cudaMemcpyDeviceToDevice, ctx->stream));
+            k_ps_update<<<B, 256, sizeof(double) * 2 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
+                                                                        ctx->sv_p0, ctx->sv_ldl, (int)(3 * N), tol, max_iter, ctx->sv_p,
+                                                                        d_active, d_count, d_conv, d_hist_p, hist_cap);
+            k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, 0, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
+            rc = launch_factor_solve(ctx, B, d_active, d_info);
+            if (rc) return rc;
+            if (d_hist_mu) k_copy_hist_mu<<<B, 256, 0, ctx->stream>>>((int)N, ctx->sv_mu, d_count, d_active_prev, d_hist_mu, hist_cap);
+            k_loop_gate<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, max_iter, d_count, d_conv, d_active, d_nact);
+        }
+        FB_CUDA(cudaMemcpyAsync(&n_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    FB_CUDA(cudaMemcpyAsync(host_p, ctx->sv_p, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(host_mu, ctx->sv_mu, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_chol) FB_CUDA(cudaMemcpyAsync(host_chol, ctx->sv_D, sizeof(double) * B * N * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(host_niter, d_count, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int> conv(B), info(B);
+    FB_CUDA(cudaMemcpyAsync(conv.data(), d_conv, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(info.data(), d_info, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_hist_p) {
+        FB_CUDA(cudaMemcpyAsync(host_hist_p, d_hist_p, sizeof(double) * (size_t)B * hist_cap * N, cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(host_hist_mu, d_hist_mu, sizeof(double) * (size_t)B * hist_cap * N, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (d_hist_p) { cudaFree(d_hist_p); cudaFree(d_hist_mu); cudaFree(d_active_prev); }
+    int worst = 0;
+    for (int b = 0; b < B; b++) {
+        if (host_converged) host_converged[b] = conv[b];
+        if (host_info) host_info[b] = info[b];
+        if (info[b]) worst = FB_E_NOTPD;
+    }
+    if (worst) ctx->err = "Cholesky factorisation met a non-positive pivot";
+    return worst;
+}
+
+}  // extern "C"

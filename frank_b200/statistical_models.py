@@ -238,3 +238,127 @@ class VisibilityMapping(object):
     @property
     def scale_height(self):
         return self._scale_height
+
+
+class GaussianModel(object):
+    r"""Posterior of the linear (Gaussian) brightness model: D^-1 = M + S(p)^-1, mu = D j.
+
+    API mirror of frank.statistical_models.GaussianModel (frank/statistical_models.py:571-904) for one
+    field (Nfields = 1).  The Cholesky factorisation and the solve run on the GPU
+    (frank_b200/csrc/fb_solve.cu); the O(N^2) results are held as NumPy arrays so the object pickles like
+    the reference's.
+
+    Parameters
+    ----------
+    DHT : DiscreteHankelTransform
+    M : array (N, N) or (Nf, N, N) ; j : array (N,) or (Nf, N)
+    p : array (N,), optional power spectrum
+    scale : optional per-channel scale factors (unit scale if None)
+    guess : accepted for signature compatibility (the reference only uses it to infer Nfields)
+    noise_likelihood : float
+    """
+
+    def __init__(self, DHT, M, j, p=None, scale=None, guess=None, Nfields=None, noise_likelihood=0, device=None,
+                 _solution=None):
+        self._DHT = DHT
+        M = np.asarray(M)
+        j = np.asarray(j)
+        if M.ndim == 2:
+            M = M.reshape(1, *M.shape)
+        if j.ndim == 1:
+            j = j.reshape(1, *j.shape)
+        Nf, Nr = j.shape
+        if Nfields is None:
+            Nfields = 1 if guess is None else np.asarray(guess).reshape(-1, Nr).shape[0]
+        if Nfields != 1:
+            raise NotImplementedError("frank_b200 solves single-field models (Nfields = 1)")
+        self._Nfields = 1
+        if p is not None:
+            p = np.asarray(p, dtype=np.float64).reshape(-1, Nr)
+            if np.any(p <= 0) or np.any(np.isnan(p)):                                  # :688-698
+                raise ValueError("Bad value in power spectrum. The power"
+                                 " spectrum must be positive and not contain"
+                                 " any NaN values. This is likely due to"
+                                 " your UVtable (incorrect units or weights), "
+                                 " or the deprojection being applied (incorrect"
+                                 " geometry and/or phase center). Else you may"
+                                 " want to adjust `rout` (ensure it is larger than"
+                                 " the source) or `n` (up to ~300).")
+        self._p = p
+        s = np.ones([Nf, 1]) if scale is None else np.asarray(scale, dtype=np.float64).reshape(Nf, -1)
+        # channel sum with scale factors (statistical_models.py:711-726)
+        self._M = np.zeros([Nr, Nr])
+        self._j = np.zeros(Nr)
+        for si, Mi, ji in zip(s, M, j):
+            self._j += si[0] * ji
+            self._M += si[0] * si[0] * Mi
+        self._like_noise = noise_likelihood
+        self._device = device
+        self._cov = None
+        self._Sinv_cache = None
+        if _solution is not None:
+            self._mu, self._U = _solution
+        else:
+            self._fit()
+
+    def _fit(self):
+        ctx = _lib.get_context(self._device)
+        ctx.dht_setup(self._DHT)
+        mu, chol, info, rc = ctx.gaussian_fit(self._M, self._j, None if self._p is None else self._p[0])
+        if rc == _lib.FB_E_NOTPD:
+            # the reference falls back to an SVD pseudo-inverse here (statistical_models.py:747-755)
+            raise np.linalg.LinAlgError("D^-1 = M + S^-1 is not positive definite (pivot {}); the SVD "
+                                        "pseudo-inverse fallback of the reference is not provided".format(int(info[0])))
+        self._mu = mu[0]
+        self._U = np.triu(chol[0])
+
+    @property
+    def _Sinv(self):
+        if self._p is None:
+            return None
+        if self._Sinv_cache is None:
+            Y = self._DHT.coefficients()
+            self._Sinv_cache = np.dot(Y.T * (1 / self._p[0]), Y)
+        return self._Sinv_cache
+
+    def Dsolve(self, b):
+        r"""D b through the GPU-computed Cholesky factor (post-fit helper, statistical_models.py:762-781)."""
+        import scipy.linalg
+        return scipy.linalg.cho_solve((self._U, False), b)
+
+    def log_likelihood(self, I=None):
+        r"""log P(V|p) (I is None) or log P(I, V|p), statistical_models.py:790-856."""
+        if I is None:
+            like = 0.5 * np.sum(self._j * self._mu)
+            if self._p is not None:
+                like += 0.5 * np.linalg.slogdet(self.Dsolve(self._Sinv))[1]
+        else:
+            Sinv = 0 if self._p is None else self._Sinv
+            like = np.sum(self._j * I) - 0.5 * np.dot(I, np.dot(self._M + Sinv, I))
+            if self._p is not None:
+                like += 0.5 * np.linalg.slogdet(2 * np.pi * Sinv)[1]
+        return like + self._like_noise
+
+    def solve_non_negative(self):
+        import scipy.optimize
+        Sinv = 0 if self._p is None else self._Sinv
+        return scipy.optimize.nnls(self._M + Sinv, self._j, maxiter=100 * len(self._j))[0]
+
+    def draw(self, N):
+        return np.random.multivariate_normal(self.mean.reshape(-1), self.covariance, N)
+
+    mean = property(lambda self: self._mu, doc="Posterior mean, Jy / sr")
+    MAP = property(lambda self: self._mu, doc="Posterior maximum, Jy / sr")
+    s_0 = property(lambda self: 0)
+    num_fields = property(lambda self: 1)
+    size = property(lambda self: self._DHT.size)
+
+    @property
+    def covariance(self):
+        if self._cov is None:
+            self._cov = self.Dsolve(np.eye(self.size))
+        return self._cov
+
+    @property
+    def power_spectrum(self):
+        return None if self._p is None else self._p.reshape(self.size)

@@ -98,6 +98,30 @@ int fb_last_map_timing(fb_ctx *ctx, double *out4);
  * Re V' [n] and perm [n] (sorted position -> index into the caller's arrays), device -> host. */
 int fb_debug_prepped(fb_ctx *ctx, int64_t n, double *host_a, double *host_kz, double *host_Vre, uint32_t *host_perm);
 
+/* ---- GaussianModel (frank/statistical_models.py:650-781), batched over B power spectra ---------
+ * D^-1 = M + Y^T diag(1/p_b) Y (has_prior != 0) or D^-1 = M; upper Cholesky D^-1 = U^T U (scipy.linalg.cho_factor
+ * default); mu_b = D j.  Host pointers: M [N*N], j [N], p [B*N]; outputs mu [B*N], chol [B*N*N] (optional: the
+ * upper triangle holds U), info [B] (0, or 1 + index of the first non-positive pivot).
+ * Returns FB_E_NOTPD when a factorisation failed (reference: LinAlgError -> SVD fallback, :747-755),
+ * FB_E_BADP for a non-positive / NaN spectrum (:688-698). */
+int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p, int has_prior,
+                    double *host_mu, double *host_chol, int *host_info);
+
+/* ---- FrankFitter._fit power-spectrum loop, Normal method (frank/radial_fitters.py:765-785) --------
+ * Device-resident loop, batched over B hyper-parameter points sharing M and j:
+ *     while not converged(p, p_old) and count <= max_iter:
+ *         p_old = p ; p = CriticalFilter.update_power_spectrum(fit) ; fit = GaussianModel(p) ; count += 1
+ * entered with the fit of p_init.  alpha [B], p0 [B] are the inverse-gamma prior parameters (filter.py:170-173);
+ * ldl [B*3*N] is the banded L D L^T factorisation of the pentadiagonal SPD matrix T + I of each point
+ * (filter.py:23-62, 155): D, then the first and second sub-diagonal of the unit lower factor.
+ * Outputs: p [B*N] final spectrum, mu [B*N] its posterior mean, chol [B*N*N] (optional), niter [B] = count,
+ * converged [B], info [B]; hist_p / hist_mu [B*hist_cap*N] (optional) receive every iteration's p and mu
+ * (FrankFitter's iteration_diagnostics). */
+int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p_init,
+                         const double *host_alpha, const double *host_p0, const double *host_ldl, double tol, int max_iter,
+                         double *host_p, double *host_mu, double *host_chol, int *host_niter, int *host_converged,
+                         int *host_info, double *host_hist_p, double *host_hist_mu, int hist_cap);
+
 /* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]). */
 int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out);
 

@@ -64,6 +64,20 @@ def synthetic(n_vis, N, Rmax=1.6, seed=12345, geom=(30., 40., 1e-3, -2e-3)):
     return u, v, V, w, g
 
 
+def self_noise(make_fitter, u, v, V, w, MAP, nperm=3):
+    """How far the REFERENCE's fitted profile moves (relative to its peak) when the same visibilities are
+    presented in another order or accumulated with another block_size -- the round-off floor any
+    re-implementation inherits (the posterior precision matrices have condition numbers 1e7..1e10)."""
+    worst = 0.0
+    for k in range(nperm):
+        perm = np.random.default_rng(1000 + k).permutation(len(u))
+        sol = make_fitter({}).fit(u[perm], v[perm], V[perm], w[perm] if np.ndim(w) else w)
+        worst = max(worst, np.max(np.abs(sol.MAP - MAP)) / np.max(np.abs(MAP)))
+    sol = make_fitter({'block_size': 20000}).fit(u, v, V, w)
+    worst = max(worst, np.max(np.abs(sol.MAP - MAP)) / np.max(np.abs(MAP)))
+    return worst
+
+
 def main():
     # ---- J0 -------------------------------------------------------------------------------
     rng = np.random.default_rng(7)
@@ -118,21 +132,26 @@ def main():
                         MAP_first=np.array(diag['MAP'][:3]), r=sol.r, q=sol.q, covariance=sol.covariance,
                         log_evidence=FF.log_evidence_laplace(), log_like=sol.log_likelihood(),
                         upred=uu, vpred=vv, Vpred=sol.predict(uu, vv),
-                        Vpred_deproj=sol.predict_deprojected(sol.q))
+                        Vpred_deproj=sol.predict_deprojected(sol.q),
+                        self_noise=self_noise(lambda kw: FrankFitter(1.6, N, g, alpha=1.05, weights_smooth=1e-4,
+                                                                     verbose=False, **kw), u, v, V, w, sol.MAP))
     # alpha / wsmooth variation (config 4 grid points)
     sweep = []
     for alpha, ws in [(1.3, 1e-2), (1.01, 1e-1)]:
         FF2 = FrankFitter(1.6, N, g, alpha=alpha, weights_smooth=ws, verbose=False,
                           store_iteration_diagnostics=True)
         s2 = FF2.fit(u, v, V, w)
-        sweep.append((alpha, ws, FF2.iteration_diagnostics['num_iterations'], s2.MAP, s2.power_spectrum))
+        sn = self_noise(lambda kw: FrankFitter(1.6, N, g, alpha=alpha, weights_smooth=ws, verbose=False, **kw),
+                        u, v, V, w, s2.MAP)
+        sweep.append((alpha, ws, FF2.iteration_diagnostics['num_iterations'], s2.MAP, s2.power_spectrum, sn))
     np.savez_compressed(os.path.join(OUT, 'fit_sweep.npz'), alpha=[s[0] for s in sweep], ws=[s[1] for s in sweep],
                         num_iterations=[s[2] for s in sweep], MAP=np.array([s[3] for s in sweep]),
-                        power_spectrum=np.array([s[4] for s in sweep]))
+                        power_spectrum=np.array([s[4] for s in sweep]), self_noise=np.array([s[5] for s in sweep]))
     # non-parametric (no prior) fit
     FB = FourierBesselFitter(1.6, 20, g, verbose=False)
     sb = FB.fit(u, v, V, w)
-    np.savez_compressed(os.path.join(OUT, 'fit_fourier_bessel.npz'), MAP=sb.MAP)
+    np.savez_compressed(os.path.join(OUT, 'fit_fourier_bessel.npz'), MAP=sb.MAP,
+                        self_noise=self_noise(lambda kw: FourierBesselFitter(1.6, 20, g, verbose=False, **kw), u, v, V, w, sb.MAP))
 
     # ---- LogNormal fit --------------------------------------------------------------------
     Nl = 40
@@ -143,14 +162,18 @@ def main():
     dl = FL.iteration_diagnostics
     np.savez_compressed(os.path.join(OUT, 'fit_lognormal.npz'), N=Nl, u=ul, v=vl, V=Vl, w=wl, M=FL._M, j=FL._j, MAP=sl.MAP, power_spectrum=sl.power_spectrum,
                         num_iterations=dl['num_iterations'], s_MAP=sl._fit.MAP,
-                        p_first=np.array(dl['power_spectrum'][:3]), MAP_first=np.array(dl['MAP'][:3]))
+                        p_first=np.array(dl['power_spectrum'][:3]), MAP_first=np.array(dl['MAP'][:3]),
+                        self_noise=self_noise(lambda kw: FrankFitter(1.6, Nl, g, alpha=1.3, weights_smooth=1e-2, method='LogNormal',
+                                                                     verbose=False, **kw), ul, vl, Vl, wl, sl.MAP, nperm=1))
 
     # ---- debris Normal fit ----------------------------------------------------------------
     FD = FrankDebrisFitter(1.6, 40, g, lambda r: 0.05 * r, alpha=1.3, weights_smooth=1e-2, verbose=False,
                            store_iteration_diagnostics=True)
     sd = FD.fit(ul, vl, Vl, wl)
     np.savez_compressed(os.path.join(OUT, 'fit_debris.npz'), N=40, MAP=sd.MAP, power_spectrum=sd.power_spectrum,
-                        num_iterations=FD.iteration_diagnostics['num_iterations'])
+                        num_iterations=FD.iteration_diagnostics['num_iterations'],
+                        self_noise=self_noise(lambda kw: FrankDebrisFitter(1.6, 40, g, lambda r: 0.05 * r, alpha=1.3,
+                                                                           weights_smooth=1e-2, verbose=False, **kw), ul, vl, Vl, wl, sd.MAP))
 
     # ---- AS 209 subsample (196 visibilities), N=20 -------------------------------------
     ua, va, re, im, wa = np.genfromtxt(os.path.join(REF, 'docs/tutorials/test_datafile.txt')).T
@@ -162,7 +185,10 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'fit_as209sub.npz'), u=ua, v=va, V=Va, w=wa,
                         geom=np.array([ga.inc, ga.PA, ga.dRA, ga.dDec]), MAP=sa.MAP,
                         power_spectrum=sa.power_spectrum, M=FA._M, j=FA._j, H0=FA._H0,
-                        num_iterations=FA.iteration_diagnostics['num_iterations'])
+                        num_iterations=FA.iteration_diagnostics['num_iterations'],
+                        self_noise=self_noise(lambda kw: FrankFitter(1.6, 20, ga, alpha=1.05, weights_smooth=1e-2, verbose=False,
+                                                                     check_qbounds=False, convergence_failure='warn', **kw),
+                                              ua, va, Va, wa, sa.MAP))
 
     # ---- UV binner ------------------------------------------------------------------------
     uvd = out['q']

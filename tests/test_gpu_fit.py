@@ -1,0 +1,192 @@
+"""GPU parity tests of the solver path (GaussianModel, CriticalFilter, FrankFitter) against fixtures produced by the
+unmodified reference and against the CPU oracle.  Run on a B200: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from oracle import frank_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+# Fitted profiles are compared relative to the profile's peak, as the north star states it (1e-8 of peak).
+# The posterior precision matrices of these fits have condition numbers 1e7..1e10, so round-off in M and j is
+# amplified: the REFERENCE run against itself with its visibilities permuted (or with another block_size) moves
+# its own fitted profile by the `self_noise` stored in each fixture (tests/golden/make_golden.py; 8e-9 .. 7e-8 of
+# peak for the Normal fits).  End-to-end fits are held to max(1e-8, 4 x that self-noise); where only the solver
+# is compared (same M and j as the reference) the bar is the plain 1e-8.
+SOLVER_TOL = 1e-8
+
+
+def peak_tol(fixture, i=None):
+    sn = float(fixture['self_noise'] if i is None else fixture['self_noise'][i])
+    return max(1e-8, 4.0 * sn)
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def peak_err(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+@pytest.fixture(scope='module')
+def fb():
+    from frank_b200 import _lib
+    from frank_b200.geometry import FixedGeometry
+    from frank_b200.hankel import DiscreteHankelTransform
+    from frank_b200.statistical_models import VisibilityMapping, GaussianModel
+    from frank_b200.filter import CriticalFilter
+    from frank_b200.radial_fitters import FrankFitter, FourierBesselFitter
+    from frank_b200.debris_fitters import FrankDebrisFitter
+    from frank_b200.constants import rad_to_arcsec
+
+    class NS:
+        pass
+    ns = NS()
+    ns.lib, ns.FixedGeometry, ns.DHT, ns.VM, ns.GaussianModel = _lib, FixedGeometry, DiscreteHankelTransform, VisibilityMapping, GaussianModel
+    ns.CriticalFilter, ns.FrankFitter, ns.FourierBesselFitter, ns.FrankDebrisFitter, ns.r2a = CriticalFilter, FrankFitter, FourierBesselFitter, FrankDebrisFitter, rad_to_arcsec
+    return ns
+
+
+def geom_of(fb, g):
+    return fb.FixedGeometry(*[float(x) for x in g['geom']])
+
+
+def test_gaussian_model_vs_oracle(fb, golden):
+    """One GaussianModel solve (statistical_models.py:700-745) on the reference's M, j."""
+    g = golden('mapping.npz')
+    N = int(g['N'])
+    dht, odht = fb.DHT(1.6 / fb.r2a, N), fo.DHTTables(1.6 / fo.RAD_TO_ARCSEC, N)
+    p = 1e3 * (odht.q / odht.q[0]) ** -2
+    ref = fo.GaussianSolve(odht, g['M_opt_thick'], g['j_opt_thick'], p)
+    got = fb.GaussianModel(dht, g['M_opt_thick'], g['j_opt_thick'], p)
+    assert rel(got.MAP, ref.mu) < 1e-9
+    assert rel(got._U, np.triu(ref.chol[0])) < 1e-11
+    assert rel(got.covariance, ref.Dsolve(np.eye(N))) < 1e-8
+    with pytest.raises(ValueError):
+        fb.GaussianModel(dht, g['M_opt_thick'], g['j_opt_thick'], -p)
+
+
+def test_update_power_spectrum_step(fb, golden):
+    """One CriticalFilter.update_power_spectrum step (filter.py:154-177) against the oracle."""
+    g = golden('mapping.npz')
+    N = int(g['N'])
+    dht, odht = fb.DHT(1.6 / fb.r2a, N), fo.DHTTables(1.6 / fo.RAD_TO_ARCSEC, N)
+    p = 1e3 * (odht.q / odht.q[0]) ** -2
+    ofit = fo.GaussianSolve(odht, g['M_opt_thick'], g['j_opt_thick'], p)
+    pref = fo.update_power_spectrum(odht, ofit, fo.smoothing_matrix(odht, 1e-4), 1.05, 1e-15)
+    filt = fb.CriticalFilter(dht, 1.05, 1e-15, 1e-4)
+    fit = fb.GaussianModel(dht, g['M_opt_thick'], g['j_opt_thick'], p)
+    pgot = filt.update_power_spectrum(fit)
+    assert np.max(np.abs(pgot / pref - 1)) < 1e-9
+
+
+def test_frank_fitter_normal_vs_reference_golden(fb, golden):
+    """FrankFitter(method='Normal').fit end to end: same iteration count, profile within 1e-8 of peak."""
+    g, f = golden('mapping.npz'), golden('fit_normal.npz')
+    FF = fb.FrankFitter(1.6, int(g['N']), geom_of(fb, g), alpha=1.05, weights_smooth=1e-4, verbose=False,
+                        store_iteration_diagnostics=True)
+    sol = FF.fit(g['u'], g['v'], g['V'], g['w'])
+    d = FF.iteration_diagnostics
+    assert d['num_iterations'] == int(f['num_iterations'])
+    assert peak_err(sol.MAP, f['MAP']) <= peak_tol(f)
+    assert peak_err(sol.power_spectrum, f['power_spectrum']) <= peak_tol(f)
+    assert np.max(np.abs(sol.power_spectrum / f['power_spectrum'] - 1)) <= 1e-6
+    assert rel(np.array(d['power_spectrum'][:3]), f['p_first']) < 1e-9
+    assert rel(np.array(d['MAP'][:3]), f['MAP_first']) < 1e-9
+    assert len(d['MAP']) == d['num_iterations']
+    assert np.array_equal(sol.r, f['r']) and np.array_equal(sol.q, f['q'])
+    assert rel(sol.covariance, f['covariance']) < 1e-6
+    assert abs(FF.log_evidence_laplace() - float(f['log_evidence'])) < 1e-6 * abs(float(f['log_evidence']))
+    assert abs(sol.log_likelihood() - float(f['log_like'])) < 1e-8 * abs(float(f['log_like']))
+
+
+def test_solver_loop_on_reference_matrices(fb, golden):
+    """The device power-spectrum loop fed with the REFERENCE's M and j: same iteration count, profile and
+    spectrum within 1e-8 of peak (isolates the solver from the mapping)."""
+    g, f = golden('mapping.npz'), golden('fit_normal.npz')
+    N = int(g['N'])
+    dht = fb.DHT(1.6 / fb.r2a, N)
+    FF = fb.FrankFitter(1.6, N, geom_of(fb, g), alpha=1.05, weights_smooth=1e-4, verbose=False,
+                        store_iteration_diagnostics=True)
+    sol = FF.fit_preprocessed({'hash': [False, dht, geom_of(fb, g), 'opt_thick', None], 'M': g['M_opt_thick'],
+                               'j': g['j_opt_thick'], 'null_likelihood': float(g['H0_opt_thick'])})
+    assert FF.iteration_diagnostics['num_iterations'] == int(f['num_iterations'])
+    assert peak_err(sol.MAP, f['MAP']) <= SOLVER_TOL
+    assert np.max(np.abs(sol.power_spectrum / f['power_spectrum'] - 1)) <= 1e-6
+
+
+def test_two_stage_fit_is_bit_identical(fb, golden):
+    """frank/tests.py:296-314: fit() and preprocess_visibilities() + fit_preprocessed() agree exactly."""
+    g = golden('mapping.npz')
+    FF = fb.FrankFitter(1.6, int(g['N']), geom_of(fb, g), alpha=1.3, weights_smooth=1e-2, verbose=False)
+    sol1 = FF.fit(g['u'], g['v'], g['V'], g['w'])
+    pre = FF.preprocess_visibilities(g['u'], g['v'], g['V'], g['w'])
+    sol2 = FF.fit_preprocessed(pre)
+    assert np.array_equal(sol1.MAP, sol2.MAP) and np.array_equal(sol1.power_spectrum, sol2.power_spectrum)
+
+
+def test_sweep_points_vs_reference_golden(fb, golden):
+    g, f = golden('mapping.npz'), golden('fit_sweep.npz')
+    for i in range(len(f['alpha'])):
+        FF = fb.FrankFitter(1.6, int(g['N']), geom_of(fb, g), alpha=float(f['alpha'][i]), weights_smooth=float(f['ws'][i]),
+                            verbose=False, store_iteration_diagnostics=True)
+        sol = FF.fit(g['u'], g['v'], g['V'], g['w'])
+        assert FF.iteration_diagnostics['num_iterations'] == int(f['num_iterations'][i])
+        assert peak_err(sol.MAP, f['MAP'][i]) <= peak_tol(f, i)
+
+
+def test_batched_sweep_matches_single_fits(fb, golden):
+    """Config 4 shape: a batch of (alpha, wsmooth) points in one device loop equals the one-at-a-time fits."""
+    g = golden('mapping.npz')
+    N = int(g['N'])
+    dht = fb.DHT(1.6 / fb.r2a, N)
+    ctx = fb.lib.get_context()
+    ctx.dht_setup(dht)
+    alphas, wss = [1.05, 1.3, 1.5, 1.2], [1e-4, 1e-2, 1e-1, 1e-3]
+    filts = [fb.CriticalFilter(dht, a, 1e-15, w) for a, w in zip(alphas, wss)]
+    FF = fb.FrankFitter(1.6, N, geom_of(fb, g), verbose=False)
+    FF._build_matrices({'hash': [False, dht, geom_of(fb, g), 'opt_thick', None], 'M': g['M_opt_thick'], 'j': g['j_opt_thick'],
+                        'null_likelihood': 0.0})
+    p_init = FF._starting_spectrum()
+    out = ctx.frank_normal_loop(g['M_opt_thick'], g['j_opt_thick'], np.tile(p_init, (4, 1)), np.array(alphas),
+                                np.full(4, 1e-15), np.stack([f._ldl for f in filts]), 1e-3, 2000)
+    for b in range(4):
+        one = ctx.frank_normal_loop(g['M_opt_thick'], g['j_opt_thick'], p_init, alphas[b], 1e-15, filts[b]._ldl, 1e-3, 2000)
+        assert out['niter'][b] == one['niter'][0]
+        assert np.array_equal(out['p'][b], one['p'][0]) and np.array_equal(out['mu'][b], one['mu'][0])
+
+
+def test_as209_subsample_vs_reference_golden(fb, golden):
+    f = golden('fit_as209sub.npz')
+    FF = fb.FrankFitter(1.6, 20, geom_of(fb, f), alpha=1.05, weights_smooth=1e-2, verbose=False,
+                        store_iteration_diagnostics=True, check_qbounds=False, convergence_failure='warn')
+    sol = FF.fit(f['u'], f['v'], f['V'], f['w'])
+    assert FF.iteration_diagnostics['num_iterations'] == int(f['num_iterations'])
+    assert np.max(np.abs(FF._M - f['M'])) <= 1e-14 * np.max(np.abs(f['M']))
+    assert peak_err(sol.MAP, f['MAP']) <= peak_tol(f)
+
+
+def test_fourier_bessel_and_debris_vs_reference_golden(fb, golden):
+    g = golden('mapping.npz')
+    FB = fb.FourierBesselFitter(1.6, 20, geom_of(fb, g), verbose=False)
+    sol = FB.fit(g['u'], g['v'], g['V'], g['w'])
+    assert rel(sol.MAP, golden('fit_fourier_bessel.npz')['MAP']) < 1e-9
+    fl, fd = golden('fit_lognormal.npz'), golden('fit_debris.npz')
+    FD = fb.FrankDebrisFitter(1.6, 40, geom_of(fb, g), lambda r: 0.05 * r, alpha=1.3, weights_smooth=1e-2, verbose=False,
+                              store_iteration_diagnostics=True)
+    sd = FD.fit(fl['u'], fl['v'], fl['V'], fl['w'])
+    assert FD.iteration_diagnostics['num_iterations'] == int(fd['num_iterations'])
+    assert peak_err(sd.MAP, fd['MAP']) <= peak_tol(fd)
+
+
+def test_non_convergence_policy(fb, golden):
+    g = golden('mapping.npz')
+    FF = fb.FrankFitter(1.6, int(g['N']), geom_of(fb, g), verbose=False, max_iter=5)
+    with pytest.raises(RuntimeError):
+        FF.fit(g['u'], g['v'], g['V'], g['w'])
+    FF = fb.FrankFitter(1.6, int(g['N']), geom_of(fb, g), verbose=False, max_iter=5, convergence_failure='ignore',
+                        store_iteration_diagnostics=True)
+    FF.fit(g['u'], g['v'], g['V'], g['w'])
+    assert FF.iteration_diagnostics['num_iterations'] == 6      # count <= max_iter lets max_iter + 1 updates through

@@ -1,0 +1,199 @@
+"""GPU parity tests of the visibility-mapping path (through the C ABI) against the CPU oracle and against
+fixtures produced by the unmodified reference.  Run on a B200: pytest -m gpu."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import frank_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EPS = np.finfo(np.float64).eps
+
+
+def gram_ok(M, Mref, rtol=1e-10, c_eps=16):
+    """Per-entry criterion of the north star with the floor any float64 summation needs:
+    |dM_kl| <= 1e-10 |M_kl| + c_eps * eps * sqrt(M_kk M_ll).
+    The second term is the Cauchy-Schwarz scale of the k,l dot product; entries that cancel to 1e-7..1e-9 of it
+    change by more than 1e-10 relative when the REFERENCE itself is re-run with its visibilities permuted or
+    with another block_size ('Parity floor')."""
+    d = np.sqrt(np.abs(np.diag(Mref)))
+    tol = rtol * np.abs(Mref) + c_eps * EPS * np.outer(d, d)
+    return float(np.max(np.abs(M - Mref) / tol))
+
+
+def vec_ok(j, jref, M, H0scale, rtol=1e-10, c_eps=16):
+    tol = rtol * np.abs(jref) + c_eps * EPS * np.sqrt(np.abs(np.diag(M))) * H0scale
+    return float(np.max(np.abs(j - jref) / tol))
+
+
+@pytest.fixture(scope='module')
+def fb():
+    import frank_b200  # noqa: F401
+    from frank_b200 import _lib
+    from frank_b200.geometry import FixedGeometry
+    from frank_b200.hankel import DiscreteHankelTransform
+    from frank_b200.statistical_models import VisibilityMapping
+    from frank_b200.constants import rad_to_arcsec
+
+    class NS:
+        pass
+    ns = NS()
+    ns.lib, ns.FixedGeometry, ns.DHT, ns.VM, ns.r2a = _lib, FixedGeometry, DiscreteHankelTransform, VisibilityMapping, rad_to_arcsec
+    return ns
+
+
+def mapping_from_golden(fb, g, **kw):
+    inc, PA, dRA, dDec = [float(x) for x in g['geom']]
+    dht = fb.DHT(float(g['Rmax']) / fb.r2a, int(g['N']))
+    vm = fb.VM(dht, fb.FixedGeometry(inc, PA, dRA, dDec), verbose=False, **kw)
+    return dht, vm
+
+
+def test_j0_device_accuracy(fb, golden):
+    """The device J0 (Taylor table) against the exactly rounded function and against SciPy's J0 (reference)."""
+    g = golden('j0_golden.npz')
+    ctx = fb.lib.get_context()
+    dht = fb.DHT(1.6 / fb.r2a, 2000)
+    ctx.dht_setup(dht)
+    x = g['x'][g['x'] < dht._j_nk[-1]]
+    got = ctx.debug_j0(x)
+    subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle')])
+    lib = ctypes.CDLL(os.path.join(ROOT, 'oracle', '_build', 'liboracle_j0.so'))
+    exact = np.empty_like(x)
+    lib.oracle_j0_exact_array(x.ctypes.data_as(ctypes.c_void_p), exact.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(x.size))
+    assert np.max(np.abs(got - exact)) <= 1.2e-16           # half an ulp of values <= 1
+    big = x > 30
+    assert np.max(np.abs(got[big] - exact[big])) <= 3e-17
+    ref = g['j0'][g['x'] < dht._j_nk[-1]]
+    assert np.max(np.abs(got - ref)) <= 5e-16                # SciPy's own error for x <= 30
+    assert np.max(np.abs(got[big] - ref[big])) <= 1e-16
+
+
+def test_prepass_bits(fb, golden):
+    """Deprojection / hypot / kz bit-identical to NumPy's; Re V' to 2 ulp (sin/cos differ by an ulp)."""
+    g = golden('mapping.npz')
+    dht, vm = mapping_from_golden(fb, g)
+    vm.map_visibilities(g['u'], g['v'], g['V'], g['w'])
+    n = len(g['u'])
+    a, kz, Vre, perm = fb.lib.get_context().debug_prepped(n)
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    assert np.array_equal(a, (g['q'] * (1. / dht.Qmax))[perm])
+    assert np.array_equal(kz, g['wp'][perm])
+    assert np.max(np.abs(Vre - g['Vp'].real[perm])) <= 4 * EPS * np.max(np.abs(g['Vp'].real))
+    assert np.all(np.diff(a) >= -a.max() / 60000)          # sorted by baseline bin
+
+
+@pytest.mark.parametrize('model', ['opt_thick', 'opt_thin'])
+def test_mapping_vs_reference_golden(fb, golden, model):
+    g = golden('mapping.npz')
+    dht, vm = mapping_from_golden(fb, g, vis_model=model)
+    m = vm.map_visibilities(g['u'], g['v'], g['V'], g['w'])
+    assert m['mult_freq'] is False and m['channels'] is None and m['M'].shape == (dht.size, dht.size)
+    assert gram_ok(m['M'], g[f'M_{model}']) <= 1.0
+    assert np.max(np.abs(m['M'] - g[f'M_{model}'])) <= 1e-14 * np.max(np.abs(g[f'M_{model}']))
+    assert np.max(np.abs(m['j'] - g[f'j_{model}'])) <= 1e-13 * np.max(np.abs(g[f'j_{model}']))
+    assert abs(m['null_likelihood'] - float(g[f'H0_{model}'])) <= 1e-12 * abs(float(g[f'H0_{model}']))
+    assert np.array_equal(m['M'], m['M'].T)
+
+
+def test_mapping_debris_scalar_multi(fb, golden):
+    g = golden('mapping.npz')
+    dht, vm = mapping_from_golden(fb, g, vis_model='debris', scale_height=lambda r: 0.05 * r)
+    assert np.array_equal(vm._H2, g['H2_debris'])
+    m = vm.map_visibilities(g['u'], g['v'], g['V'], g['w'])
+    assert gram_ok(m['M'], g['M_debris']) <= 1.0
+    assert np.max(np.abs(m['j'] - g['j_debris'])) <= 1e-13 * np.max(np.abs(g['j_debris']))
+    dht, vm = mapping_from_golden(fb, g)
+    m = vm.map_visibilities(g['u'], g['v'], g['V'], 2.5)     # scalar weights (radial_fitters.py:544)
+    assert gram_ok(m['M'], g['M_scalar_w']) <= 1.0
+    assert abs(m['null_likelihood'] - float(g['H0_scalar_w'])) <= 1e-12 * abs(float(g['H0_scalar_w']))
+    m = vm.map_visibilities(g['u'], g['v'], g['V'], g['w'], frequencies=g['freqs'])
+    assert m['mult_freq'] is True and np.array_equal(m['channels'], g['channels'])
+    for c in range(len(g['channels'])):
+        assert gram_ok(m['M'][c], g['M_multi'][c]) <= 1.0
+    assert np.max(np.abs(m['j'] - g['j_multi'])) <= 1e-13 * np.max(np.abs(g['j_multi']))
+    assert abs(m['null_likelihood'] - float(g['H0_multi'])) <= 1e-12 * abs(float(g['H0_multi']))
+
+
+def test_qbounds_error(fb, golden):
+    """frank/tests.py:415-431: data beyond the last collocation point raise ValueError."""
+    g = golden('mapping.npz')
+    inc, PA, dRA, dDec = [float(x) for x in g['geom']]
+    vm = fb.VM(fb.DHT(1.6 / fb.r2a, 20), fb.FixedGeometry(inc, PA, dRA, dDec), verbose=False)
+    with pytest.raises(ValueError):
+        vm.map_visibilities(g['u'], g['v'], g['V'], g['w'])
+    vm.check_qbounds = False
+    vm.map_visibilities(g['u'], g['v'], g['V'], g['w'])     # FourierBesselFitter path: no check
+
+
+@pytest.mark.parametrize('n,N', [(1, 20), (63, 20), (64, 33), (65, 100), (5000, 300), (40000, 500), (3000, 1000)])
+def test_mapping_vs_oracle_sizes(fb, n, N):
+    """Ragged / tiny / multi-panel shapes against the CPU oracle on the same seeded inputs."""
+    u, v, V, w, odht = fo.synthetic_disc(n, N, seed=100 + n)
+    ref = fo.map_visibilities(odht, u, v, V, w, 30., 40., 1e-3, -2e-3)
+    vm = fb.VM(fb.DHT(1.6 / fb.r2a, N), fb.FixedGeometry(30., 40., 1e-3, -2e-3), verbose=False)
+    m = vm.map_visibilities(u, v, V, w)
+    assert gram_ok(m['M'], ref['M']) <= 1.0
+    assert np.max(np.abs(m['M'] - ref['M'])) <= 2e-14 * np.max(np.abs(ref['M']))
+    assert np.max(np.abs(m['j'] - ref['j'])) <= 1e-12 * np.max(np.abs(ref['j']))
+    assert abs(m['null_likelihood'] - ref['null_likelihood']) <= 1e-12 * abs(ref['null_likelihood'])
+
+
+def test_mapping_empty(fb):
+    vm = fb.VM(fb.DHT(1.6 / fb.r2a, 40), fb.FixedGeometry(30., 40.), verbose=False, check_qbounds=False)
+    m = vm.map_visibilities(np.zeros(0), np.zeros(0), np.zeros(0, dtype=complex), np.zeros(0))
+    assert np.all(m['M'] == 0) and np.all(m['j'] == 0) and m['null_likelihood'] == 0
+
+
+def test_device_and_host_entry_points_agree(fb):
+    import torch
+    u, v, V, w, odht = fo.synthetic_disc(20000, 120, seed=5)
+    vm = fb.VM(fb.DHT(1.6 / fb.r2a, 120), fb.FixedGeometry(30., 40., 1e-3, -2e-3), verbose=False)
+    mh = vm.map_visibilities(u, v, V, w)
+    md = vm.map_visibilities(*[torch.from_numpy(x).cuda() for x in (u, v, V, w)])
+    assert np.array_equal(mh['M'], md['M']) and np.array_equal(mh['j'], md['j'])
+    assert mh['null_likelihood'] == md['null_likelihood']
+    # deterministic: a second call gives the same bits (frank/tests.py:296-314 relies on this)
+    m2 = vm.map_visibilities(u, v, V, w)
+    assert np.array_equal(mh['M'], m2['M']) and np.array_equal(mh['j'], m2['j'])
+
+
+def test_full_size_properties(fb):
+    """BASELINE.json config 2 shape (1e7 visibilities, N = 300) through size-independent properties:
+    linearity in the weights, additivity over a split of the visibilities, symmetry, positive diagonal,
+    and agreement of a 2e4-visibility slice with the oracle."""
+    import torch
+    n, N = 10_000_000, 300
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    dht = fb.DHT(1.6 / fb.r2a, N)
+    q = 0.98 * dht.q[-1] * torch.sqrt(torch.rand(n, device='cuda', dtype=torch.float64, generator=gen))
+    th = 2 * np.pi * torch.rand(n, device='cuda', dtype=torch.float64, generator=gen)
+    u, v = q * torch.cos(th), q * torch.sin(th)
+    V = torch.complex(torch.exp(-(q / 1e6) ** 2), 0.1 * torch.sin(q / 3e5))
+    w = 1e4 * (0.5 + 1.5 * torch.rand(n, device='cuda', dtype=torch.float64, generator=gen))
+    vm = fb.VM(dht, fb.FixedGeometry(30., 40., 1e-3, -2e-3), verbose=False, check_qbounds=False)
+    full = vm.map_visibilities(u, v, V, w)
+    M = full['M']
+    assert np.array_equal(M, M.T) and np.all(np.diag(M) > 0)
+    half = n // 2 + 12345
+    a = vm.map_visibilities(u[:half], v[:half], V[:half], w[:half])
+    b = vm.map_visibilities(u[half:], v[half:], V[half:], w[half:])
+    d = np.sqrt(np.diag(M))
+    # float64 accumulation of ~7e4 DMMA steps per accumulator: random-walk round-off ~ eps * sqrt(7e4) / 3.5 = 75 eps
+    # relative to the Cauchy-Schwarz scale of each entry (the reference's chunked dgemm accumulation is at ~50 eps)
+    SUM_TOL = 256 * EPS
+    assert np.max(np.abs(a['M'] + b['M'] - M) / np.outer(d, d)) < SUM_TOL
+    assert np.max(np.abs(a['j'] + b['j'] - full['j'])) < 1e-12 * np.max(np.abs(full['j']))
+    assert abs(a['null_likelihood'] + b['null_likelihood'] - full['null_likelihood']) < 1e-12 * abs(full['null_likelihood'])
+    w2 = vm.map_visibilities(u, v, V, 2.0 * w)
+    assert np.array_equal(w2['M'], 2.0 * M) or np.max(np.abs(w2['M'] - 2.0 * M) / np.outer(d, d)) < SUM_TOL
+    k = 20000
+    us, vs, Vs, ws = [x[:k].cpu().numpy() for x in (u, v, V, w)]
+    ref = fo.map_visibilities(fo.DHTTables(1.6 / fo.RAD_TO_ARCSEC, N), us, vs, Vs, ws, 30., 40., 1e-3, -2e-3, check_qbounds=False)
+    got = vm.map_visibilities(us, vs, Vs, ws)
+    assert gram_ok(got['M'], ref['M']) <= 1.0
