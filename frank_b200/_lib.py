@@ -38,6 +38,8 @@ _SIGNATURES = {
     'fb_map_visibilities_host': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_i, _c_p, _c_i, ctypes.POINTER(FBGeometry),
                                   _c_i, _c_d, _c_p, _c_i, _c_d, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_last_map_timing': ([_c_p, _c_p], _c_i),
+    'fb_timer_start': ([_c_p], _c_i),
+    'fb_timer_stop': ([_c_p, _c_p], _c_i),
     'fb_debug_prepped': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
@@ -137,6 +139,15 @@ class Context(object):
                 _ptr(M), _ptr(j), _ptr(H0), _ptr(qmm))
         self.check(rc, 'fb_map_visibilities')
         return rc, qmm[0], qmm[1]
+
+    def timer_start(self):
+        self.check(self._lib.fb_timer_start(self._h), 'fb_timer_start')
+
+    def timer_stop(self):
+        """Device milliseconds on the library stream since timer_start (CUDA events)."""
+        t = np.zeros(1)
+        self.check(self._lib.fb_timer_stop(self._h, _ptr(t)), 'fb_timer_stop')
+        return float(t[0])
 
     def last_map_timing(self):
         t = np.zeros(4)

@@ -238,6 +238,26 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
     return 0;
 }
 
+int fb_timer_start(fb_ctx *ctx)
+{
+    if (!ctx) return -1;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->tev[0]) { FB_CUDA(cudaEventCreate(&ctx->tev[0])); FB_CUDA(cudaEventCreate(&ctx->tev[1])); }
+    FB_CUDA(cudaEventRecord(ctx->tev[0], ctx->stream));
+    return 0;
+}
+
+int fb_timer_stop(fb_ctx *ctx, double *elapsed_ms)
+{
+    if (!ctx || !elapsed_ms || !ctx->tev[0]) return -1;
+    FB_CUDA(cudaEventRecord(ctx->tev[1], ctx->stream));
+    FB_CUDA(cudaEventSynchronize(ctx->tev[1]));
+    float ms = 0;
+    FB_CUDA(cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[1]));
+    *elapsed_ms = ms;
+    return 0;
+}
+
 int fb_last_map_timing(fb_ctx *ctx, double *out4)
 {
     if (!ctx || !out4) return -1;

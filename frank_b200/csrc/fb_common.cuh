@@ -82,6 +82,7 @@ struct fb_ctx {
     double *sv_ldl = nullptr, *sv_M = nullptr, *sv_j = nullptr, *sv_Z = nullptr;
     int *sv_flags = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t tev[2] = {};
     double timing[4] = {0, 0, 0, 0};
     int num_sms = 148;
     int64_t last_n = 0;

@@ -93,6 +93,11 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
  * out[2] split-K reduction + scaling, out[3] host<->device copies (host entry point only). */
 int fb_last_map_timing(fb_ctx *ctx, double *out4);
 
+/* CUDA-event stopwatch on the context's stream (all library kernels are launched on it): start records an event,
+ * stop records a second one, waits for it and returns the device time between them in milliseconds. */
+int fb_timer_start(fb_ctx *ctx);
+int fb_timer_stop(fb_ctx *ctx, double *elapsed_ms);
+
 /* Pre-passed visibilities of the most recent map call in the (baseline-sorted) order the Gram kernel reads
  * them, for parity tests of the geometry pre-pass (geometry.py:202-236): a = q * (1/Qmax) [n], kz [n],
  * Re V' [n] and perm [n] (sorted position -> index into the caller's arrays), device -> host. */

@@ -1,0 +1,86 @@
+"""CPU-only tests of the host-side mirror: DHT tables, geometry helpers, smoothing-matrix bands, API surface."""
+import numpy as np
+import pytest
+
+from oracle import frank_oracle as fo
+from frank_b200.constants import rad_to_arcsec
+from frank_b200.filter import banded_ldl, smoothing_bands, spectral_smoothing_matrix
+from frank_b200.geometry import FixedGeometry, apply_phase_shift, deproject
+from frank_b200.hankel import DiscreteHankelTransform
+
+
+def test_dht_matches_reference_golden(golden):
+    g = golden('dht.npz')
+    d = DiscreteHankelTransform(float(g['Rmax']), int(g['N']))
+    for name, got in [('r', d.r), ('q', d.q), ('Ykm', d._Ykm), ('scale_factor', d._scale_factor),
+                      ('coeff', d.coefficients()), ('coeff_qs', d.coefficients(g['qs'])), ('Hf', d.transform(g['f'])),
+                      ('Hf_qs', d.transform(g['f'], g['qs']))]:
+        assert np.array_equal(got, g[name]), name
+    assert d.Qmax == float(g['Qmax']) and d.size == int(g['N']) and d.order == 0
+    r, q = DiscreteHankelTransform.get_collocation_points(float(g['Rmax']), int(g['N']))
+    assert np.array_equal(r, g['r']) and np.array_equal(q, g['q'])
+    with pytest.raises(AttributeError):
+        d.coefficients(direction='sideways')
+
+
+def test_hankel_gauss_pair():
+    """frank/tests.py:37-94: exp(-r^2/2) <-> 2 pi exp(-(2 pi q)^2/2)."""
+    d = DiscreteHankelTransform(5.0, 100)
+    f = np.exp(-0.5 * d.r ** 2)
+    F = 2 * np.pi * np.exp(-0.5 * (2 * np.pi * d.q) ** 2)
+    np.testing.assert_allclose(d.transform(f, direction='forward'), F, atol=1e-5, rtol=0)
+    np.testing.assert_allclose(d.transform(F, direction='backward'), f, atol=1e-5, rtol=0)
+    np.testing.assert_allclose(np.dot(d.coefficients(d.q), f), d.transform(f), atol=1e-12, rtol=0)
+
+
+def test_geometry_matches_reference_golden(golden):
+    g = golden('mapping.npz')
+    geom = FixedGeometry(*[float(x) for x in g['geom']])
+    up, vp, wp, Vp = geom.apply_correction(g['u'], g['v'], g['V'], use3D=True)
+    for name, got in [('up', up), ('vp', vp), ('wp', wp), ('Vp', Vp)]:
+        assert np.array_equal(got, g[name]), name
+    u2, v2 = geom.reproject(*geom.deproject(g['u'], g['v']))
+    np.testing.assert_allclose(u2, g['u'], rtol=1e-12)
+    _, _, V2 = geom.undo_correction(up, vp, Vp)
+    np.testing.assert_allclose(V2, g['V'], rtol=1e-10)
+    s = geom.device_scalars()
+    assert s.cos_inc == np.cos(float(g['geom'][0]) * np.pi / 180)
+    assert geom.clone().inc == geom.inc and 'FixedGeometry' in repr(geom)
+
+
+def test_smoothing_matrix_and_band_factorisation():
+    for N, ws in [(20, 1e-4), (60, 1e-2), (300, 1e-1)]:
+        d = DiscreteHankelTransform(1.6 / rad_to_arcsec, N)
+        o = fo.DHTTables(1.6 / fo.RAD_TO_ARCSEC, N)
+        Tref = fo.smoothing_matrix(o, ws).toarray()
+        T = spectral_smoothing_matrix(d, ws).toarray()
+        assert np.max(np.abs(T - Tref)) <= 1e-14 * np.max(np.abs(Tref))
+        b = smoothing_bands(d, ws)
+        b[2] += 1
+        ldl = banded_ldl(b)
+        L = np.eye(N) + np.diag(ldl[1][1:], -1) + np.diag(ldl[2][2:], -2)
+        A = Tref + np.eye(N)
+        assert np.max(np.abs(L @ np.diag(ldl[0]) @ L.T - A)) <= 1e-13 * np.max(np.abs(A))
+        assert np.all(ldl[0] > 0)
+
+
+def test_fitter_constructor_errors():
+    from frank_b200.radial_fitters import FrankFitter, FourierBesselFitter
+    from frank_b200.statistical_models import VisibilityMapping
+    g = FixedGeometry(30, 40)
+    with pytest.raises(ValueError):
+        FrankFitter(1.6, 20, g, method='Poisson')
+    with pytest.raises(ValueError):
+        FrankFitter(1.6, 20, g, convergence_failure='explode')
+    with pytest.raises(ValueError):
+        FourierBesselFitter(1.6, 20, g, assume_optically_thick=True, scale_height=lambda r: r)
+    with pytest.raises(ValueError):
+        VisibilityMapping(DiscreteHankelTransform(1e-5, 20), g, vis_model='opaque')
+    with pytest.raises(ValueError):
+        VisibilityMapping(DiscreteHankelTransform(1e-5, 20), g, vis_model='debris')
+    FF = FrankFitter(1.6, 20, g, verbose=False)
+    assert FF.size == 20 and abs(FF.Rmax - 1.6) < 1e-12 and FF.fit_method() == 'FrankFitter: Normal method'
+    vm = FF._vis_map
+    assert vm.check_hash([False, FF._DHT, g, 'opt_thick', None])
+    assert not vm.check_hash([True, FF._DHT, g, 'opt_thick', None])
+    assert not vm.check_hash([False, FF._DHT, FixedGeometry(31, 40), 'opt_thick', None])
