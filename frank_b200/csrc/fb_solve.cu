@@ -15,6 +15,7 @@
 #include "fb_common.cuh"
 
 #include <cmath>
+#include <string>
 
 namespace {
 
@@ -38,20 +39,23 @@ k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restri
     const int bj = bi + rem;
     const double *p = p_all + (size_t)b * N;
     double *Dinv = Dinv_all + (size_t)b * N * N;
-    __shared__ double Ya[16][NB + 4], Yb[16][NB + 4];     // [k][i] slices of Y scaled / unscaled
+    constexpr int KS = 32;
+    __shared__ double Ya[KS][NB + 4], Yb[KS][NB + 4];     // [k][i] slices of Y scaled / unscaled
+    extern __shared__ double ip_s[];                      // [N] 1 / p
+    for (int i = threadIdx.x; i < N; i += 256) ip_s[i] = 1.0 / p[i];
+    __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double acc[4][4] = {};
-    for (int k0 = 0; k0 < N; k0 += 16) {
-        for (int e = threadIdx.x; e < 16 * NB; e += 256) {
-            const int kk = e / NB, c = e % NB, k = k0 + kk;
+    for (int k0 = 0; k0 < N; k0 += KS) {
+        for (int e = threadIdx.x; e < KS * NB; e += 256) {
+            const int kk = e >> 6, c = e & 63, k = k0 + kk;
             const int ia = bi * NB + c, ib = bj * NB + c;
-            const double ip = k < N ? 1.0 / p[k] : 0.0;
-            Ya[kk][c] = (k < N && ia < N) ? Y[(size_t)k * N + ia] * ip : 0.0;     // einsum order: (Y_ji * (1/p)_j) * Y_jk
+            Ya[kk][c] = (k < N && ia < N) ? Y[(size_t)k * N + ia] * ip_s[k] : 0.0;     // einsum order: (Y_ji * (1/p)_j) * Y_jk
             Yb[kk][c] = (k < N && ib < N) ? Y[(size_t)k * N + ib] : 0.0;
         }
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; kk++) {
+#pragma unroll 8
+        for (int kk = 0; kk < KS; kk++) {
             double a[4], bb[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) { a[r] = Ya[kk][ty * 4 + r]; bb[r] = Yb[kk][tx * 4 + r]; }
@@ -86,51 +90,59 @@ k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__rest
     extern __shared__ double dyn_sm[];
     double (*D)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm);
     double (*R)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm + NB * SLD);
+    __shared__ double diag[NB];
     const int tid = threadIdx.x;
     const int j = k + blockIdx.x;
     const int r0 = k * NB, c0 = j * NB;
     const int nk = min(NB, N - r0), nj = min(NB, N - c0);
     for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e / NB, c = e % NB;
+        const int r = e >> 6, c = e & 63;
         D[r][c] = (r < nk && c < nk && c >= r) ? A[(size_t)(r0 + r) * N + r0 + c] : (r == c ? 1.0 : 0.0);
         if (blockIdx.x > 0) R[r][c] = (r < nk && c < nj) ? A[(size_t)(r0 + r) * N + c0 + c] : 0.0;
     }
     __syncthreads();
-    // unblocked upper Cholesky of D in shared memory (every CTA of the panel repeats it: 64 short steps)
+    // unblocked upper Cholesky of D in shared memory (every CTA of the panel repeats it: 64 short steps).
+    // Pivots go to diag[] so that D[c][c] can be read by every thread of step c without a write hazard.
+    const int tx = tid & 15, ty = tid >> 4;
     for (int c = 0; c < nk; c++) {
         const double piv = D[c][c];
-        if (tid == 0 && blockIdx.x == 0 && !(piv > 0.0)) atomicCAS(&info[b], 0, r0 + c + 1);
         const double d = sqrt(piv), inv = 1.0 / d;
-        __syncthreads();
-        if (tid == 0) D[c][c] = d;
-        for (int e = tid + c + 1; e < nk; e += 256) D[c][e] = D[c][e] * inv;
+        if (tid == 0) {
+            diag[c] = d;
+            if (blockIdx.x == 0 && !(piv > 0.0)) atomicCAS(&info[b], 0, r0 + c + 1);
+        }
+        if (tid > c && tid < nk) D[c][tid] = D[c][tid] * inv;
         __syncthreads();
         // trailing update of the upper triangle: D[i][jj] -= U[c][i] U[c][jj], c < i <= jj
-        const int m = nk - c - 1;
-        for (int e = tid; e < m * m; e += 256) {
-            const int i = c + 1 + e / m, jj = c + 1 + e % m;
-            if (jj >= i) D[i][jj] = fma(-D[c][i], D[c][jj], D[i][jj]);
+        for (int i = c + 1 + ty; i < nk; i += 16) {
+            const double ui = D[c][i];
+            for (int jj = c + 1 + tx; jj < nk; jj += 16)
+                if (jj >= i) D[i][jj] = fma(-ui, D[c][jj], D[i][jj]);
         }
         __syncthreads();
     }
+    if (tid < nk) D[tid][tid] = diag[tid];
+    __syncthreads();
     if (blockIdx.x == 0) {
         for (int e = tid; e < NB * NB; e += 256) {
-            const int r = e / NB, c = e % NB;
+            const int r = e >> 6, c = e & 63;
             if (r < nk && c < nk && c >= r) A[(size_t)(r0 + r) * N + r0 + c] = D[r][c];
         }
         return;
     }
-    // forward substitution U_kk^T X = R, all 64 columns at once: 4 threads per column
-    const int col = tid & 63, part = tid >> 6;
+    // forward substitution U_kk^T X = R.  Four threads of one warp share a column, so a warp-level barrier is
+    // all the synchronisation the 64 dependent steps need.
+    const int col = tid >> 2, part = tid & 3;
     for (int r = 0; r < nk; r++) {
-        if (part == 0) R[r][col] = R[r][col] / D[r][r];
-        __syncthreads();
-        const double x = R[r][col];
+        const double x = R[r][col] / D[r][r];
+        __syncwarp();
+        if (part == 0) R[r][col] = x;
         for (int rr = r + 1 + part; rr < nk; rr += 4) R[rr][col] = fma(-D[r][rr], x, R[rr][col]);
-        __syncthreads();
+        __syncwarp();
     }
+    __syncthreads();
     for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e / NB, c = e % NB;
+        const int r = e >> 6, c = e & 63;
         if (r < nk && c < nj) A[(size_t)(r0 + r) * N + c0 + c] = R[r][c];
     }
 }
@@ -178,81 +190,44 @@ k_chol_update(int N, int nb, int k, double *__restrict__ A_all, const int *__res
         }
 }
 
-// ---- Z = U^-T R for a slab of right-hand sides; returns column sums of squares ----------------------------------------
-// R = Y^T (columns = rows of Y).  grid (ceil(N / 32), B), 256 threads.  The slab of Z (N x 32) lives in shared
-// memory (N <= 512) or in a global scratch (larger N).
-constexpr int TS = 32;                 // right-hand sides per CTA
+// ---- Tr2_i = || U^-T Y[i, :]^T ||^2 : forward substitution for a slab of right-hand sides -------------------------
+// Right-hand side c is row c of Y.  grid (ceil(N / TS), B), 256 threads: 8 threads of one warp share a column
+// of Z (kept in shared memory, or in a global scratch when N is large).  U is walked in panels of TP rows staged
+// in shared memory (rows of the row-major upper factor are contiguous -> coalesced), so the N dependent steps
+// touch shared memory only and need nothing but warp-level barriers inside a panel.
+constexpr int TS = 8;                  // right-hand sides per CTA: one warp per column
+constexpr int TP = 32;                 // rows of U per staged panel
 
 __global__ void __launch_bounds__(256)
-k_trsm_tr2(int N, int nb, const double *__restrict__ U_all, const double *__restrict__ Y, const int *__restrict__ active,
-           double *__restrict__ Zscratch_all, double *__restrict__ tr2_all)
+k_trsm_tr2(int N, const double *__restrict__ U_all, const double *__restrict__ Y, const int *__restrict__ active,
+           double *__restrict__ tr2_all)
 {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     const double *U = U_all + (size_t)b * N * N;
     extern __shared__ double sm[];
-    double *Ub = sm;                       // [NB][SLD]   current block of U
-    double *Zs = sm + NB * SLD;            // [N_pad][TS + 1] when it fits, else a [NB][TS+1] window
-    const bool in_smem = Zscratch_all == nullptr;
-    double *Zg = in_smem ? nullptr : Zscratch_all + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)nb * NB * TS;
-    const int tid = threadIdx.x;
-    const int c0 = blockIdx.x * TS;        // first right-hand side = row c0 of Y
-    const int col = tid & 31, part = tid >> 5;          // 8 threads per right-hand side
-    auto Z = [&](int r, int c) -> double & { return in_smem ? Zs[r * (TS + 1) + c] : Zg[(size_t)r * TS + c]; };
-
-    for (int kb = 0; kb < nb; kb++) {
-        const int r0 = kb * NB, nk = min(NB, N - r0);
-        // acc = R block: R[r0 + r][c0 + col] = Y[c0 + col][r0 + r]
-        double acc[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int r = part * 8 + q;
-            acc[q] = (r < nk && c0 + col < N) ? Y[(size_t)(c0 + col) * N + r0 + r] : 0.0;
-        }
-        // minus sum_{ib < kb} U_{ib,kb}^T Z_ib
-        for (int ib = 0; ib < kb; ib++) {
-            __syncthreads();
-            for (int e = tid; e < NB * NB; e += 256) {
-                const int r = e / NB, c = e % NB;
-                Ub[r * SLD + c] = (c < nk) ? U[(size_t)(ib * NB + r) * N + r0 + c] : 0.0;
-            }
-            __syncthreads();
-#pragma unroll 4
-            for (int i = 0; i < NB; i++) {
-                const double z = Z(ib * NB + i, col);
-#pragma unroll
-                for (int q = 0; q < 8; q++) acc[q] = fma(-Ub[i * SLD + part * 8 + q], z, acc[q]);
-            }
-        }
-        // diagonal block solve U_kk^T X = acc
+    double *Up = sm;                                        // [TP][N]  panel of U rows
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *Z = sm + TP * N + warp * N;                     // [N] this warp's right-hand side / solution
+    const int c = blockIdx.x * TS + warp;                   // right-hand side = row c of Y
+    for (int r = lane; r < N; r += 32) Z[r] = c < N ? Y[(size_t)c * N + r] : 0.0;
+    double ssq = 0.0;
+    for (int r1 = 0; r1 < N; r1 += TP) {
+        const int nk = min(TP, N - r1);
         __syncthreads();
-        for (int e = tid; e < NB * NB; e += 256) {
-            const int r = e / NB, c = e % NB;
-            Ub[r * SLD + c] = (r < nk && c < nk && c >= r) ? U[(size_t)(r0 + r) * N + r0 + c] : (r == c ? 1.0 : 0.0);
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) Z(r0 + part * 8 + q, col) = acc[q];
+        for (int r = warp; r < nk; r += 8)
+            for (int cc = r1 + lane; cc < N; cc += 32) Up[r * N + cc] = U[(size_t)(r1 + r) * N + cc];
         __syncthreads();
         for (int r = 0; r < nk; r++) {
-            if (part == 0) Z(r0 + r, col) = Z(r0 + r, col) / Ub[r * SLD + r];
-            __syncthreads();
-            const double x = Z(r0 + r, col);
-            for (int rr = r + 1 + part; rr < nk; rr += 8) Z(r0 + rr, col) = fma(-Ub[r * SLD + rr], x, Z(r0 + rr, col));
-            __syncthreads();
+            const double *Ur = Up + r * N;
+            const double z = Z[r1 + r] / Ur[r1 + r];
+            ssq = fma(z, z, ssq);
+            __syncwarp();
+            for (int rr = r1 + r + 1 + lane; rr < N; rr += 32) Z[rr] = fma(-Ur[rr], z, Z[rr]);
+            __syncwarp();
         }
     }
-    // column sums of squares: Tr2[c0 + col]
-    double s = 0.0;
-    for (int r = part; r < N; r += 8) { const double z = Z(r, col); s = fma(z, z, s); }
-    __syncthreads();
-    double *red = Ub;
-    red[part * 32 + col] = s;
-    __syncthreads();
-    if (part == 0 && c0 + col < N) {
-        double t = 0.0;
-        for (int q = 0; q < 8; q++) t += red[q * 32 + col];
-        tr2_all[(size_t)b * N + c0 + col] = t;
-    }
+    if (lane == 0 && c < N) tr2_all[(size_t)b * N + c] = ssq;
 }
 
 // ---- mu = U^-1 U^-T j, one CTA (1024 threads) per problem ---------------------------------------------------------
@@ -276,10 +251,8 @@ k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__rest
     for (int r1 = 0; r1 < N; r1 += PR) {
         const int nk = min(PR, N - r1);
         __syncthreads();
-        for (int e = tid; e < nk * (N - r1); e += blockDim.x) {
-            const int r = e / (N - r1), c = r1 + e % (N - r1);
-            S[r * N + c] = U[(size_t)(r1 + r) * N + c];
-        }
+        for (int r = warp; r < nk; r += nw)
+            for (int c = r1 + lane; c < N; c += 32) S[r * N + c] = U[(size_t)(r1 + r) * N + c];
         __syncthreads();
         if (warp == 0) {
             double xl = lane < nk ? x[r1 + lane] : 0.0;
@@ -303,10 +276,8 @@ k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__rest
     for (int r1 = last; r1 >= 0; r1 -= PR) {
         const int nk = min(PR, N - r1);
         __syncthreads();
-        for (int e = tid; e < nk * (N - r1); e += blockDim.x) {
-            const int r = e / (N - r1), c = r1 + e % (N - r1);
-            S[r * N + c] = U[(size_t)(r1 + r) * N + c];
-        }
+        for (int r = warp; r < nk; r += nw)
+            for (int c = r1 + lane; c < N; c += 32) S[r * N + c] = U[(size_t)(r1 + r) * N + c];
         __syncthreads();
         // tail dot products with the already final part of mu: one warp per panel row
         for (int r = warp; r < nk; r += nw) {
@@ -344,13 +315,14 @@ k_ps_update(int N, const double *__restrict__ Y, const double *__restrict__ mu_a
 {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
-    extern __shared__ double sh[];         // mu[N], rhs[N]
-    double *mu = sh, *rhs = sh + N;
+    extern __shared__ double sh[];         // mu[N], rhs[N], ldl[3N]
+    double *mu = sh, *rhs = sh + N, *ldl_s = sh + 2 * N;
     __shared__ int not_conv;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *p = p_all + (size_t)b * N;
     const double *ldl = ldl_all + (size_t)b * ldl_stride;
     for (int i = tid; i < N; i += 256) mu[i] = mu_all[(size_t)b * N + i];
+    for (int i = tid; i < 3 * N; i += 256) ldl_s[i] = ldl[i];
     if (tid == 0) not_conv = 0;
     __syncthreads();
     const double alpha = alpha_all[b], p0 = p0_all[b];
@@ -368,7 +340,7 @@ k_ps_update(int N, const double *__restrict__ Y, const double *__restrict__ mu_a
     __syncthreads();
     if (tid == 0) {
         // L y = rhs ; D w = y ; L^T tau = w   (unit lower-triangular L with two sub-diagonals)
-        const double *Dd = ldl, *L1 = ldl + N, *L2 = ldl + 2 * N;
+        const double *Dd = ldl_s, *L1 = ldl_s + N, *L2 = ldl_s + 2 * N;
         for (int i = 0; i < N; i++) {
             double v = rhs[i];
             if (i >= 1) v = fma(-L1[i], rhs[i - 1], v);
@@ -450,10 +422,6 @@ static int ensure_solver_ws(fb_ctx *ctx, int B)
     FB_CUDA(cudaMalloc(&ctx->sv_flags, sizeof(int) * (4 * B + 8)));
     FB_CUDA(cudaMalloc(&ctx->sv_M, sizeof(double) * N * N));
     FB_CUDA(cudaMalloc(&ctx->sv_j, sizeof(double) * N));
-    if (N > 512) {
-        const int nb = ((int)N + NB - 1) / NB, slabs = ((int)N + TS - 1) / TS;
-        FB_CUDA(cudaMalloc(&ctx->sv_Z, sizeof(double) * (size_t)B * slabs * nb * NB * TS));
-    }
     ctx->sv_B = B;
     ctx->sv_N = (int)N;
     return 0;
@@ -480,14 +448,19 @@ static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_i
     return 0;
 }
 
+static int allow_build_smem(fb_ctx *ctx)
+{
+    FB_CUDA(cudaFuncSetAttribute(k_build_dinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ctx->N)));
+    return 0;
+}
+
 static int launch_tr2(fb_ctx *ctx, int B, const int *d_active)
 {
-    const int N = ctx->N, nb = (N + NB - 1) / NB, slabs = (N + TS - 1) / TS;
-    const bool in_smem = N <= 512;
-    const size_t smem = sizeof(double) * (NB * SLD + (in_smem ? (size_t)nb * NB * (TS + 1) : 0));
-    if (in_smem) FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_trsm_tr2<<<dim3(slabs, B), 256, smem, ctx->stream>>>(N, nb, ctx->sv_D, ctx->d_Y, d_active, in_smem ? nullptr : ctx->sv_Z,
-                                                         ctx->sv_tr2);
+    const int N = ctx->N, slabs = (N + TS - 1) / TS;
+    const size_t smem = sizeof(double) * ((size_t)TP * N + (size_t)TS * N);
+    if (smem > 220 * 1024) FB_FAIL(-33, "k_trsm_tr2: N too large for the staged panel");
+    FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_trsm_tr2<<<dim3(slabs, B), 256, smem, ctx->stream>>>(N, ctx->sv_D, ctx->d_Y, d_active, ctx->sv_tr2);
     FB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -509,12 +482,14 @@ int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host
     FB_CUDA(cudaMemcpyAsync(ctx->sv_M, host_M, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(ctx->sv_j, host_j, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
     const int nb = ((int)N + NB - 1) / NB;
+    rc = allow_build_smem(ctx);
+    if (rc) return rc;
     if (has_prior) {
         if (!host_p) FB_FAIL(-32, "fb_gaussian_fit: power spectrum missing");
         for (size_t i = 0; i < (size_t)B * N; i++)
             if (!(host_p[i] > 0.0)) FB_FAIL(FB_E_BADP, "bad value in power spectrum");        // statistical_models.py:688
         FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p, sizeof(double) * B * N, cudaMemcpyHostToDevice, ctx->stream));
-        k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, 0, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, nullptr, ctx->sv_D);
+        k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, nullptr, ctx->sv_D);
     } else {
         for (int b = 0; b < B; b++)
             FB_CUDA(cudaMemcpyAsync(ctx->sv_D + (size_t)b * N * N, ctx->sv_M, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -567,32 +542,52 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
         FB_CUDA(cudaMalloc(&d_hist_mu, sizeof(double) * (size_t)B * hist_cap * N));
     }
     const int nb = ((int)N + NB - 1) / NB;
+    rc = allow_build_smem(ctx);
+    if (rc) return rc;
     // fit for the initial spectrum (the reference enters the loop with `fit` of p_init, radial_fitters.py:752-763)
-    k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, 0, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
+    k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
     rc = launch_factor_solve(ctx, B, d_active, d_info);
     if (rc) return rc;
     int *d_active_prev = nullptr;
     if (d_hist_mu) FB_CUDA(cudaMalloc(&d_active_prev, sizeof(int) * B));
 
+    // One iteration = a fixed sequence of ~15 small kernels: capture it once into a CUDA graph and replay it
+    // (launch-latency bound loop); the host polls the number of active problems every `poll` iterations.
+    auto enqueue_iteration = [&]() -> int {
+        int r = launch_tr2(ctx, B, d_active);
+        if (r) return r;
+        if (d_active_prev) FB_CUDA(cudaMemcpyAsync(d_active_prev, d_active, sizeof(int) * B, cudaMemcpyDeviceToDevice, ctx->stream));
+        k_ps_update<<<B, 256, sizeof(double) * 5 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
+                                                                    ctx->sv_p0, ctx->sv_ldl, (int)(3 * N), tol, max_iter, ctx->sv_p,
+                                                                    d_active, d_count, d_conv, d_hist_p, hist_cap);
+        k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
+        r = launch_factor_solve(ctx, B, d_active, d_info);
+        if (r) return r;
+        if (d_hist_mu) k_copy_hist_mu<<<B, 256, 0, ctx->stream>>>((int)N, ctx->sv_mu, d_count, d_active_prev, d_hist_mu, hist_cap);
+        k_loop_gate<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, max_iter, d_count, d_conv, d_active, d_nact);
+        return 0;
+    };
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    FB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_iteration();
+    {
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) FB_FAIL(-40, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    }
+    FB_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+
     int n_active = B, it = 0;
     const int poll = 8;
     while (n_active > 0 && it <= max_iter + 1) {
-        for (int s = 0; s < poll; s++, it++) {
-            rc = launch_tr2(ctx, B, d_active);
-            if (rc) return rc;
-            if (d_active_prev) FB_CUDA(cudaMemcpyAsync(d_active_prev, d_active, sizeof(int) * B, cudaMemcpyDeviceToDevice, ctx->stream));
-            k_ps_update<<<B, 256, sizeof(double) * 2 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
-                                                                        ctx->sv_p0, ctx->sv_ldl, (int)(3 * N), tol, max_iter, ctx->sv_p,
-                                                                        d_active, d_count, d_conv, d_hist_p, hist_cap);
-            k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, 0, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
-            rc = launch_factor_solve(ctx, B, d_active, d_info);
-            if (rc) return rc;
-            if (d_hist_mu) k_copy_hist_mu<<<B, 256, 0, ctx->stream>>>((int)N, ctx->sv_mu, d_count, d_active_prev, d_hist_mu, hist_cap);
-            k_loop_gate<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, max_iter, d_count, d_conv, d_active, d_nact);
-        }
+        for (int sidx = 0; sidx < poll; sidx++, it++) FB_CUDA(cudaGraphLaunch(gexec, ctx->stream));
         FB_CUDA(cudaMemcpyAsync(&n_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         FB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    cudaGraphExecDestroy(gexec);
+    cudaGraphDestroy(graph);
     FB_CUDA(cudaMemcpyAsync(host_p, ctx->sv_p, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(host_mu, ctx->sv_mu, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
     if (host_chol) FB_CUDA(cudaMemcpyAsync(host_chol, ctx->sv_D, sizeof(double) * B * N * N, cudaMemcpyDeviceToHost, ctx->stream));
