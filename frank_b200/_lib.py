@@ -43,6 +43,11 @@ _SIGNATURES = {
     'fb_debug_prepped': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
+    'fb_ln_setup': ([_c_p, _c_p, _c_p, _c_d, _c_d], _c_i),
+    'fb_ln_set_spectrum': ([_c_p, _c_p], _c_i),
+    'fb_ln_eval': ([_c_p, _c_p, _c_p, _c_p], _c_i),
+    'fb_ln_newton_direction': ([_c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
+    'fb_ln_posterior': ([_c_p, _c_p, _c_p, _c_d, _c_d, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_frank_normal_loop': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p,
                               _c_p, _c_p, _c_p, _c_p, _c_i], _c_i),
 }
@@ -201,6 +206,41 @@ class Context(object):
         self.check(rc, 'fb_frank_normal_loop')
         return {'p': p, 'mu': mu, 'chol': chol, 'niter': niter, 'converged': conv, 'info': info, 'status': rc,
                 'hist_p': hp, 'hist_mu': hm}
+
+    # -- LogNormal model ------------------------------------------------------------------------
+    def ln_setup(self, M, j, s0, full_hessian=1.0):
+        M = np.ascontiguousarray(M, dtype=np.float64); j = np.ascontiguousarray(j, dtype=np.float64)
+        self.check(self._lib.fb_ln_setup(self._h, _ptr(M), _ptr(j), float(s0), float(full_hessian)), 'fb_ln_setup')
+
+    def ln_set_spectrum(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        return self.check(self._lib.fb_ln_set_spectrum(self._h, _ptr(p)), 'fb_ln_set_spectrum')
+
+    def ln_eval(self, s, want_grad=False):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        f = np.zeros(1)
+        g = np.empty_like(s) if want_grad else None
+        self.check(self._lib.fb_ln_eval(self._h, _ptr(s), _ptr(f), _ptr(g)), 'fb_ln_eval')
+        return (float(f[0]), g) if want_grad else float(f[0])
+
+    def ln_newton_direction(self, s, refactor):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        g, dx = np.empty_like(s), np.empty_like(s)
+        info = np.zeros(1, dtype=np.int32)
+        rc = self.check(self._lib.fb_ln_newton_direction(self._h, _ptr(s), int(refactor), _ptr(g), _ptr(dx), _ptr(info)),
+                        'fb_ln_newton_direction')
+        return g, dx, rc
+
+    def ln_posterior(self, s, p, alpha=None, p0=None, ldl=None, want_chol=True):
+        s = np.ascontiguousarray(s, dtype=np.float64); p = np.ascontiguousarray(p, dtype=np.float64)
+        N = s.size
+        chol = np.empty((N, N)) if want_chol else None
+        p_new = np.empty(N) if ldl is not None else None
+        ldl_c = None if ldl is None else np.ascontiguousarray(ldl, dtype=np.float64)
+        info = np.zeros(1, dtype=np.int32)
+        rc = self.check(self._lib.fb_ln_posterior(self._h, _ptr(s), _ptr(p), float(alpha or 0.0), float(p0 or 0.0), _ptr(ldl_c),
+                                                  _ptr(chol), _ptr(p_new), _ptr(info)), 'fb_ln_posterior')
+        return chol, p_new, rc
 
     def debug_j0(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -81,6 +81,10 @@ struct fb_ctx {
     double *sv_D = nullptr, *sv_p = nullptr, *sv_mu = nullptr, *sv_tr2 = nullptr, *sv_alpha = nullptr, *sv_p0 = nullptr;
     double *sv_ldl = nullptr, *sv_M = nullptr, *sv_j = nullptr, *sv_Z = nullptr;
     int *sv_flags = nullptr;
+    // LogNormal model state
+    int ln_N = 0;
+    double *ln_S = nullptr, *ln_vec = nullptr;
+    double ln_s0 = 0.0, ln_full_hess = 1.0;
     cudaEvent_t ev[8] = {};
     cudaEvent_t tev[2] = {};
     double timing[4] = {0, 0, 0, 0};

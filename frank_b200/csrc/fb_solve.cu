@@ -72,9 +72,9 @@ k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restri
         for (int c = 0; c < 4; c++) {
             const int i = bi * NB + ty * 4 + r, j = bj * NB + tx * 4 + c;
             if (i < N && j < N) {
-                const double v = M[(size_t)i * N + j] + acc[r][c];
+                const double v = (M ? M[(size_t)i * N + j] : 0.0) + acc[r][c];
                 Dinv[(size_t)i * N + j] = v;
-                if (bi != bj) Dinv[(size_t)j * N + i] = M[(size_t)j * N + i] + acc[r][c];
+                if (bi != bj) Dinv[(size_t)j * N + i] = (M ? M[(size_t)j * N + i] : 0.0) + acc[r][c];
             }
         }
 }
@@ -397,6 +397,73 @@ __global__ void k_copy_hist_mu(int N, const double *__restrict__ mu_all, const i
     for (int i = threadIdx.x; i < N; i += blockDim.x) hist_mu[((size_t)b * hist_cap + c) * N + i] = mu_all[(size_t)b * N + i];
 }
 
+// ---- LogNormal MAP model (frank/statistical_models.py:1088-1132), single channel / single field / unit scale -------
+// I = exp(s + s0);  f = 1/2 s^T S^-1 s + 1/2 I^T M I - I.j;  g = S^-1 s + I o (M I - j).  One CTA; the two
+// matrix-vector products are row sweeps (rows are contiguous) with a fixed reduction order.
+__global__ void __launch_bounds__(1024)
+k_ln_eval(int N, const double *__restrict__ M, const double *__restrict__ Sinv, const double *__restrict__ jvec,
+          const double *__restrict__ s_in, double s0, double *__restrict__ I_out, double *__restrict__ r_out,
+          double *__restrict__ g_out, double *__restrict__ f_out)
+{
+    extern __shared__ double sh[];
+    double *sv = sh, *Iv = sh + N, *fpart = sh + 2 * N;     // fpart[N]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int i = tid; i < N; i += blockDim.x) {
+        const double si = s_in[i];
+        sv[i] = si;
+        const double Ii = exp(si + s0);
+        Iv[i] = Ii;
+        I_out[i] = Ii;
+    }
+    __syncthreads();
+    for (int r = warp; r < N; r += nw) {
+        double mi = 0.0, ss = 0.0;
+        const double *Mr = M + (size_t)r * N, *Sr = Sinv + (size_t)r * N;
+        for (int c = lane; c < N; c += 32) {
+            mi = fma(Mr[c], Iv[c], mi);
+            ss = fma(Sr[c], sv[c], ss);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mi += __shfl_down_sync(0xffffffffu, mi, o);
+            ss += __shfl_down_sync(0xffffffffu, ss, o);
+        }
+        if (lane == 0) {
+            const double res = mi - jvec[r];                 // (M I - j)_r
+            r_out[r] = Iv[r] * res;                          // diagonal term of the Hessian: I o (M I - j)
+            g_out[r] = ss + Iv[r] * res;
+            fpart[r] = 0.5 * sv[r] * ss + 0.5 * Iv[r] * mi - Iv[r] * jvec[r];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double acc = 0.0;
+        for (int i = lane; i < N; i += 32) acc += fpart[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) f_out[0] = acc;
+    }
+}
+
+// Hessian  diag(I) M diag(I) + full_hess * diag(I o (M I - j)) + S^-1     (statistical_models.py:1113-1132)
+__global__ void __launch_bounds__(256)
+k_ln_hess(int N, const double *__restrict__ M, const double *__restrict__ Sinv, const double *__restrict__ Iv,
+          const double *__restrict__ rdiag, double full_hess, double *__restrict__ H)
+{
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (r < N && c < N) {
+        double v = Iv[r] * M[(size_t)r * N + c] * Iv[c] + Sinv[(size_t)r * N + c];
+        if (r == c) v += full_hess * rdiag[r];
+        H[(size_t)r * N + c] = v;
+    }
+}
+
+__global__ void k_negate(int N, const double *__restrict__ in, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = -in[i];
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -609,6 +676,159 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     }
     if (worst) ctx->err = "Cholesky factorisation met a non-positive pivot";
     return worst;
+}
+
+
+// ---- LogNormalMAPModel (frank/statistical_models.py:1073-1160) -----------------------------------------------------------
+static int ln_ensure(fb_ctx *ctx)
+{
+    const size_t N = ctx->N;
+    if (ctx->ln_N == (int)N && ctx->ln_S) return 0;
+    for (void **p : {(void **)&ctx->ln_S, (void **)&ctx->ln_vec}) {
+        if (*p) FB_CUDA(cudaFree(*p));
+        *p = nullptr;
+    }
+    FB_CUDA(cudaMalloc(&ctx->ln_S, sizeof(double) * N * N));
+    FB_CUDA(cudaMalloc(&ctx->ln_vec, sizeof(double) * (6 * N + 8)));       // s, I, rdiag, g, -g, f
+    ctx->ln_N = (int)N;
+    return 0;
+}
+
+int fb_ln_setup(fb_ctx *ctx, const double *host_M, const double *host_j, double s0, double full_hessian)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0 || !ctx->d_Y) FB_FAIL(-30, "fb_ln_setup: fb_dht_setup (with Ycoef) has not been called");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_solver_ws(ctx, 1);
+    if (rc) return rc;
+    rc = ln_ensure(ctx);
+    if (rc) return rc;
+    const size_t N = ctx->N;
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_M, host_M, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_j, host_j, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->ln_s0 = s0;
+    ctx->ln_full_hess = full_hessian;
+    return 0;
+}
+
+int fb_ln_set_spectrum(fb_ctx *ctx, const double *host_p)
+{
+    if (!ctx || !ctx->ln_S) return -1;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    for (size_t i = 0; i < N; i++)
+        if (!(host_p[i] > 0.0)) FB_FAIL(FB_E_BADP, "bad value in power spectrum");            // statistical_models.py:1053
+    const int nb = ((int)N + NB - 1) / NB;
+    int rc = allow_build_smem(ctx);
+    if (rc) return rc;
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    k_build_dinv<<<dim3(nb * (nb + 1) / 2, 1), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, nullptr, ctx->d_Y, ctx->sv_p, nullptr, ctx->ln_S);
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int ln_eval_device(fb_ctx *ctx, const double *host_s)
+{
+    const size_t N = ctx->N;
+    double *d_s = ctx->ln_vec, *d_I = d_s + N, *d_r = d_I + N, *d_g = d_r + N, *d_f = d_g + 2 * N;
+    FB_CUDA(cudaMemcpyAsync(d_s, host_s, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t smem = sizeof(double) * 3 * N;
+    FB_CUDA(cudaFuncSetAttribute(k_ln_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ln_eval<<<1, 1024, smem, ctx->stream>>>((int)N, ctx->sv_M, ctx->ln_S, ctx->sv_j, d_s, ctx->ln_s0, d_I, d_r, d_g, d_f);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* f(s) and optionally the gradient g(s) [N] (statistical_models.py:1088-1111). */
+int fb_ln_eval(fb_ctx *ctx, const double *host_s, double *host_f, double *host_g)
+{
+    if (!ctx || !ctx->ln_S || !host_s || !host_f) return -1;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = ln_eval_device(ctx, host_s);
+    if (rc) return rc;
+    const size_t N = ctx->N;
+    double *d_g = ctx->ln_vec + 3 * N, *d_f = d_g + 2 * N;
+    FB_CUDA(cudaMemcpyAsync(host_f, d_f, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_g) FB_CUDA(cudaMemcpyAsync(host_g, d_g, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+/* Newton direction dx = -Hess(s_fact)^-1 g(s): refactor != 0 rebuilds and factorises the Hessian at s (the
+ * reference re-uses its LU factors while full steps are accepted, minimizer.py:236-239,276). Also returns g(s). */
+int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, double *host_g, double *host_dx, int *host_info)
+{
+    if (!ctx || !ctx->ln_S || !host_s || !host_dx) return -1;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    int rc = ln_eval_device(ctx, host_s);
+    if (rc) return rc;
+    double *d_s = ctx->ln_vec, *d_I = d_s + N, *d_r = d_I + N, *d_g = d_r + N, *d_ng = d_g + N;
+    int *d_info = ctx->sv_flags;
+    if (refactor) {
+        FB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
+        k_ln_hess<<<dim3(((int)N + 31) / 32, ((int)N + 7) / 8), 256, 0, ctx->stream>>>((int)N, ctx->sv_M, ctx->ln_S, d_I, d_r, ctx->ln_full_hess, ctx->sv_D);
+        const int nb = ((int)N + NB - 1) / NB;
+        const size_t blk2 = sizeof(double) * 2 * NB * SLD;
+        FB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
+        FB_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
+        for (int k = 0; k < nb; k++) {
+            k_chol_panel<<<dim3(nb - k, 1), 256, blk2, ctx->stream>>>((int)N, nb, k, ctx->sv_D, nullptr, d_info);
+            const int nt = nb - k - 1;
+            if (nt > 0) k_chol_update<<<dim3(nt * (nt + 1) / 2, 1), 256, blk2, ctx->stream>>>((int)N, nb, k, ctx->sv_D, nullptr);
+        }
+    }
+    k_negate<<<((int)N + 255) / 256, 256, 0, ctx->stream>>>((int)N, d_g, d_ng);
+    int PR = 32;
+    while (PR > 1 && sizeof(double) * (N + 32 + (size_t)PR * N) > 200 * 1024) PR /= 2;
+    const size_t smem = sizeof(double) * (N + 32 + (size_t)PR * N);
+    FB_CUDA(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_solve_mu<<<1, 1024, smem, ctx->stream>>>((int)N, PR, ctx->sv_D, d_ng, 0, nullptr, ctx->sv_mu);
+    FB_CUDA(cudaGetLastError());
+    int info = 0;
+    if (host_g) FB_CUDA(cudaMemcpyAsync(host_g, d_g, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(host_dx, ctx->sv_mu, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (host_info) *host_info = info;
+    if (info) FB_FAIL(FB_E_NOTPD, "Hessian is not positive definite");
+    return 0;
+}
+
+/* Posterior at the MAP point: factorise Hess(s_MAP) (statistical_models.py:1148-1158), optionally return the upper
+ * factor, and run one CriticalFilter.update_power_spectrum with it (filter.py:154-177): p_new [N]. */
+int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, double alpha, double p0, const double *host_ldl,
+                    double *host_chol, double *host_p_new, int *host_info)
+{
+    if (!ctx || !ctx->ln_S || !host_s) return -1;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    std::vector<double> g(N), dx(N);
+    int info = 0;
+    int rc = fb_ln_newton_direction(ctx, host_s, 1, g.data(), dx.data(), &info);
+    if (host_info) *host_info = info;
+    if (rc) return rc;
+    if (host_chol) FB_CUDA(cudaMemcpyAsync(host_chol, ctx->sv_D, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_p_new) {
+        int *d_flags = ctx->sv_flags + 1;      // count, converged scratch
+        FB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_mu, host_s, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_alpha, &alpha, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_p0, &p0, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_ldl, host_ldl, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
+        rc = launch_tr2(ctx, 1, nullptr);
+        if (rc) return rc;
+        k_ps_update<<<1, 256, sizeof(double) * 5 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha, ctx->sv_p0,
+                                                                    ctx->sv_ldl, (int)(3 * N), 1e-3, 0, ctx->sv_p, nullptr, d_flags, d_flags + 1,
+                                                                    nullptr, 0);
+        FB_CUDA(cudaGetLastError());
+        FB_CUDA(cudaMemcpyAsync(host_p_new, ctx->sv_p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 }  // extern "C"

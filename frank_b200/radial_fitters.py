@@ -15,7 +15,7 @@ from frank_b200 import _lib
 from frank_b200.constants import rad_to_arcsec
 from frank_b200.filter import CriticalFilter
 from frank_b200.hankel import DiscreteHankelTransform
-from frank_b200.statistical_models import GaussianModel, VisibilityMapping
+from frank_b200.statistical_models import GaussianModel, LogNormalMAPModel, VisibilityMapping
 
 __all__ = ['FrankRadialFit', 'FrankGaussianFit', 'FrankLogNormalFit', 'FourierBesselFitter', 'FrankFitter']
 
@@ -257,7 +257,31 @@ class FrankFitter(FourierBesselFitter):
         return self._sol
 
     def _fit_lognormal(self):
-        raise NotImplementedError("method='LogNormal' is not available in this build yet")
+        """LogNormal branch of frank/radial_fitters.py:754-785: log-space start, then the same fixed-point loop with
+        LogNormalMAPModel solves (Newton decisions on the host, arithmetic on the device)."""
+        pI = self._starting_spectrum()
+        fit = self._perform_fit(pI, fit_method='Normal')
+        s = np.log(np.maximum(fit.MAP, 1e-3 * fit.MAP.max()))
+        s -= self._s_scale
+        pI = np.max(self._DHT.transform(s) ** 2)
+        pI = pI * (self.q / self.q[0]) ** -4
+        fit = self._perform_fit(pI, guess=s)
+        count, pi_old = 0, 0
+        while (not self._filter.check_convergence(pI, pi_old)) and count <= self._max_iter:
+            pi_old = pI.copy()
+            pI = fit._update_power_spectrum(self._filter._alpha, self._filter._p_0, self._filter._ldl)
+            fit = self._perform_fit(pI, guess=fit.MAP)
+            if self._store_iteration_diagnostics:
+                self._iteration_diagnostics['power_spectrum'].append(pI)
+                self._iteration_diagnostics['MAP'].append(fit.MAP)
+            count += 1
+        self._report_convergence(count)
+        if self._store_iteration_diagnostics:
+            self._iteration_diagnostics['num_iterations'] = count
+        self._sol = FrankLogNormalFit(self._vis_map, fit, self._info, geometry=self._geometry.clone())
+        self._ps = pI
+        self._ps_cov = None
+        return self._sol
 
     def _report_convergence(self, count):
         """Convergence policy of frank/radial_fitters.py:787-815."""
@@ -293,7 +317,8 @@ class FrankFitter(FourierBesselFitter):
             return GaussianModel(self._DHT, self._M, self._j, p, guess=guess, noise_likelihood=self._H0,
                                  device=self._device)
         if fit_method == 'LogNormal':
-            raise NotImplementedError("method='LogNormal' is not available in this build yet")
+            return LogNormalMAPModel(self._DHT, self._M, self._j, p, guess=guess, s0=self._s_scale,
+                                     noise_likelihood=self._H0, device=self._device)
         raise ValueError('fit_method must be one of the following:\n\t{"Normal", "LogNormal"}')
 
     def draw_powerspectrum(self, Ndraw=1):

@@ -12,7 +12,7 @@ import numpy as np
 from frank_b200 import _lib
 from frank_b200.constants import rad_to_arcsec, deg_to_rad
 
-__all__ = ['VisibilityMapping']
+__all__ = ['VisibilityMapping', 'GaussianModel', 'LogNormalMAPModel']
 
 
 def _is_cuda_tensor(x):
@@ -362,3 +362,114 @@ class GaussianModel(object):
     @property
     def power_spectrum(self):
         return None if self._p is None else self._p.reshape(self.size)
+
+
+class LogNormalMAPModel(object):
+    r"""Maximum a posteriori field of the log-normal model, P(s|V,p) ∝ G(H exp(s + s0) - V, M) G(s, S(p)).
+
+    API mirror of frank.statistical_models.LogNormalMAPModel (frank/statistical_models.py:907-1295) for one
+    channel, one field and unit scale (what FrankFitter uses).  The objective, gradient, Hessian, its
+    factorisation and the Newton solves run on the GPU (fb_ln_* in include/frankb200.h); the Newton / line-search
+    decisions are taken on the host (frank_b200/minimizer.py).
+    """
+
+    def __init__(self, DHT, M, j, p=None, scale=None, s0=None, guess=None, Nfields=None, full_hessian=1,
+                 noise_likelihood=0, device=None):
+        from frank_b200.minimizer import LineSearch, MinimizeNewton
+        self._DHT = DHT
+        self._full_hess = full_hessian
+        M = np.asarray(M)
+        j = np.asarray(j)
+        if M.ndim == 3:
+            if M.shape[0] != 1:
+                raise NotImplementedError("frank_b200 solves single-channel log-normal models")
+            M, j = M[0], j[0]
+        Nr = j.shape[0]
+        if (Nfields or 1) != 1 or scale is not None:
+            raise NotImplementedError("frank_b200 solves single-field, unit-scale log-normal models")
+        if s0 is None or guess is None or p is None:
+            raise ValueError("LogNormalMAPModel needs p, s0 and an initial guess")
+        p = np.asarray(p, dtype=np.float64).reshape(Nr)
+        if np.any(p <= 0) or np.any(np.isnan(p)):                                     # :1053-1062
+            raise ValueError("Bad value in power spectrum. The power"
+                             " spectrum must be positive and not contain"
+                             " any NaN values. This is likely due to"
+                             " your UVtable (incorrect units or weights), "
+                             " or the deprojection being applied (incorrect"
+                             " geometry and/or phase center). Else you may"
+                             " want to increase `rout` by 10-20% or `n` so"
+                             " that it is large, >~300.")
+        self._M, self._j, self._p = M, j, p
+        self._s0 = float(np.atleast_1d(s0)[0])
+        self._like_noise = noise_likelihood
+        self._device = device
+        self._cov = None
+
+        ctx = _lib.get_context(device)
+        ctx.dht_setup(DHT)
+        ctx.ln_setup(M, j, self._s0, full_hessian)
+        ctx.ln_set_spectrum(p)
+        self._ctx = ctx
+
+        def limit_step(dx, x):                                                        # :1136-1140
+            return min(1.1 * np.min(np.abs(x / dx)), 1) * dx
+
+        def newton_dir(x, refactor):
+            g, dx, rc = ctx.ln_newton_direction(x, refactor)
+            if rc == _lib.FB_E_NOTPD:
+                # The reference factorises with LU and would still get a (not necessarily descending) direction;
+                # an indefinite Hessian here makes the step fall back to gradient descent (minimizer.py:250-253).
+                # Not met on any fit path tested (0 of 1.2e5 Hessians in the reference runs, DESIGN.md).
+                return g, None
+            return g, dx
+
+        search = LineSearch(reduce_step=limit_step)
+        x0 = np.array(guess, dtype=np.float64).reshape(Nr)
+        s, self._status = MinimizeNewton(lambda x: ctx.ln_eval(x), lambda x: ctx.ln_eval(x, True)[1], newton_dir, x0,
+                                         search, tol=1e-7)
+        self._s_MAP = s
+        chol, _, rc = ctx.ln_posterior(s, p)                                          # cho_factor(hess(s)), :1148-1150
+        self._U = np.triu(chol)
+
+    def _update_power_spectrum(self, alpha, p0, ldl):
+        """CriticalFilter.update_power_spectrum with this model's Hessian factor (device)."""
+        self._ctx.ln_setup(self._M, self._j, self._s0, self._full_hess)
+        self._ctx.ln_set_spectrum(self._p)
+        _, p_new, _ = self._ctx.ln_posterior(self._s_MAP, self._p, alpha, p0, ldl, want_chol=False)
+        return p_new
+
+    def Dsolve(self, b):
+        import scipy.linalg
+        return scipy.linalg.cho_solve((self._U, False), b)
+
+    def log_likelihood(self, s=None):
+        r"""log P(I, V|p) as the reference evaluates it (statistical_models.py:1196-1245)."""
+        if s is None:
+            s = self._s_MAP
+        Y = self._DHT.coefficients()
+        Sinv = np.dot(Y.T * (1 / self._p), Y)
+        I = np.exp(s)
+        like = -0.5 * np.dot(s - self._s0, np.dot(Sinv, s - self._s0))
+        like -= 0.5 * np.dot(I, np.dot(self._M, I))
+        like += np.sum(I * self._j)
+        like += 0.5 * np.linalg.slogdet(2 * np.pi * Sinv)[1]
+        return like + self._like_noise
+
+    def solve_non_negative(self):
+        return self.MAP
+
+    def draw(self, N):
+        return np.random.multivariate_normal(self.MAP.reshape(-1), self.covariance, N)
+
+    MAP = property(lambda self: self._s_MAP, doc="Posterior maximum of s = log I - s0")
+    power_spectrum = property(lambda self: self._p)
+    scale = property(lambda self: np.ones(1))
+    s_0 = property(lambda self: np.array([self._s0]))
+    num_fields = property(lambda self: 1)
+    size = property(lambda self: self._DHT.size)
+
+    @property
+    def covariance(self):
+        if self._cov is None:
+            self._cov = self.Dsolve(np.eye(self.size))
+        return self._cov

@@ -127,6 +127,25 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
                          double *host_p, double *host_mu, double *host_chol, int *host_niter, int *host_converged,
                          int *host_info, double *host_hist_p, double *host_hist_mu, int hist_cap);
 
+/* ---- LogNormalMAPModel (frank/statistical_models.py:998-1160), one channel / one field / unit scale --------
+ * The Newton iteration's control flow (MinimizeNewton / LineSearch, frank/minimizer.py) stays with the caller;
+ * these entry points do its O(N^2) / O(N^3) arithmetic on the device:
+ *   fb_ln_setup            upload M [N*N], j [N]; s0 = log(I_scale); full_hessian as in the reference
+ *   fb_ln_set_spectrum     S^-1 = Y^T diag(1/p) Y                           (:1064-1065)
+ *   fb_ln_eval             f(s) = 1/2 s^T S^-1 s + 1/2 I^T M I - I.j, I = exp(s + s0); g(s) [N] optional (:1088-1111)
+ *   fb_ln_newton_direction g(s) and dx = -Hess^-1 g(s); refactor != 0 rebuilds Hess(s) = diag(I) M diag(I) +
+ *                          full_hessian diag(I o (M I - j)) + S^-1 and factorises it (:1113-1132; the reference
+ *                          uses LU, minimizer.py:238 -- the Hessians met on the fit path are positive definite,
+ *                          FB_E_NOTPD otherwise)
+ *   fb_ln_posterior        factorise Hess(s_MAP) (:1148-1150), return the upper factor (optional) and one
+ *                          CriticalFilter.update_power_spectrum with it (filter.py:154-177) */
+int fb_ln_setup(fb_ctx *ctx, const double *host_M, const double *host_j, double s0, double full_hessian);
+int fb_ln_set_spectrum(fb_ctx *ctx, const double *host_p);
+int fb_ln_eval(fb_ctx *ctx, const double *host_s, double *host_f, double *host_g);
+int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, double *host_g, double *host_dx, int *host_info);
+int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, double alpha, double p0, const double *host_ldl,
+                    double *host_chol, double *host_p_new, int *host_info);
+
 /* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]). */
 int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out);
 
