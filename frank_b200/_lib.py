@@ -43,6 +43,8 @@ _SIGNATURES = {
     'fb_debug_prepped': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
+    'fb_uv_max': ([_c_p, _c_l, _c_p, _c_p], _c_i),
+    'fb_uv_bin': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_ln_setup': ([_c_p, _c_p, _c_p, _c_d, _c_d], _c_i),
     'fb_ln_set_spectrum': ([_c_p, _c_p], _c_i),
     'fb_ln_eval': ([_c_p, _c_p, _c_p, _c_p], _c_i),
@@ -241,6 +243,26 @@ class Context(object):
         rc = self.check(self._lib.fb_ln_posterior(self._h, _ptr(s), _ptr(p), float(alpha or 0.0), float(p0 or 0.0), _ptr(ldl_c),
                                                   _ptr(chol), _ptr(p_new), _ptr(info)), 'fb_ln_posterior')
         return chol, p_new, rc
+
+    # -- uv binning -----------------------------------------------------------------------------
+    def uv_max(self, uv):
+        uv = np.ascontiguousarray(uv, dtype=np.float64)
+        m = np.zeros(1)
+        self.check(self._lib.fb_uv_max(self._h, uv.size, _ptr(uv), _ptr(m)), 'fb_uv_max')
+        return float(m[0])
+
+    def uv_bin(self, uv, V, w, bin_width, nbins):
+        uv = np.ascontiguousarray(uv, dtype=np.float64)
+        n = uv.size
+        is_c = np.iscomplexobj(V)
+        V = np.ascontiguousarray(V, dtype=np.complex128 if is_c else np.float64)
+        w = np.ascontiguousarray(np.atleast_1d(w), dtype=np.float64)
+        idx = np.empty(n, dtype=np.int32)
+        counts = np.empty(nbins, dtype=np.int64)
+        sums = np.empty((nbins, 4)); err = np.empty((nbins, 2))
+        self.check(self._lib.fb_uv_bin(self._h, n, _ptr(uv), _ptr(V), int(is_c), _ptr(w), int(w.size > 1), float(bin_width),
+                                       int(nbins), _ptr(idx), _ptr(counts), _ptr(sums), _ptr(err)), 'fb_uv_bin')
+        return idx, counts, sums, err
 
     def debug_j0(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -116,3 +116,5 @@ int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, con
 int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, double *dev_M, double *dev_j);
 int fb_build_j0_table(fb_ctx *ctx, double x_max);
 int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max);
+uint64_t *fb_radix_sort_items(fb_ctx *ctx, int64_t n, uint64_t *buf0, uint64_t *buf1, int nbits, int *status);
+int fb_items_from_keys(fb_ctx *ctx, int64_t n, const int32_t *dev_keys, uint64_t *items);

@@ -6,8 +6,8 @@
 // uv-binning pass (frank/utilities.py:300-367 accumulates with np.bincount; here bins become contiguous
 // segments).
 //
-// Key = (channel << 16) | floor(a * key_scale) clipped to 16 bits; payload = original index.  8-bit digits,
-// 2 passes (3 with channels).  Each pass: per-block digit histograms -> exclusive scan over (digit, block) ->
+// Key = floor(a * key_scale) clipped to 16 bits (Gram) or the uv-bin index (binner); payload = original index.
+// 8-bit digits, 2 passes for the Gram, ceil(bits / 8) for the binner.  Each pass: per-block digit histograms -> exclusive scan over (digit, block) ->
 // stable scatter.  Stability (and therefore bit-reproducible sums downstream) comes from ranking inside a
 // block with __match_any_sync in a fixed element order.
 #include "fb_common.cuh"
@@ -25,20 +25,28 @@ __device__ __forceinline__ int64_t elem_index(int64_t base, int warp, int round,
     return base + (int64_t)warp * (32 * SORT_ROUNDS) + round * 32 + lane;
 }
 
-__device__ __forceinline__ uint64_t make_item(const double4 *__restrict__ rec, const int32_t *__restrict__ chan, int64_t i,
-                                              double key_scale)
+// key = floor(a * key_scale) clipped to 16 bits, payload = index
+__global__ void __launch_bounds__(256)
+k_items_from_rec(int64_t n, const double4 *__restrict__ rec, double key_scale, uint64_t *__restrict__ items)
 {
-    int k = __double2int_rz(rec[i].x * key_scale);
-    k = k < 0 ? 0 : (k > 65535 ? 65535 : k);
-    uint64_t key = (uint64_t)k;
-    if (chan) key |= (uint64_t)(uint32_t)chan[i] << 16;
-    return (key << 32) | (uint64_t)(uint32_t)i;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int k = __double2int_rz(rec[i].x * key_scale);
+        k = k < 0 ? 0 : (k > 65535 ? 65535 : k);
+        items[i] = ((uint64_t)k << 32) | (uint64_t)(uint32_t)i;
+    }
 }
 
-template <bool FIRST>
+// key = a non-negative 32-bit integer per element (uv-bin index), payload = index
+__global__ void __launch_bounds__(256)
+k_items_from_keys(int64_t n, const int32_t *__restrict__ keys, uint64_t *__restrict__ items)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) items[i] = ((uint64_t)(uint32_t)keys[i] << 32) | (uint64_t)(uint32_t)i;
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_hist(int64_t n, const double4 *__restrict__ rec, const int32_t *__restrict__ chan, double key_scale,
-            const uint64_t *__restrict__ items, int shift, uint32_t *__restrict__ hist, int nblocks)
+k_sort_hist(int64_t n, const uint64_t *__restrict__ items, int shift, uint32_t *__restrict__ hist, int nblocks)
 {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
@@ -48,10 +56,7 @@ k_sort_hist(int64_t n, const double4 *__restrict__ rec, const int32_t *__restric
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
         int64_t i = elem_index(base, warp, r, lane);
-        if (i < n) {
-            uint64_t it = FIRST ? make_item(rec, chan, i, key_scale) : items[i];
-            atomicAdd(&h[(it >> shift) & 255], 1u);
-        }
+        if (i < n) atomicAdd(&h[(items[i] >> shift) & 255], 1u);
     }
     __syncthreads();
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
@@ -93,10 +98,8 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *__restrict__ data,
     }
 }
 
-template <bool FIRST>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_scatter(int64_t n, const double4 *__restrict__ rec, const int32_t *__restrict__ chan, double key_scale,
-               const uint64_t *__restrict__ items, int shift, const uint32_t *__restrict__ offs, int nblocks,
+k_sort_scatter(int64_t n, const uint64_t *__restrict__ items, int shift, const uint32_t *__restrict__ offs, int nblocks,
                uint64_t *__restrict__ out)
 {
     __shared__ uint32_t cnt[SORT_WARPS][256];
@@ -111,7 +114,7 @@ k_sort_scatter(int64_t n, const double4 *__restrict__ rec, const int32_t *__rest
     for (int r = 0; r < SORT_ROUNDS; r++) {
         int64_t i = elem_index(base, warp, r, lane);
         const bool ok = i < n;
-        it[r] = ok ? (FIRST ? make_item(rec, chan, i, key_scale) : items[i]) : ~0ull;
+        it[r] = ok ? items[i] : ~0ull;
         const unsigned active = __ballot_sync(0xffffffffu, ok);
         if (ok) {
             const int d = (int)((it[r] >> shift) & 255);
@@ -170,31 +173,49 @@ k_sort_gather(int64_t n, int64_t n_pad, const uint64_t *__restrict__ items, cons
 
 }  // namespace
 
-// Sort ctx->d_rec[0..n) by key and write ctx->d_a/d_sw/d_swV/d_kz (padded to n_pad) and ctx->d_perm.
-int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max)
+// Stable LSD radix sort of n items (key << 32 | index) on `nbits` key bits, 8 bits per pass, ping-ponging between
+// buf0 (input) and buf1.  Returns the buffer holding the sorted items.
+uint64_t *fb_radix_sort_items(fb_ctx *ctx, int64_t n, uint64_t *buf0, uint64_t *buf1, int nbits, int *status)
 {
-    if (n <= 0) return 0;
+    *status = 0;
     const int nblocks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
     const size_t hist_need = (size_t)256 * nblocks;
     if (hist_need > ctx->hist_cap) {
-        if (ctx->d_hist) FB_CUDA(cudaFree(ctx->d_hist));
+        if (ctx->d_hist) cudaFree(ctx->d_hist);
         ctx->d_hist = nullptr;
-        FB_CUDA(cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * hist_need));
+        if (cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * hist_need) != cudaSuccess) { *status = -50; ctx->err = "radix sort: out of memory"; return nullptr; }
         ctx->hist_cap = hist_need;
     }
+    uint64_t *src = buf0, *dst = buf1;
+    for (int shift = 32; shift < 32 + nbits; shift += 8) {
+        k_sort_hist<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, src, shift, ctx->d_hist, nblocks);
+        k_sort_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, (int64_t)hist_need);
+        k_sort_scatter<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, src, shift, ctx->d_hist, nblocks, dst);
+        uint64_t *t = src; src = dst; dst = t;
+    }
+    if (cudaGetLastError() != cudaSuccess) { *status = -51; ctx->err = "radix sort: launch failed"; return nullptr; }
+    return src;
+}
+
+int fb_items_from_keys(fb_ctx *ctx, int64_t n, const int32_t *dev_keys, uint64_t *items)
+{
+    k_items_from_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, dev_keys, items);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Sort ctx->d_rec[0..n) by baseline bin and write ctx->d_a/d_sw/d_swV/d_kz (padded to n_pad) and ctx->d_perm.
+int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max)
+{
+    if (n <= 0) return 0;
     const double key_scale = a_max > 0 ? 65535.5 / a_max : 0.0;
     const double4 *rec = (const double4 *)ctx->d_rec;
     uint64_t *buf0 = ctx->d_items, *buf1 = ctx->d_items + ctx->cap;
-    // pass 0: low byte of the baseline bin
-    k_sort_hist<true><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, rec, nullptr, key_scale, nullptr, 32, ctx->d_hist, nblocks);
-    k_sort_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, (int64_t)hist_need);
-    k_sort_scatter<true><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, rec, nullptr, key_scale, nullptr, 32, ctx->d_hist, nblocks, buf0);
-    // pass 1: high byte
-    k_sort_hist<false><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, rec, nullptr, key_scale, buf0, 40, ctx->d_hist, nblocks);
-    k_sort_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, (int64_t)hist_need);
-    k_sort_scatter<false><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, rec, nullptr, key_scale, buf0, 40, ctx->d_hist, nblocks, buf1);
-    FB_CUDA(cudaGetLastError());
-    k_sort_gather<<<(unsigned)((n_pad + 255) / 256), 256, 0, ctx->stream>>>(n, n_pad, buf1, rec, ctx->d_a, ctx->d_sw, ctx->d_swV,
+    k_items_from_rec<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, rec, key_scale, buf0);
+    int st = 0;
+    uint64_t *sorted = fb_radix_sort_items(ctx, n, buf0, buf1, 16, &st);
+    if (st) return st;
+    k_sort_gather<<<(unsigned)((n_pad + 255) / 256), 256, 0, ctx->stream>>>(n, n_pad, sorted, rec, ctx->d_a, ctx->d_sw, ctx->d_swV,
                                                                          ctx->d_kz, ctx->d_perm);
     FB_CUDA(cudaGetLastError());
     return 0;

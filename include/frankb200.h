@@ -146,6 +146,18 @@ int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, doub
 int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, double alpha, double p0, const double *host_ldl,
                     double *host_chol, double *host_p_new, int *host_info);
 
+/* ---- UVDataBinner (frank/utilities.py:180-400) -------------------------------------------------------------
+ * fb_uv_max: max(uv) (the caller forms nbins = ceil(max / width) with the reference's guard, utilities.py:205-208).
+ * fb_uv_bin: bin index per visibility (bit-exact with the reference's floor(uv * (1/width)) and its three fix-ups,
+ *   :338-347), counts per bin (int64), sums [nbins*4] = (sum w uv, sum w, sum w Re V, sum w Im V) (:349-361) and
+ *   err [nbins*2] = (sum w^2 (Re V - mu)^2, sum w^2 (Im V - mu)^2) with mu the weighted bin mean (:236-247).
+ *   V is interleaved complex (v_is_complex != 0) or real.  Visibilities are stably sorted by bin and each bin
+ *   is reduced in a fixed order (deterministic). */
+int fb_uv_max(fb_ctx *ctx, int64_t n, const double *host_uv, double *host_max);
+int fb_uv_bin(fb_ctx *ctx, int64_t n, const double *host_uv, const double *host_V, int v_is_complex, const double *host_w,
+              int w_stride, double bin_width, int nbins, int32_t *host_idx, long long *host_counts, double *host_sums,
+              double *host_err);
+
 /* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]). */
 int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out);
 
