@@ -43,6 +43,7 @@ _SIGNATURES = {
     'fb_debug_prepped': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
+    'fb_predict_visibilities': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
     'fb_uv_max': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_uv_bin': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_ln_setup': ([_c_p, _c_p, _c_p, _c_d, _c_d], _c_i),
@@ -243,6 +244,16 @@ class Context(object):
         rc = self.check(self._lib.fb_ln_posterior(self._h, _ptr(s), _ptr(p), float(alpha or 0.0), float(p0 or 0.0), _ptr(ldl_c),
                                                   _ptr(chol), _ptr(p_new), _ptr(info)), 'fb_ln_posterior')
         return chol, p_new, rc
+
+    def predict_visibilities(self, q, kz, I, vis_model, model_scale, H2):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        I = np.ascontiguousarray(I, dtype=np.float64)
+        kzc = None if kz is None else np.ascontiguousarray(np.broadcast_to(kz, q.shape), dtype=np.float64)
+        H2c = None if H2 is None else np.ascontiguousarray(H2, dtype=np.float64)
+        V = np.empty_like(q)
+        self.check(self._lib.fb_predict_visibilities(self._h, q.size, _ptr(q), _ptr(kzc), _ptr(I), int(vis_model), float(model_scale),
+                                                     _ptr(H2c), _ptr(V)), 'fb_predict_visibilities')
+        return V
 
     # -- uv binning -----------------------------------------------------------------------------
     def uv_max(self, uv):

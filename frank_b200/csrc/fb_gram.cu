@@ -425,6 +425,30 @@ k_gram_finalize(int N, int NT, int P, long long n_tiles, const int *__restrict__
     }
 }
 
+// K8: predicted visibilities V_i = sum_k H_ik I_k, H_ik = c_k J0(a_i j_k) scale_ik   (statistical_models.py:279-329).
+// One warp per visibility, lanes stride over the modes; fixed shuffle tree.
+__global__ void __launch_bounds__(256)
+k_predict(int64_t n, int N, const double *__restrict__ q, const double *__restrict__ kz, double invQmax,
+          const double *__restrict__ jk, const double *__restrict__ ck, const double *__restrict__ Ik,
+          const double *__restrict__ H2, double scale, const double2 *__restrict__ tab, int rows, double *__restrict__ V)
+{
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const double a = __dmul_rn(q[i], invQmax);
+    double kk = 0.0;
+    if (H2) { kk = kz[i]; kk = -kk * kk; }
+    double acc = 0.0;
+    for (int k = lane; k < N; k += 32) {
+        double h = ck[k] * j0_tab(__dmul_rn(a, jk[k]), tab, rows - 1);
+        h *= H2 ? exp(kk * H2[k]) : scale;
+        acc = fma(h, Ik[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) V[i] = acc;
+}
+
 __global__ void k_j0_debug(int64_t n, const double *__restrict__ x, double *__restrict__ out, const double2 *tab, int rows)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -587,5 +611,47 @@ extern "C" int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double 
     FB_CUDA(cudaMemcpy(host_out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
     cudaFree(dx);
     cudaFree(dout);
+    return 0;
+}
+
+extern "C" int fb_predict_visibilities(fb_ctx *ctx, int64_t n, const double *host_q, const double *host_kz, const double *host_I,
+                                       int vis_model, double model_scale, const double *host_H2, double *host_V)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0) FB_FAIL(-11, "fb_predict_visibilities: fb_dht_setup has not been called");
+    if (n < 0 || !host_q || !host_I || !host_V) FB_FAIL(-12, "fb_predict_visibilities: bad arguments");
+    if (vis_model == FB_MODEL_DEBRIS && (!host_H2 || !host_kz)) FB_FAIL(-15, "fb_predict_visibilities: debris model needs kz and H2");
+    if (n == 0) return 0;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const int N = ctx->N;
+    double qmax = 0.0;
+    for (int64_t i = 0; i < n; i++) qmax = host_q[i] > qmax ? host_q[i] : qmax;
+    const double xneed = qmax * ctx->invQmax * ctx->h_jk[N - 1];
+    if (xneed * 4.0 + 2.0 > (double)ctx->tab_rows) {
+        int rc = fb_build_j0_table(ctx, xneed * 1.05);
+        if (rc) return rc;
+    }
+    const bool debris = vis_model == FB_MODEL_DEBRIS;
+    double *d_q = nullptr, *d_kz = nullptr, *d_I = nullptr, *d_V = nullptr;
+    FB_CUDA(cudaMalloc(&d_q, sizeof(double) * n));
+    FB_CUDA(cudaMalloc(&d_V, sizeof(double) * n));
+    FB_CUDA(cudaMalloc(&d_I, sizeof(double) * N));
+    FB_CUDA(cudaMemcpyAsync(d_q, host_q, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(d_I, host_I, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    if (debris) {
+        FB_CUDA(cudaMalloc(&d_kz, sizeof(double) * n));
+        FB_CUDA(cudaMemcpyAsync(d_kz, host_kz, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<double> h2(ctx->NC, 0.0);
+        for (int k = 0; k < N; k++) h2[k] = host_H2[k];
+        FB_CUDA(cudaMemcpyAsync(ctx->d_H2, h2.data(), sizeof(double) * ctx->NC, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    k_predict<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(n, N, d_q, d_kz, ctx->invQmax, ctx->d_jk, ctx->d_ck, d_I,
+                                                              debris ? ctx->d_H2 : nullptr, model_scale, ctx->d_tab, ctx->tab_rows, d_V);
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaMemcpyAsync(host_V, d_V, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_q); cudaFree(d_V); cudaFree(d_I);
+    if (d_kz) cudaFree(d_kz);
     return 0;
 }

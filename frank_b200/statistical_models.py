@@ -214,6 +214,29 @@ class VisibilityMapping(object):
             return hash[4] is None
         return False if hash[4] is None else bool(np.all(self._scale_height == hash[4]))
 
+    def predict_visibilities(self, I, q, k=None, geometry=None):
+        r"""Predicted (deprojected-plane) visibilities of the profile I at baselines q
+        (frank/statistical_models.py:279-329); k is the vertical uv-distance, needed by the debris model."""
+        q = np.asarray(q, dtype=np.float64)
+        ctx = self._context()
+        if self._vis_model == 'debris':
+            if k is None:
+                raise ValueError("the debris model needs the vertical uv-distance k")
+            return ctx.predict_visibilities(q.reshape(-1), np.asarray(k).reshape(-1), I, 2, 1.0, self._H2).reshape(q.shape)
+        return ctx.predict_visibilities(q.reshape(-1), None, I, _lib.MODEL_CODE[self._vis_model],
+                                        self._model_scale(geometry), None).reshape(q.shape)
+
+    def invert_visibilities(self, V, R, geometry=None):
+        r"""Brightness at radii R / arcsec from visibilities at the collocation frequencies
+        (frank/statistical_models.py:331-384); a handful of points, evaluated on the host."""
+        R = np.atleast_1d(R)
+        if self._vis_model == 'debris':
+            scale = np.ones(self.size)
+        else:
+            scale = np.atleast_1d(self._model_scale(geometry))
+        H = self._DHT.coefficients(R / rad_to_arcsec, direction='backward') * (1 / scale).reshape(1, -1)
+        return np.dot(H, V)[R < self.Rmax]
+
     # -- small host-side helpers kept for API compatibility -----------------------------------
     def transform(self, f, q=None, direction='forward'):
         if direction == 'backward' and q is not None:

@@ -158,6 +158,12 @@ int fb_uv_bin(fb_ctx *ctx, int64_t n, const double *host_uv, const double *host_
               int w_stride, double bin_width, int nbins, int32_t *host_idx, long long *host_counts, double *host_sums,
               double *host_err);
 
+/* ---- VisibilityMapping.predict_visibilities (frank/statistical_models.py:279-329) ---------------------------
+ * V_i = sum_k H_ik I_k with the same design rows as the mapping; q [n] deprojected baselines, kz [n] (debris model
+ * only), I [N] brightness at the collocation points, V [n] out. */
+int fb_predict_visibilities(fb_ctx *ctx, int64_t n, const double *host_q, const double *host_kz, const double *host_I,
+                            int vis_model, double model_scale, const double *host_H2, double *host_V);
+
 /* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]). */
 int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out);
 

@@ -197,3 +197,22 @@ def test_full_size_properties(fb):
     ref = fo.map_visibilities(fo.DHTTables(1.6 / fo.RAD_TO_ARCSEC, N), us, vs, Vs, ws, 30., 40., 1e-3, -2e-3, check_qbounds=False)
     got = vm.map_visibilities(us, vs, Vs, ws)
     assert gram_ok(got['M'], ref['M']) <= 1.0
+
+
+def test_predict_visibilities_vs_reference_golden(fb, golden):
+    """statistical_models.py:279-329 and FrankRadialFit.predict (radial_fitters.py:56-98)."""
+    g, f = golden('mapping.npz'), golden('fit_normal.npz')
+    dht, vm = mapping_from_golden(fb, g)
+    V = vm.predict_visibilities(g['I_pred'], g['q'], g['wp'])
+    assert np.max(np.abs(V - g['V_pred'])) <= 1e-13 * np.max(np.abs(g['V_pred']))
+    k = golden('gauss_kat.npz')                                   # frank/tests.py:97-130, inc = 60 deg
+    vmk = fb.VM(fb.DHT(5.0, 100), fb.FixedGeometry(60, 0), verbose=False)
+    Vk = vmk.predict_visibilities(k['I'], k['q'])
+    assert np.max(np.abs(Vk - k['V_model'])) <= 1e-13 * np.max(np.abs(k['V_model']))
+    np.testing.assert_allclose(Vk, k['V_exact'], atol=1e-5, rtol=0)
+    from frank_b200.radial_fitters import FrankFitter
+    FF = FrankFitter(1.6, int(g['N']), fb.FixedGeometry(*[float(x) for x in g['geom']]), verbose=False)
+    sol = FF.fit(g['u'], g['v'], g['V'], g['w'])
+    Vp = sol.predict(f['upred'], f['vpred'])
+    assert np.max(np.abs(Vp - f['Vpred'])) <= 1e-7 * np.max(np.abs(f['Vpred']))
+    assert np.max(np.abs(sol.predict_deprojected(sol.q) - f['Vpred_deproj'])) <= 1e-7 * np.max(np.abs(f['Vpred_deproj']))
