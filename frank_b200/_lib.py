@@ -188,7 +188,7 @@ class Context(object):
         self.check(rc, 'fb_gaussian_fit')
         return mu, chol, info, rc
 
-    def frank_normal_loop(self, M, j, p_init, alpha, p0, ldl, tol, max_iter, want_chol=True, hist_cap=0):
+    def frank_normal_loop(self, M, j, p_init, alpha, p0, Tinv, tol, max_iter, want_chol=True, hist_cap=0):
         """fb_frank_normal_loop for B hyper-parameter points.  Returns a dict."""
         N = M.shape[0]
         M = np.ascontiguousarray(M, dtype=np.float64)
@@ -197,13 +197,13 @@ class Context(object):
         B = p_init.shape[0]
         alpha = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64), (B,)))
         p0 = np.ascontiguousarray(np.broadcast_to(np.asarray(p0, dtype=np.float64), (B,)))
-        ldl = np.ascontiguousarray(np.broadcast_to(np.asarray(ldl, dtype=np.float64), (B, 3, N)))
+        Tinv = np.ascontiguousarray(np.broadcast_to(np.asarray(Tinv, dtype=np.float64), (B, N, N)))
         p = np.empty((B, N)); mu = np.empty((B, N))
         chol = np.empty((B, N, N)) if want_chol else None
         niter = np.zeros(B, dtype=np.int32); conv = np.zeros(B, dtype=np.int32); info = np.zeros(B, dtype=np.int32)
         hp = np.zeros((B, hist_cap, N)) if hist_cap > 0 else None
         hm = np.zeros((B, hist_cap, N)) if hist_cap > 0 else None
-        rc = self._lib.fb_frank_normal_loop(self._h, B, _ptr(M), _ptr(j), _ptr(p_init), _ptr(alpha), _ptr(p0), _ptr(ldl),
+        rc = self._lib.fb_frank_normal_loop(self._h, B, _ptr(M), _ptr(j), _ptr(p_init), _ptr(alpha), _ptr(p0), _ptr(Tinv),
                                             float(tol), int(max_iter), _ptr(p), _ptr(mu), _ptr(chol), _ptr(niter),
                                             _ptr(conv), _ptr(info), _ptr(hp), _ptr(hm), int(hist_cap))
         self.check(rc, 'fb_frank_normal_loop')
@@ -234,12 +234,12 @@ class Context(object):
                         'fb_ln_newton_direction')
         return g, dx, rc
 
-    def ln_posterior(self, s, p, alpha=None, p0=None, ldl=None, want_chol=True):
+    def ln_posterior(self, s, p, alpha=None, p0=None, Tinv=None, want_chol=True):
         s = np.ascontiguousarray(s, dtype=np.float64); p = np.ascontiguousarray(p, dtype=np.float64)
         N = s.size
         chol = np.empty((N, N)) if want_chol else None
-        p_new = np.empty(N) if ldl is not None else None
-        ldl_c = None if ldl is None else np.ascontiguousarray(ldl, dtype=np.float64)
+        p_new = np.empty(N) if Tinv is not None else None
+        ldl_c = None if Tinv is None else np.ascontiguousarray(Tinv, dtype=np.float64)
         info = np.zeros(1, dtype=np.int32)
         rc = self.check(self._lib.fb_ln_posterior(self._h, _ptr(s), _ptr(p), float(alpha or 0.0), float(p0 or 0.0), _ptr(ldl_c),
                                                   _ptr(chol), _ptr(p_new), _ptr(info)), 'fb_ln_posterior')

@@ -79,7 +79,7 @@ struct fb_ctx {
     // solver workspaces (fb_solve.cu)
     int sv_B = 0, sv_N = 0;
     double *sv_D = nullptr, *sv_p = nullptr, *sv_mu = nullptr, *sv_tr2 = nullptr, *sv_alpha = nullptr, *sv_p0 = nullptr;
-    double *sv_ldl = nullptr, *sv_M = nullptr, *sv_j = nullptr, *sv_Z = nullptr;
+    double *sv_Tinv = nullptr, *sv_M = nullptr, *sv_j = nullptr, *sv_Z = nullptr, *sv_rdiag = nullptr;
     int *sv_flags = nullptr;
     // LogNormal model state
     int ln_N = 0;

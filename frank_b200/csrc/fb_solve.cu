@@ -80,71 +80,120 @@ k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restri
 }
 
 // ---- Cholesky panel: factor A_kk, then U_kj = U_kk^-T A_kj for the block row ----------------------------------------
-// grid (nb - k, B): block x = 0 factors and stores the diagonal block, x > 0 solves block column k + x.
+// grid (nb - k, B): block x = 0 factors and stores the diagonal block, x > 0 solves block column k + x (and repeats
+// the 64 x 64 factorisation, which is cheaper than waiting for it).  Both the factorisation and the triangular
+// solve keep their 64 x 64 operand in registers (a 4 x 4 sub-block per thread); each of the 64 dependent steps
+// broadcasts one row through shared memory and costs one __syncthreads.
 __global__ void __launch_bounds__(256)
-k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active, int *__restrict__ info)
+k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active, int *__restrict__ info,
+             double *__restrict__ rdiag_all)
 {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     double *A = A_all + (size_t)b * N * N;
     extern __shared__ double dyn_sm[];
-    double (*D)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm);
-    double (*R)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm + NB * SLD);
-    __shared__ double diag[NB];
-    const int tid = threadIdx.x;
+    double (*D)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm);              // rows of U_kk as they become final
+    double (*X)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm + NB * SLD);   // rows of the solved block
+    __shared__ double rinv[NB];                                                // 1 / U_cc
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int j = k + blockIdx.x;
     const int r0 = k * NB, c0 = j * NB;
     const int nk = min(NB, N - r0), nj = min(NB, N - c0);
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        D[r][c] = (r < nk && c < nk && c >= r) ? A[(size_t)(r0 + r) * N + r0 + c] : (r == c ? 1.0 : 0.0);
-        if (blockIdx.x > 0) R[r][c] = (r < nk && c < nj) ? A[(size_t)(r0 + r) * N + c0 + c] : 0.0;
+    // ---- diagonal block into registers: rows ty*4.., columns tx*4.. (identity padding beyond nk)
+    double a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int i = ty * 4 + r, jj = tx * 4 + c;
+            a[r][c] = (i < nk && jj < nk && jj >= i) ? A[(size_t)(r0 + i) * N + r0 + jj] : (i == jj ? 1.0 : 0.0);
+        }
+    for (int c = 0; c < NB; c++) {
+        // the owners of row c publish it (unscaled); everybody scales it locally
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (ty * 4 + r == c) {
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) D[c][tx * 4 + cc] = a[r][cc];
+            }
+        __syncthreads();
+        const double piv = D[c][c];
+        if (tid == 0 && blockIdx.x == 0 && c < nk && !(piv > 0.0)) atomicCAS(&info[b], 0, r0 + c + 1);
+        // 1/sqrt(pivot) in one short dependency chain (MUFU seed + Newton) instead of an IEEE sqrt and a division:
+        // this chain is the critical path of the 64 dependent steps
+        const double inv = rsqrt(piv), d = piv * inv;
+        if (tid == 0) rinv[c] = inv;
+        double ui[4], uj[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) { ui[r] = D[c][ty * 4 + r] * inv; uj[r] = D[c][tx * 4 + r] * inv; }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const int i = ty * 4 + r, jj = tx * 4 + cc;
+                if (i > c && jj >= i) a[r][cc] = fma(-ui[r], uj[cc], a[r][cc]);
+                else if (i == c) a[r][cc] = jj > c ? uj[cc] : (jj == c ? d : a[r][cc]);
+            }
+        // no second barrier: row c of D is never written again, and row c + 1 is published only after every
+        // thread has passed this step's barrier... but a fast thread could publish row c + 1 while a slow one
+        // still reads row c -- different rows, no hazard.
     }
     __syncthreads();
-    // unblocked upper Cholesky of D in shared memory (every CTA of the panel repeats it: 64 short steps).
-    // Pivots go to diag[] so that D[c][c] can be read by every thread of step c without a write hazard.
-    const int tx = tid & 15, ty = tid >> 4;
-    for (int c = 0; c < nk; c++) {
-        const double piv = D[c][c];
-        const double d = sqrt(piv), inv = 1.0 / d;
-        if (tid == 0) {
-            diag[c] = d;
-            if (blockIdx.x == 0 && !(piv > 0.0)) atomicCAS(&info[b], 0, r0 + c + 1);
-        }
-        if (tid > c && tid < nk) D[c][tid] = D[c][tid] * inv;
-        __syncthreads();
-        // trailing update of the upper triangle: D[i][jj] -= U[c][i] U[c][jj], c < i <= jj
-        for (int i = c + 1 + ty; i < nk; i += 16) {
-            const double ui = D[c][i];
-            for (int jj = c + 1 + tx; jj < nk; jj += 16)
-                if (jj >= i) D[i][jj] = fma(-ui, D[c][jj], D[i][jj]);
-        }
-        __syncthreads();
-    }
-    if (tid < nk) D[tid][tid] = diag[tid];
+    // final U_kk rows into shared memory (scaled) for the triangular solve, and to global memory from CTA 0
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) D[ty * 4 + r][tx * 4 + cc] = a[r][cc];
     __syncthreads();
     if (blockIdx.x == 0) {
-        for (int e = tid; e < NB * NB; e += 256) {
-            const int r = e >> 6, c = e & 63;
-            if (r < nk && c < nk && c >= r) A[(size_t)(r0 + r) * N + r0 + c] = D[r][c];
-        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const int i = ty * 4 + r, jj = tx * 4 + cc;
+                if (i < nk && jj < nk && jj >= i) A[(size_t)(r0 + i) * N + r0 + jj] = a[r][cc];
+            }
+        if (tid < nk) rdiag_all[(size_t)b * N + r0 + tid] = rinv[tid];
         return;
     }
-    // forward substitution U_kk^T X = R.  Four threads of one warp share a column, so a warp-level barrier is
-    // all the synchronisation the 64 dependent steps need.
-    const int col = tid >> 2, part = tid & 3;
-    for (int r = 0; r < nk; r++) {
-        const double x = R[r][col] / D[r][r];
-        __syncwarp();
-        if (part == 0) R[r][col] = x;
-        for (int rr = r + 1 + part; rr < nk; rr += 4) R[rr][col] = fma(-D[r][rr], x, R[rr][col]);
-        __syncwarp();
+    // ---- forward substitution U_kk^T X = R with R in registers (rows ty*4.., columns tx*4..)
+    double rr_[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+            const int i = ty * 4 + r, jj = tx * 4 + cc;
+            rr_[r][cc] = (i < nk && jj < nj) ? A[(size_t)(r0 + i) * N + c0 + jj] : 0.0;
+        }
+    for (int r = 0; r < NB; r++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (ty * 4 + q == r) {
+                const double dinv = rinv[r];
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+                    const double x = rr_[q][cc] * dinv;
+                    rr_[q][cc] = x;
+                    X[r][tx * 4 + cc] = x;
+                }
+            }
+        __syncthreads();
+        double xr[4], ur[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { xr[q] = X[r][tx * 4 + q]; ur[q] = D[r][ty * 4 + q]; }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (ty * 4 + q > r)
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) rr_[q][cc] = fma(-ur[q], xr[cc], rr_[q][cc]);
     }
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        if (r < nk && c < nj) A[(size_t)(r0 + r) * N + c0 + c] = R[r][c];
-    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+            const int i = ty * 4 + r, jj = tx * 4 + cc;
+            if (i < nk && jj < nj) A[(size_t)(r0 + i) * N + c0 + jj] = rr_[r][cc];
+        }
 }
 
 // ---- trailing update A_ij -= U_ki^T U_kj, k < i <= j -----------------------------------------------------------------
@@ -199,12 +248,13 @@ constexpr int TS = 8;                  // right-hand sides per CTA: one warp per
 constexpr int TP = 32;                 // rows of U per staged panel
 
 __global__ void __launch_bounds__(256)
-k_trsm_tr2(int N, const double *__restrict__ U_all, const double *__restrict__ Y, const int *__restrict__ active,
-           double *__restrict__ tr2_all)
+k_trsm_tr2(int N, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ Y,
+           const int *__restrict__ active, double *__restrict__ tr2_all)
 {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     const double *U = U_all + (size_t)b * N * N;
+    const double *rdiag = rdiag_all + (size_t)b * N;
     extern __shared__ double sm[];
     double *Up = sm;                                        // [TP][N]  panel of U rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -220,7 +270,7 @@ k_trsm_tr2(int N, const double *__restrict__ U_all, const double *__restrict__ Y
         __syncthreads();
         for (int r = 0; r < nk; r++) {
             const double *Ur = Up + r * N;
-            const double z = Z[r1 + r] / Ur[r1 + r];
+            const double z = Z[r1 + r] * rdiag[r1 + r];
             ssq = fma(z, z, ssq);
             __syncwarp();
             for (int rr = r1 + r + 1 + lane; rr < N; rr += 32) Z[rr] = fma(-Ur[rr], z, Z[rr]);
@@ -235,13 +285,14 @@ k_trsm_tr2(int N, const double *__restrict__ U_all, const double *__restrict__ Y
 // contiguous): the PR x PR triangle is solved by one warp with shuffles, the rest of the panel is a
 // block update done by all threads.
 __global__ void __launch_bounds__(1024)
-k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__restrict__ jvec, int j_stride,
-           const int *__restrict__ active, double *__restrict__ mu_all)
+k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ jvec,
+           int j_stride, const int *__restrict__ active, double *__restrict__ mu_all)
 {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     const double *U = U_all + (size_t)b * N * N;
     extern __shared__ double shm[];
+    const double *rdiag = rdiag_all + (size_t)b * N;
     double *x = shm;                       // [N]  right-hand side / solution
     double *zp = shm + N;                  // [32] panel solution
     double *S = shm + N + 32;              // [PR][N] panel of U rows
@@ -256,9 +307,10 @@ k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__rest
         __syncthreads();
         if (warp == 0) {
             double xl = lane < nk ? x[r1 + lane] : 0.0;
+            const double rd = lane < nk ? rdiag[r1 + lane] : 0.0;
             for (int r = 0; r < nk; r++) {
                 double zr = 0.0;
-                if (lane == r) { xl = xl / S[r * N + r1 + r]; zr = xl; }
+                if (lane == r) { xl = xl * rd; zr = xl; }
                 zr = __shfl_sync(0xffffffffu, zr, r);
                 if (lane > r && lane < nk) xl = fma(-S[r * N + r1 + lane], zr, xl);
             }
@@ -290,9 +342,10 @@ k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__rest
         __syncthreads();
         if (warp == 0) {
             double al = lane < nk ? zp[lane] : 0.0;
+            const double rd = lane < nk ? rdiag[r1 + lane] : 0.0;
             for (int r = nk - 1; r >= 0; r--) {
                 double mr = 0.0;
-                if (lane == r) { al = al / S[r * N + r1 + r]; mr = al; }
+                if (lane == r) { al = al * rd; mr = al; }
                 mr = __shfl_sync(0xffffffffu, mr, r);
                 if (lane < r) al = fma(-S[lane * N + r1 + r], mr, al);
             }
@@ -303,32 +356,32 @@ k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__rest
     for (int i = tid; i < N; i += blockDim.x) mu_all[(size_t)b * N + i] = x[i];
 }
 
-// ---- power-spectrum update, one CTA per problem -----------------------------------------------------------------
-// Tr1 = (Y mu)^2 ; beta = (p0 + 0.5 (Tr1 + Tr2)) / p - (alpha - 1 + 0.5) ; (T + I) tau = beta + log p ; p_new = exp(tau).
-// The SPD pentadiagonal matrix T + I is passed as its banded L D L^T factorisation (host, once per filter):
-// ldl[0] = D, ldl[1] = L sub-diagonal 1, ldl[2] = L sub-diagonal 2.
-__global__ void __launch_bounds__(256)
+// ---- power-spectrum update, one CTA (1024 threads) per problem ----------------------------------------------------------
+// Tr1 = (Y mu)^2 ; beta = (p0 + 0.5 (Tr1 + Tr2)) / p - (alpha - 1 + 0.5) ; tau = (T + I)^-1 (beta + log p) ; p_new = exp(tau).
+// (T + I) is a fixed SPD pentadiagonal matrix per filter (condition number <= ~1e6); its dense inverse is formed once
+// on the host, so the solve is a matrix-vector product instead of 3 N dependent steps.
+__global__ void __launch_bounds__(1024)
 k_ps_update(int N, const double *__restrict__ Y, const double *__restrict__ mu_all, const double *__restrict__ tr2_all,
-            const double *__restrict__ alpha_all, const double *__restrict__ p0_all, const double *__restrict__ ldl_all,
-            int ldl_stride, double tol, int max_iter, double *__restrict__ p_all, int *__restrict__ active,
+            const double *__restrict__ alpha_all, const double *__restrict__ p0_all, const double *__restrict__ Tinv_all,
+            double tol, int max_iter, double *__restrict__ p_all, int *__restrict__ active,
             int *__restrict__ count, int *__restrict__ converged, double *__restrict__ hist_p, int hist_cap)
 {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
-    extern __shared__ double sh[];         // mu[N], rhs[N], ldl[3N]
-    double *mu = sh, *rhs = sh + N, *ldl_s = sh + 2 * N;
+    extern __shared__ double sh[];         // mu[N], rhs[N]
+    double *mu = sh, *rhs = sh + N;
     __shared__ int not_conv;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const double *p = p_all + (size_t)b * N;
-    const double *ldl = ldl_all + (size_t)b * ldl_stride;
-    for (int i = tid; i < N; i += 256) mu[i] = mu_all[(size_t)b * N + i];
-    for (int i = tid; i < 3 * N; i += 256) ldl_s[i] = ldl[i];
+    const double *Tinv = Tinv_all + (size_t)b * N * N;
+    for (int i = tid; i < N; i += blockDim.x) mu[i] = mu_all[(size_t)b * N + i];
     if (tid == 0) not_conv = 0;
     __syncthreads();
     const double alpha = alpha_all[b], p0 = p0_all[b];
-    for (int i = warp; i < N; i += 8) {
+    for (int i = warp; i < N; i += nw) {
         double s = 0.0;
-        for (int c = lane; c < N; c += 32) s = fma(Y[(size_t)i * N + c], mu[c], s);
+        const double *Yi = Y + (size_t)i * N;
+        for (int c = lane; c < N; c += 32) s = fma(Yi[c], mu[c], s);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
         if (lane == 0) {
@@ -338,36 +391,26 @@ k_ps_update(int N, const double *__restrict__ Y, const double *__restrict__ mu_a
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        // L y = rhs ; D w = y ; L^T tau = w   (unit lower-triangular L with two sub-diagonals)
-        const double *Dd = ldl_s, *L1 = ldl_s + N, *L2 = ldl_s + 2 * N;
-        for (int i = 0; i < N; i++) {
-            double v = rhs[i];
-            if (i >= 1) v = fma(-L1[i], rhs[i - 1], v);
-            if (i >= 2) v = fma(-L2[i], rhs[i - 2], v);
-            rhs[i] = v;
-        }
-        for (int i = 0; i < N; i++) rhs[i] = rhs[i] / Dd[i];
-        for (int i = N - 1; i >= 0; i--) {
-            double v = rhs[i];
-            if (i + 1 < N) v = fma(-L1[i + 1], rhs[i + 1], v);
-            if (i + 2 < N) v = fma(-L2[i + 2], rhs[i + 2], v);
-            rhs[i] = v;
-        }
-    }
-    __syncthreads();
     int bad = 0;
-    for (int i = tid; i < N; i += 256) {
-        const double pn = exp(rhs[i]), po = p[i];
-        if (!(fabs(pn - po) <= tol * pn)) bad = 1;
-        p_all[(size_t)b * N + i] = pn;
-        if (hist_p && count[b] < hist_cap) hist_p[((size_t)b * hist_cap + count[b]) * N + i] = pn;
+    const int cnt0 = count[b];
+    for (int i = warp; i < N; i += nw) {
+        double s = 0.0;
+        const double *Ti = Tinv + (size_t)i * N;
+        for (int c = lane; c < N; c += 32) s = fma(Ti[c], rhs[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const double pn = exp(s), po = p[i];
+            if (!(fabs(pn - po) <= tol * pn)) bad = 1;
+            mu[i] = pn;                      // staged: p is still being read by other warps
+            if (hist_p && cnt0 < hist_cap) hist_p[((size_t)b * hist_cap + cnt0) * N + i] = pn;
+        }
     }
     if (bad) atomicOr(&not_conv, 1);
     __syncthreads();
+    for (int i = tid; i < N; i += blockDim.x) p_all[(size_t)b * N + i] = mu[i];
     if (tid == 0) {
-        const int c = count[b] + 1;
-        count[b] = c;
+        count[b] = cnt0 + 1;
         converged[b] = not_conv ? 0 : 1;
         // while (not converged and count <= max_iter)          radial_fitters.py:769-770
         // (the solve of the new p still runs in this iteration; `active` is cleared afterwards by k_loop_gate)
@@ -474,8 +517,8 @@ static int ensure_solver_ws(fb_ctx *ctx, int B)
     const size_t N = ctx->N;
     if (B <= ctx->sv_B && ctx->sv_N == (int)N) return 0;
     for (void **p : {(void **)&ctx->sv_D, (void **)&ctx->sv_p, (void **)&ctx->sv_mu, (void **)&ctx->sv_tr2, (void **)&ctx->sv_alpha,
-                     (void **)&ctx->sv_p0, (void **)&ctx->sv_ldl, (void **)&ctx->sv_flags, (void **)&ctx->sv_M, (void **)&ctx->sv_j,
-                     (void **)&ctx->sv_Z}) {
+                     (void **)&ctx->sv_p0, (void **)&ctx->sv_Tinv, (void **)&ctx->sv_flags, (void **)&ctx->sv_M, (void **)&ctx->sv_j,
+                     (void **)&ctx->sv_Z, (void **)&ctx->sv_rdiag}) {
         if (*p) FB_CUDA(cudaFree(*p));
         *p = nullptr;
     }
@@ -483,9 +526,10 @@ static int ensure_solver_ws(fb_ctx *ctx, int B)
     FB_CUDA(cudaMalloc(&ctx->sv_p, sizeof(double) * B * N));
     FB_CUDA(cudaMalloc(&ctx->sv_mu, sizeof(double) * B * N));
     FB_CUDA(cudaMalloc(&ctx->sv_tr2, sizeof(double) * B * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_rdiag, sizeof(double) * B * N));
     FB_CUDA(cudaMalloc(&ctx->sv_alpha, sizeof(double) * B));
     FB_CUDA(cudaMalloc(&ctx->sv_p0, sizeof(double) * B));
-    FB_CUDA(cudaMalloc(&ctx->sv_ldl, sizeof(double) * B * 3 * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_Tinv, sizeof(double) * B * N * N));
     FB_CUDA(cudaMalloc(&ctx->sv_flags, sizeof(int) * (4 * B + 8)));
     FB_CUDA(cudaMalloc(&ctx->sv_M, sizeof(double) * N * N));
     FB_CUDA(cudaMalloc(&ctx->sv_j, sizeof(double) * N));
@@ -502,7 +546,7 @@ static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_i
     FB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
     FB_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
     for (int k = 0; k < nb; k++) {
-        k_chol_panel<<<dim3(nb - k, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info);
+        k_chol_panel<<<dim3(nb - k, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag);
         const int nt = nb - k - 1;
         if (nt > 0) k_chol_update<<<dim3(nt * (nt + 1) / 2, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active);
     }
@@ -510,7 +554,7 @@ static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_i
     while (PR > 1 && sizeof(double) * ((size_t)N + 32 + (size_t)PR * N) > 200 * 1024) PR /= 2;
     const size_t smem = sizeof(double) * ((size_t)N + 32 + (size_t)PR * N);
     FB_CUDA(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_mu<<<B, 1024, smem, ctx->stream>>>(N, PR, ctx->sv_D, ctx->sv_j, 0, d_active, ctx->sv_mu);
+    k_solve_mu<<<B, 1024, smem, ctx->stream>>>(N, PR, ctx->sv_D, ctx->sv_rdiag, ctx->sv_j, 0, d_active, ctx->sv_mu);
     FB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -527,7 +571,7 @@ static int launch_tr2(fb_ctx *ctx, int B, const int *d_active)
     const size_t smem = sizeof(double) * ((size_t)TP * N + (size_t)TS * N);
     if (smem > 220 * 1024) FB_FAIL(-33, "k_trsm_tr2: N too large for the staged panel");
     FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_trsm_tr2<<<dim3(slabs, B), 256, smem, ctx->stream>>>(N, ctx->sv_D, ctx->d_Y, d_active, ctx->sv_tr2);
+    k_trsm_tr2<<<dim3(slabs, B), 256, smem, ctx->stream>>>(N, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2);
     FB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -578,13 +622,13 @@ int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host
 }
 
 int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p_init,
-                         const double *host_alpha, const double *host_p0, const double *host_ldl, double tol, int max_iter,
+                         const double *host_alpha, const double *host_p0, const double *host_Tinv, double tol, int max_iter,
                          double *host_p, double *host_mu, double *host_chol, int *host_niter, int *host_converged,
                          int *host_info, double *host_hist_p, double *host_hist_mu, int hist_cap)
 {
     if (!ctx) return -1;
     if (ctx->N == 0 || !ctx->d_Y) FB_FAIL(-30, "fb_frank_normal_loop: fb_dht_setup (with Ycoef) has not been called");
-    if (B < 1 || !host_M || !host_j || !host_p_init || !host_alpha || !host_p0 || !host_ldl || !host_p || !host_mu || !host_niter)
+    if (B < 1 || !host_M || !host_j || !host_p_init || !host_alpha || !host_p0 || !host_Tinv || !host_p || !host_mu || !host_niter)
         FB_FAIL(-31, "fb_frank_normal_loop: bad arguments");
     FB_CUDA(cudaSetDevice(ctx->device));
     const size_t N = ctx->N;
@@ -602,7 +646,7 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p_init, sizeof(double) * B * N, cudaMemcpyHostToDevice, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(ctx->sv_alpha, host_alpha, sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(ctx->sv_p0, host_p0, sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
-    FB_CUDA(cudaMemcpyAsync(ctx->sv_ldl, host_ldl, sizeof(double) * B * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_Tinv, host_Tinv, sizeof(double) * B * N * N, cudaMemcpyHostToDevice, ctx->stream));
     double *d_hist_p = nullptr, *d_hist_mu = nullptr;
     if (hist_cap > 0 && host_hist_p && host_hist_mu) {
         FB_CUDA(cudaMalloc(&d_hist_p, sizeof(double) * (size_t)B * hist_cap * N));
@@ -621,12 +665,13 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     // One iteration = a fixed sequence of ~15 small kernels: capture it once into a CUDA graph and replay it
     // (launch-latency bound loop); the host polls the number of active problems every `poll` iterations.
     auto enqueue_iteration = [&]() -> int {
+        // the fit's mean was computed at the end of the previous iteration; Tr2 needs only the factor
         int r = launch_tr2(ctx, B, d_active);
         if (r) return r;
         if (d_active_prev) FB_CUDA(cudaMemcpyAsync(d_active_prev, d_active, sizeof(int) * B, cudaMemcpyDeviceToDevice, ctx->stream));
-        k_ps_update<<<B, 256, sizeof(double) * 5 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
-                                                                    ctx->sv_p0, ctx->sv_ldl, (int)(3 * N), tol, max_iter, ctx->sv_p,
-                                                                    d_active, d_count, d_conv, d_hist_p, hist_cap);
+        k_ps_update<<<B, 1024, sizeof(double) * 2 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
+                                                                     ctx->sv_p0, ctx->sv_Tinv, tol, max_iter, ctx->sv_p,
+                                                                     d_active, d_count, d_conv, d_hist_p, hist_cap);
         k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
         r = launch_factor_solve(ctx, B, d_active, d_info);
         if (r) return r;
@@ -775,7 +820,7 @@ int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, doub
         FB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
         FB_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
         for (int k = 0; k < nb; k++) {
-            k_chol_panel<<<dim3(nb - k, 1), 256, blk2, ctx->stream>>>((int)N, nb, k, ctx->sv_D, nullptr, d_info);
+            k_chol_panel<<<dim3(nb - k, 1), 256, blk2, ctx->stream>>>((int)N, nb, k, ctx->sv_D, nullptr, d_info, ctx->sv_rdiag);
             const int nt = nb - k - 1;
             if (nt > 0) k_chol_update<<<dim3(nt * (nt + 1) / 2, 1), 256, blk2, ctx->stream>>>((int)N, nb, k, ctx->sv_D, nullptr);
         }
@@ -785,7 +830,7 @@ int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, doub
     while (PR > 1 && sizeof(double) * (N + 32 + (size_t)PR * N) > 200 * 1024) PR /= 2;
     const size_t smem = sizeof(double) * (N + 32 + (size_t)PR * N);
     FB_CUDA(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_mu<<<1, 1024, smem, ctx->stream>>>((int)N, PR, ctx->sv_D, d_ng, 0, nullptr, ctx->sv_mu);
+    k_solve_mu<<<1, 1024, smem, ctx->stream>>>((int)N, PR, ctx->sv_D, ctx->sv_rdiag, d_ng, 0, nullptr, ctx->sv_mu);
     FB_CUDA(cudaGetLastError());
     int info = 0;
     if (host_g) FB_CUDA(cudaMemcpyAsync(host_g, d_g, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
@@ -799,7 +844,7 @@ int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, doub
 
 /* Posterior at the MAP point: factorise Hess(s_MAP) (statistical_models.py:1148-1158), optionally return the upper
  * factor, and run one CriticalFilter.update_power_spectrum with it (filter.py:154-177): p_new [N]. */
-int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, double alpha, double p0, const double *host_ldl,
+int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, double alpha, double p0, const double *host_Tinv,
                     double *host_chol, double *host_p_new, int *host_info)
 {
     if (!ctx || !ctx->ln_S || !host_s) return -1;
@@ -818,12 +863,12 @@ int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, dou
         FB_CUDA(cudaMemcpyAsync(ctx->sv_mu, host_s, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
         FB_CUDA(cudaMemcpyAsync(ctx->sv_alpha, &alpha, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         FB_CUDA(cudaMemcpyAsync(ctx->sv_p0, &p0, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        FB_CUDA(cudaMemcpyAsync(ctx->sv_ldl, host_ldl, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_Tinv, host_Tinv, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
         rc = launch_tr2(ctx, 1, nullptr);
         if (rc) return rc;
-        k_ps_update<<<1, 256, sizeof(double) * 5 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha, ctx->sv_p0,
-                                                                    ctx->sv_ldl, (int)(3 * N), 1e-3, 0, ctx->sv_p, nullptr, d_flags, d_flags + 1,
-                                                                    nullptr, 0);
+        k_ps_update<<<1, 1024, sizeof(double) * 2 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha, ctx->sv_p0,
+                                                                     ctx->sv_Tinv, 1e-3, 0, ctx->sv_p, nullptr, d_flags, d_flags + 1,
+                                                                     nullptr, 0);
         FB_CUDA(cudaGetLastError());
         FB_CUDA(cudaMemcpyAsync(host_p_new, ctx->sv_p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
     }

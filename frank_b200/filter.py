@@ -64,6 +64,25 @@ def banded_ldl(bands):
     return np.stack([d, l1, l2])
 
 
+def banded_inverse(ldl):
+    r"""Dense inverse of A = L D L^T given banded_ldl(A): column c solves L D L^T x = e_c.  O(N^2)."""
+    d, l1, l2 = ldl
+    N = d.size
+    X = np.eye(N)
+    for i in range(N):                       # L y = e
+        if i >= 1:
+            X[i] -= l1[i] * X[i - 1]
+        if i >= 2:
+            X[i] -= l2[i] * X[i - 2]
+    X /= d[:, None]
+    for i in range(N - 1, -1, -1):           # L^T x = y
+        if i + 1 < N:
+            X[i] -= l1[i + 1] * X[i + 1]
+        if i + 2 < N:
+            X[i] -= l2[i + 2] * X[i + 2]
+    return X
+
+
 class CriticalFilter(object):
     """Optimiser for power-spectrum priors (frank/filter.py:64-263).
 
@@ -80,13 +99,16 @@ class CriticalFilter(object):
         bands = smoothing_bands(DHT, weights_smooth)
         bands[2] += 1.0                                      # T + I  (filter.py:155)
         self._ldl = banded_ldl(bands)
+        # dense inverse of the SPD pentadiagonal T + I through its banded factorisation (host, once per filter): the
+        # device then solves (T + I) tau = rhs with one matrix-vector product per iteration
+        self._Tinv = banded_inverse(self._ldl)
 
     def update_power_spectrum(self, fit, device=None):
         """One fixed-point update of the power spectrum for the current fit (frank/filter.py:154-177)."""
         ctx = _lib.get_context(device)
         ctx.dht_setup(self._DHT)
         # one pass of the device loop: max_iter = 0 lets exactly one update through (count <= max_iter)
-        out = ctx.frank_normal_loop(fit._M, fit._j, fit.power_spectrum, self._alpha, self._p_0, self._ldl,
+        out = ctx.frank_normal_loop(fit._M, fit._j, fit.power_spectrum, self._alpha, self._p_0, self._Tinv,
                                     self._tol, 0, want_chol=False)
         return out['p'][0]
 

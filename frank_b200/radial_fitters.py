@@ -236,7 +236,7 @@ class FrankFitter(FourierBesselFitter):
         ctx = _lib.get_context(self._device)
         ctx.dht_setup(self._DHT)
         hist_cap = self._max_iter + 2 if self._store_iteration_diagnostics else 0
-        out = ctx.frank_normal_loop(self._M, self._j, pI, self._filter._alpha, self._filter._p_0, self._filter._ldl,
+        out = ctx.frank_normal_loop(self._M, self._j, pI, self._filter._alpha, self._filter._p_0, self._filter._Tinv,
                                     self._tol, self._max_iter, want_chol=True, hist_cap=hist_cap)
         if out['status'] == _lib.FB_E_NOTPD:
             raise np.linalg.LinAlgError("posterior precision matrix lost positive definiteness during the "
@@ -269,7 +269,7 @@ class FrankFitter(FourierBesselFitter):
         count, pi_old = 0, 0
         while (not self._filter.check_convergence(pI, pi_old)) and count <= self._max_iter:
             pi_old = pI.copy()
-            pI = fit._update_power_spectrum(self._filter._alpha, self._filter._p_0, self._filter._ldl)
+            pI = fit._update_power_spectrum(self._filter._alpha, self._filter._p_0, self._filter._Tinv)
             fit = self._perform_fit(pI, guess=fit.MAP)
             if self._store_iteration_diagnostics:
                 self._iteration_diagnostics['power_spectrum'].append(pI)

@@ -454,11 +454,11 @@ class LogNormalMAPModel(object):
         chol, _, rc = ctx.ln_posterior(s, p)                                          # cho_factor(hess(s)), :1148-1150
         self._U = np.triu(chol)
 
-    def _update_power_spectrum(self, alpha, p0, ldl):
+    def _update_power_spectrum(self, alpha, p0, Tinv):
         """CriticalFilter.update_power_spectrum with this model's Hessian factor (device)."""
         self._ctx.ln_setup(self._M, self._j, self._s0, self._full_hess)
         self._ctx.ln_set_spectrum(self._p)
-        _, p_new, _ = self._ctx.ln_posterior(self._s_MAP, self._p, alpha, p0, ldl, want_chol=False)
+        _, p_new, _ = self._ctx.ln_posterior(self._s_MAP, self._p, alpha, p0, Tinv, want_chol=False)
         return p_new
 
     def Dsolve(self, b):

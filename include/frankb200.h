@@ -117,13 +117,14 @@ int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host
  *     while not converged(p, p_old) and count <= max_iter:
  *         p_old = p ; p = CriticalFilter.update_power_spectrum(fit) ; fit = GaussianModel(p) ; count += 1
  * entered with the fit of p_init.  alpha [B], p0 [B] are the inverse-gamma prior parameters (filter.py:170-173);
- * ldl [B*3*N] is the banded L D L^T factorisation of the pentadiagonal SPD matrix T + I of each point
- * (filter.py:23-62, 155): D, then the first and second sub-diagonal of the unit lower factor.
+ * Tinv [B*N*N] is the dense inverse of the SPD pentadiagonal matrix T + I of each point (filter.py:23-62, 155;
+ * condition number <= ~1e6), formed once per filter on the host: the reference's sparse solve (filter.py:175) becomes
+ * a matrix-vector product.
  * Outputs: p [B*N] final spectrum, mu [B*N] its posterior mean, chol [B*N*N] (optional), niter [B] = count,
  * converged [B], info [B]; hist_p / hist_mu [B*hist_cap*N] (optional) receive every iteration's p and mu
  * (FrankFitter's iteration_diagnostics). */
 int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p_init,
-                         const double *host_alpha, const double *host_p0, const double *host_ldl, double tol, int max_iter,
+                         const double *host_alpha, const double *host_p0, const double *host_Tinv, double tol, int max_iter,
                          double *host_p, double *host_mu, double *host_chol, int *host_niter, int *host_converged,
                          int *host_info, double *host_hist_p, double *host_hist_mu, int hist_cap);
 
@@ -143,7 +144,7 @@ int fb_ln_setup(fb_ctx *ctx, const double *host_M, const double *host_j, double 
 int fb_ln_set_spectrum(fb_ctx *ctx, const double *host_p);
 int fb_ln_eval(fb_ctx *ctx, const double *host_s, double *host_f, double *host_g);
 int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, double *host_g, double *host_dx, int *host_info);
-int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, double alpha, double p0, const double *host_ldl,
+int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, double alpha, double p0, const double *host_Tinv,
                     double *host_chol, double *host_p_new, int *host_info);
 
 /* ---- UVDataBinner (frank/utilities.py:180-400) -------------------------------------------------------------

@@ -18,7 +18,7 @@ ctx = _lib.get_context(); ctx.dht_setup(dht)
 FF = FrankFitter(1.6, N, geom, verbose=False)
 FF._build_matrices({'hash': [False, dht, geom, 'opt_thick', None], 'M': g['M_opt_thick'], 'j': g['j_opt_thick'], 'null_likelihood': 0.0})
 p_init = FF._starting_spectrum()
-out = ctx.frank_normal_loop(g['M_opt_thick'], g['j_opt_thick'], p_init, 1.05, 1e-15, FF._filter._ldl, 1e-3, 2000)
+out = ctx.frank_normal_loop(g['M_opt_thick'], g['j_opt_thick'], p_init, 1.05, 1e-15, FF._filter._Tinv, 1e-3, 2000)
 peak = np.abs(f['MAP']).max()
 print('solver on reference M,j: iters', out['niter'][0], int(f['num_iterations']), 'MAP diff/peak', np.abs(out['mu'][0] - f['MAP']).max() / peak,
       'p rel', np.abs(out['p'][0] / f['power_spectrum'] - 1).max())

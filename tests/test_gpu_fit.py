@@ -152,9 +152,9 @@ def test_batched_sweep_matches_single_fits(fb, golden):
                         'null_likelihood': 0.0})
     p_init = FF._starting_spectrum()
     out = ctx.frank_normal_loop(g['M_opt_thick'], g['j_opt_thick'], np.tile(p_init, (4, 1)), np.array(alphas),
-                                np.full(4, 1e-15), np.stack([f._ldl for f in filts]), 1e-3, 2000)
+                                np.full(4, 1e-15), np.stack([f._Tinv for f in filts]), 1e-3, 2000)
     for b in range(4):
-        one = ctx.frank_normal_loop(g['M_opt_thick'], g['j_opt_thick'], p_init, alphas[b], 1e-15, filts[b]._ldl, 1e-3, 2000)
+        one = ctx.frank_normal_loop(g['M_opt_thick'], g['j_opt_thick'], p_init, alphas[b], 1e-15, filts[b]._Tinv, 1e-3, 2000)
         assert out['niter'][b] == one['niter'][0]
         assert np.array_equal(out['p'][b], one['p'][0]) and np.array_equal(out['mu'][b], one['mu'][0])
 
