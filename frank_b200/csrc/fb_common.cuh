@@ -87,6 +87,8 @@ struct fb_ctx {
     double ln_s0 = 0.0, ln_full_hess = 1.0;
     cudaEvent_t ev[8] = {};
     cudaEvent_t tev[2] = {};
+    cudaStream_t stream2 = nullptr;     // fork / join branch of the solver graph
+    cudaEvent_t fev[2] = {};
     double timing[4] = {0, 0, 0, 0};
     int num_sms = 148;
     int64_t last_n = 0;

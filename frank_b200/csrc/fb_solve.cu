@@ -434,7 +434,7 @@ __global__ void k_copy_hist_mu(int N, const double *__restrict__ mu_all, const i
                                double *__restrict__ hist_mu, int hist_cap)
 {
     const int b = blockIdx.x;
-    if (!active_before[b]) return;
+    if (active_before && !active_before[b]) return;
     const int c = count[b] - 1;
     if (c < 0 || c >= hist_cap) return;
     for (int i = threadIdx.x; i < N; i += blockDim.x) hist_mu[((size_t)b * hist_cap + c) * N + i] = mu_all[(size_t)b * N + i];
@@ -539,7 +539,7 @@ static int ensure_solver_ws(fb_ctx *ctx, int B)
 }
 
 // factor D^-1 (in ctx->sv_D) for all active problems and solve for mu
-static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_info)
+static int launch_factor(fb_ctx *ctx, int B, const int *d_active, int *d_info)
 {
     const int N = ctx->N, nb = (N + NB - 1) / NB;
     const size_t blk2 = sizeof(double) * 2 * NB * SLD;
@@ -550,13 +550,27 @@ static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_i
         const int nt = nb - k - 1;
         if (nt > 0) k_chol_update<<<dim3(nt * (nt + 1) / 2, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active);
     }
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_solve(fb_ctx *ctx, int B, const int *d_active, cudaStream_t stream)
+{
+    const int N = ctx->N;
     int PR = 32;
     while (PR > 1 && sizeof(double) * ((size_t)N + 32 + (size_t)PR * N) > 200 * 1024) PR /= 2;
     const size_t smem = sizeof(double) * ((size_t)N + 32 + (size_t)PR * N);
     FB_CUDA(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_mu<<<B, 1024, smem, ctx->stream>>>(N, PR, ctx->sv_D, ctx->sv_rdiag, ctx->sv_j, 0, d_active, ctx->sv_mu);
+    k_solve_mu<<<B, 1024, smem, stream>>>(N, PR, ctx->sv_D, ctx->sv_rdiag, ctx->sv_j, 0, d_active, ctx->sv_mu);
     FB_CUDA(cudaGetLastError());
     return 0;
+}
+
+static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_info)
+{
+    int rc = launch_factor(ctx, B, d_active, d_info);
+    if (rc) return rc;
+    return launch_solve(ctx, B, d_active, ctx->stream);
 }
 
 static int allow_build_smem(fb_ctx *ctx)
@@ -655,27 +669,31 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     const int nb = ((int)N + NB - 1) / NB;
     rc = allow_build_smem(ctx);
     if (rc) return rc;
-    // fit for the initial spectrum (the reference enters the loop with `fit` of p_init, radial_fitters.py:752-763)
+    // Factor for the initial spectrum (the reference enters the loop with `fit` of p_init, radial_fitters.py:752-763).
+    // The posterior mean of a factor is computed at the START of the next iteration, concurrently with the Tr2
+    // triangular solves (both only read U): fork / join inside the captured graph.
     k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
-    rc = launch_factor_solve(ctx, B, d_active, d_info);
+    rc = launch_factor(ctx, B, d_active, d_info);
     if (rc) return rc;
-    int *d_active_prev = nullptr;
-    if (d_hist_mu) FB_CUDA(cudaMalloc(&d_active_prev, sizeof(int) * B));
+    if (!ctx->stream2) FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    if (!ctx->fev[0]) { FB_CUDA(cudaEventCreateWithFlags(&ctx->fev[0], cudaEventDisableTiming)); FB_CUDA(cudaEventCreateWithFlags(&ctx->fev[1], cudaEventDisableTiming)); }
 
-    // One iteration = a fixed sequence of ~15 small kernels: capture it once into a CUDA graph and replay it
-    // (launch-latency bound loop); the host polls the number of active problems every `poll` iterations.
     auto enqueue_iteration = [&]() -> int {
-        // the fit's mean was computed at the end of the previous iteration; Tr2 needs only the factor
-        int r = launch_tr2(ctx, B, d_active);
+        FB_CUDA(cudaEventRecord(ctx->fev[0], ctx->stream));                    // fork
+        FB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->fev[0], 0));
+        int r = launch_solve(ctx, B, d_active, ctx->stream2);                  // mu of the current factor
         if (r) return r;
-        if (d_active_prev) FB_CUDA(cudaMemcpyAsync(d_active_prev, d_active, sizeof(int) * B, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (d_hist_mu) k_copy_hist_mu<<<B, 256, 0, ctx->stream2>>>((int)N, ctx->sv_mu, d_count, d_active, d_hist_mu, hist_cap);
+        FB_CUDA(cudaEventRecord(ctx->fev[1], ctx->stream2));
+        r = launch_tr2(ctx, B, d_active);                                      // Tr2 of the current factor
+        if (r) return r;
+        FB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->fev[1], 0));             // join
         k_ps_update<<<B, 1024, sizeof(double) * 2 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
                                                                      ctx->sv_p0, ctx->sv_Tinv, tol, max_iter, ctx->sv_p,
                                                                      d_active, d_count, d_conv, d_hist_p, hist_cap);
         k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
-        r = launch_factor_solve(ctx, B, d_active, d_info);
+        r = launch_factor(ctx, B, d_active, d_info);
         if (r) return r;
-        if (d_hist_mu) k_copy_hist_mu<<<B, 256, 0, ctx->stream>>>((int)N, ctx->sv_mu, d_count, d_active_prev, d_hist_mu, hist_cap);
         k_loop_gate<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, max_iter, d_count, d_conv, d_active, d_nact);
         return 0;
     };
@@ -700,6 +718,10 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     }
     cudaGraphExecDestroy(gexec);
     cudaGraphDestroy(graph);
+    // posterior mean of the final factor (every problem)
+    rc = launch_solve(ctx, B, nullptr, ctx->stream);
+    if (rc) return rc;
+    if (d_hist_mu) k_copy_hist_mu<<<B, 256, 0, ctx->stream>>>((int)N, ctx->sv_mu, d_count, nullptr, d_hist_mu, hist_cap);
     FB_CUDA(cudaMemcpyAsync(host_p, ctx->sv_p, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(host_mu, ctx->sv_mu, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
     if (host_chol) FB_CUDA(cudaMemcpyAsync(host_chol, ctx->sv_D, sizeof(double) * B * N * N, cudaMemcpyDeviceToHost, ctx->stream));
@@ -712,7 +734,7 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
         FB_CUDA(cudaMemcpyAsync(host_hist_mu, d_hist_mu, sizeof(double) * (size_t)B * hist_cap * N, cudaMemcpyDeviceToHost, ctx->stream));
     }
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (d_hist_p) { cudaFree(d_hist_p); cudaFree(d_hist_mu); cudaFree(d_active_prev); }
+    if (d_hist_p) { cudaFree(d_hist_p); cudaFree(d_hist_mu); }
     int worst = 0;
     for (int b = 0; b < B; b++) {
         if (host_converged) host_converged[b] = conv[b];
