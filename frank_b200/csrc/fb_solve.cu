@@ -244,11 +244,10 @@ k_chol_update(int N, int nb, int k, double *__restrict__ A_all, const int *__res
 // of Z (kept in shared memory, or in a global scratch when N is large).  U is walked in panels of TP rows staged
 // in shared memory (rows of the row-major upper factor are contiguous -> coalesced), so the N dependent steps
 // touch shared memory only and need nothing but warp-level barriers inside a panel.
-constexpr int TS = 8;                  // right-hand sides per CTA: one warp per column
-constexpr int TP = 32;                 // rows of U per staged panel
+constexpr int TS = 8;                  // right-hand sides per CTA (one warp per column); fewer for very large N
 
 __global__ void __launch_bounds__(256)
-k_trsm_tr2(int N, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ Y,
+k_trsm_tr2(int N, int TP, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ Y,
            const int *__restrict__ active, double *__restrict__ tr2_all)
 {
     const int b = blockIdx.y;
@@ -259,13 +258,14 @@ k_trsm_tr2(int N, const double *__restrict__ U_all, const double *__restrict__ r
     double *Up = sm;                                        // [TP][N]  panel of U rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *Z = sm + TP * N + warp * N;                     // [N] this warp's right-hand side / solution
-    const int c = blockIdx.x * TS + warp;                   // right-hand side = row c of Y
+    const int nwarp = blockDim.x >> 5;
+    const int c = blockIdx.x * nwarp + warp;                // right-hand side = row c of Y
     for (int r = lane; r < N; r += 32) Z[r] = c < N ? Y[(size_t)c * N + r] : 0.0;
     double ssq = 0.0;
     for (int r1 = 0; r1 < N; r1 += TP) {
         const int nk = min(TP, N - r1);
         __syncthreads();
-        for (int r = warp; r < nk; r += 8)
+        for (int r = warp; r < nk; r += nwarp)
             for (int cc = r1 + lane; cc < N; cc += 32) Up[r * N + cc] = U[(size_t)(r1 + r) * N + cc];
         __syncthreads();
         for (int r = 0; r < nk; r++) {
@@ -581,11 +581,16 @@ static int allow_build_smem(fb_ctx *ctx)
 
 static int launch_tr2(fb_ctx *ctx, int B, const int *d_active)
 {
-    const int N = ctx->N, slabs = (N + TS - 1) / TS;
-    const size_t smem = sizeof(double) * ((size_t)TP * N + (size_t)TS * N);
-    if (smem > 220 * 1024) FB_FAIL(-33, "k_trsm_tr2: N too large for the staged panel");
+    const int N = ctx->N;
+    // shared memory: TP staged rows of U + one right-hand side per warp; shrink both for very large N
+    int ts = TS, tp = 32;
+    while (sizeof(double) * ((size_t)tp + ts) * N > 200 * 1024 && tp > 4) tp /= 2;
+    while (sizeof(double) * ((size_t)tp + ts) * N > 200 * 1024 && ts > 1) ts /= 2;
+    const size_t smem = sizeof(double) * ((size_t)tp + ts) * N;
+    if (smem > 220 * 1024) FB_FAIL(-33, "k_trsm_tr2: N too large");
+    const int slabs = (N + ts - 1) / ts;
     FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_trsm_tr2<<<dim3(slabs, B), 256, smem, ctx->stream>>>(N, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2);
+    k_trsm_tr2<<<dim3(slabs, B), 32 * ts, smem, ctx->stream>>>(N, tp, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -242,3 +242,16 @@ def test_lognormal_objective_gradient_vs_oracle(fb, golden):
     ctx.ln_set_spectrum(1e2 * (odht.q / odht.q[0]) ** -4)
     _, _, rc = ctx.ln_newton_direction(f['s_MAP'] + 0.5 * np.sin(np.arange(N)), True)
     assert rc in (0, fb.lib.FB_E_NOTPD)
+
+
+def test_large_N_fit_vs_oracle(fb):
+    """N = 1000 (multi-panel Gram, small-shared-memory variants of the solver kernels) against the oracle."""
+    n, N = 30000, 1000
+    u, v, V, w, odht = fo.synthetic_disc(n, N, seed=8)
+    FF = fb.FrankFitter(1.6, N, fb.FixedGeometry(30., 40., 1e-3, -2e-3), alpha=1.3, weights_smooth=1e-1, verbose=False,
+                        store_iteration_diagnostics=True, max_iter=40, convergence_failure='ignore')
+    sol = FF.fit(u, v, V, w)
+    m = fo.map_visibilities(odht, u, v, V, w, 30., 40., 1e-3, -2e-3)
+    ref = fo.frank_fit(odht, m['M'], m['j'], alpha=1.3, weights_smooth=1e-1, max_iter=40)
+    assert FF.iteration_diagnostics['num_iterations'] == ref['num_iterations']
+    assert peak_err(sol.MAP, ref['MAP']) <= 1e-6
