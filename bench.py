@@ -275,8 +275,8 @@ def main():
                        'l2': 'inputs (400 MB per step) exceed the 126 MB L2', 'multi_gpu': 'visibility shards + NCCL all-reduce of (M, j, H0)'},
             'e2e': {'value': e2e_value, 'unit': 'Gvis.mode/s', 'h2d_bytes_per_step': 40 * n, 'd2h_bytes_per_step': 8 * (N * N + N + 1),
                     'ms_per_step': float(t.item()), 'steps': e2e_steps, 'host_buffers': 'pinned'},
-            'gpu_launches': 11 * args.steps,
-            'kernels_per_step': ['k_prep', 'k_prep_reduce', 'k_sort_hist x2', 'k_sort_scan x2', 'k_sort_scatter x2', 'k_sort_gather',
+            'gpu_launches': 12 * args.steps,
+            'kernels_per_step': ['k_prep', 'k_prep_reduce', 'k_items_from_rec', 'k_sort_hist x2', 'k_sort_scan x2', 'k_sort_scatter x2', 'k_sort_gather',
                                  'k_gram', 'k_gram_finalize'],
             'roofline': {'bound': 'tensor', 'kernel': 'k_gram (fused J0 + FP64 DMMA Gram)', 'achieved': achieved,
                          'peak': FP64_DMMA_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_DMMA_PEAK_TFLOPS,

@@ -62,39 +62,48 @@ k_sort_hist(int64_t n, const uint64_t *__restrict__ items, int shift, uint32_t *
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of `total` uint32 counters, single block of 1024 threads, slab per thread
+// exclusive scan of `total` uint32 counters in place: one block of 1024 threads walks the array in coalesced
+// chunks of 4096 (4 per thread), block-scanning each chunk with warp shuffles and carrying the running total
 __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *__restrict__ data, int64_t total)
 {
     __shared__ uint32_t warp_sums[32];
-    const int64_t per = (total + 1023) / 1024;
-    const int64_t b0 = (int64_t)threadIdx.x * per, b1 = b0 + per < total ? b0 + per : total;
-    uint32_t s = 0;
-    for (int64_t i = b0; i < b1; i++) s += data[i];
-    // block exclusive scan of s
+    __shared__ uint32_t carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_sums[warp] = inc;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_sums[lane], winc = w;
+    for (int64_t base = 0; base < total; base += 4096) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = i0 + k < total ? data[i0 + k] : 0u;
+        const uint32_t s = v[0] + v[1] + v[2] + v[3];
+        uint32_t inc = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
-        warp_sums[lane] = winc - w;
-    }
-    __syncthreads();
-    uint32_t run = warp_sums[warp] + inc - s;
-    for (int64_t i = b0; i < b1; i++) {
-        uint32_t c = data[i];
-        data[i] = run;
-        run += c;
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_sums[lane] = winc - w;
+            if (lane == 31) carry_s = carry + winc;
+        }
+        __syncthreads();
+        uint32_t run = carry + warp_sums[warp] + inc - s;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < total) data[i0 + k] = run;
+            run += v[k];
+        }
+        __syncthreads();
     }
 }
 

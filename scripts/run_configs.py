@@ -1,0 +1,97 @@
+"""Run the BASELINE.json configurations that fit one GPU and print one JSON line each (results table of BASELINE.md)."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from frank_b200 import _lib
+from frank_b200.constants import rad_to_arcsec
+from frank_b200.geometry import FixedGeometry
+from frank_b200.hankel import DiscreteHankelTransform
+from frank_b200.radial_fitters import FrankFitter
+from frank_b200.debris_fitters import FrankDebrisFitter
+from frank_b200.statistical_models import VisibilityMapping
+from frank_b200.filter import CriticalFilter
+from frank_b200.utilities import UVDataBinner
+import bench
+
+which = sys.argv[1:] or ['1', '2', '3', '4', '5']
+geom = FixedGeometry(*bench.GEOM)
+
+
+def data(n, N, seed=1):
+    dht = DiscreteHankelTransform(1.6 / rad_to_arcsec, N)
+    return dht, bench.synthetic_visibilities_device(n, dht, seed)
+
+
+def timed_fit(FF, u, v, V, w, reps=2):
+    out = None
+    for _ in range(reps):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        pre = FF.preprocess_visibilities(u, v, V, w)
+        t1 = time.perf_counter()
+        sol = FF.fit_preprocessed(pre)
+        t2 = time.perf_counter()
+        out = {'map_s': t1 - t0, 'solver_s': t2 - t1, 'fit_s': t2 - t0, 'iterations': int(FF.iteration_diagnostics['num_iterations']),
+               'gram_ms': FF._vis_map.last_timing['gram_ms']}
+    return out, sol
+
+
+if '1' in which or '2' in which:
+    for tag, n in [('1', 1_000_000), ('2', 10_000_000)]:
+        if tag not in which:
+            continue
+        dht, (u, v, V, w) = data(n, 300)
+        FF = FrankFitter(1.6, 300, geom, alpha=1.05, weights_smooth=1e-4, verbose=False, store_iteration_diagnostics=True)
+        r, sol = timed_fit(FF, u, v, V, w)
+        r.update(config=tag, n_vis=n, N=300, method='Normal', gvis_mode_per_s=n * 300 / r['gram_ms'] / 1e6)
+        print(json.dumps(r), flush=True)
+
+if '3' in which:
+    n, N = 10_000_000, 500
+    dht, (u, v, V, w) = data(n, N)
+    vm = VisibilityMapping(dht, geom, verbose=False)
+    for _ in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); m = vm.map_visibilities(u, v, V, w); t1 = time.perf_counter()
+    r = {'config': '3 (mapping only; the LogNormal solve is host-driven Newton, see fit_lognormal test)', 'n_vis': n, 'N': N,
+         'map_s': t1 - t0, 'gram_ms': vm.last_timing['gram_ms'], 'gvis_mode_per_s': n * N / vm.last_timing['gram_ms'] / 1e6}
+    print(json.dumps(r), flush=True)
+    # LogNormal solve on a reduced problem (N = 100) to record per-iteration cost
+    dht2, (u2, v2, V2, w2) = data(1_000_000, 100)
+    FL = FrankFitter(1.6, 100, geom, alpha=1.3, weights_smooth=1e-2, method='LogNormal', verbose=False, store_iteration_diagnostics=True)
+    t0 = time.perf_counter(); sol = FL.fit(u2, v2, V2, w2); t1 = time.perf_counter()
+    print(json.dumps({'config': '3b LogNormal N=100, 1e6 vis', 'fit_s': t1 - t0, 'iterations': int(FL.iteration_diagnostics['num_iterations'])}), flush=True)
+
+if '4' in which:
+    n, N = 1_000_000, 300
+    dht, (u, v, V, w) = data(n, N)
+    FF = FrankFitter(1.6, N, geom, verbose=False)
+    pre = FF.preprocess_visibilities(u, v, V, w)
+    FF._build_matrices(pre)
+    p_init = FF._starting_spectrum()
+    alphas = np.repeat(np.linspace(1.01, 1.5, 8), 8)
+    wss = np.tile(np.logspace(-4, -1, 8), 8)
+    uniq = {ws: CriticalFilter(dht, 1.05, 1e-15, ws)._Tinv for ws in np.unique(wss)}
+    Tinv = np.stack([uniq[ws] for ws in wss])
+    ctx = _lib.get_context()
+    for _ in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        out = ctx.frank_normal_loop(pre['M'], pre['j'], np.tile(p_init, (64, 1)), alphas, np.full(64, 1e-15), Tinv, 1e-3, 2000, want_chol=False)
+        t1 = time.perf_counter()
+    print(json.dumps({'config': '4', 'grid_points': 64, 'N': N, 'sweep_s': t1 - t0, 'iterations_min_max_sum': [int(out['niter'].min()), int(out['niter'].max()), int(out['niter'].sum())],
+                      'us_per_point_iteration': (t1 - t0) / out['niter'].sum() * 1e6, 'converged': int(out['converged'].sum())}), flush=True)
+
+if '5' in which:
+    n, N = int(os.environ.get('CFG5_NVIS', 100_000_000)), 2000
+    dht = DiscreteHankelTransform(1.6 / rad_to_arcsec, N)
+    u, v, V, w = bench.synthetic_visibilities_device(n, dht, 5)
+    vm = VisibilityMapping(dht, geom, vis_model='debris', scale_height=lambda r: 0.05 * r, verbose=False)
+    freqs = torch.randint(0, 4, (n,), device='cuda').to(torch.float64)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    m = vm.map_visibilities(u, v, V, w, frequencies=freqs)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    r = {'config': '5', 'n_vis': n, 'N': N, 'channels': 4, 'vis_model': 'debris', 'map_s': t1 - t0, 'gvis_mode_per_s': n * N / (t1 - t0) / 1e9}
+    print(json.dumps(r), flush=True)
+    q = torch.hypot(u, v).cpu().numpy()[:20_000_000]
+    Vh = V[:20_000_000].cpu().numpy(); wh = w[:20_000_000].cpu().numpy()
+    t0 = time.perf_counter(); b = UVDataBinner(q, Vh, wh, 1e3); t1 = time.perf_counter()
+    print(json.dumps({'config': '5 binning', 'n_vis': len(q), 'bin_width': 1e3, 'nbins': len(b), 'bin_s_host_buffers': t1 - t0}), flush=True)
