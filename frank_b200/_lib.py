@@ -42,6 +42,7 @@ _SIGNATURES = {
     'fb_timer_stop': ([_c_p, _c_p], _c_i),
     'fb_debug_prepped': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
+    'fb_debug_j0_far': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
     'fb_predict_visibilities': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
     'fb_uv_max': ([_c_p, _c_l, _c_p, _c_p], _c_i),
@@ -275,10 +276,11 @@ class Context(object):
                                        int(nbins), _ptr(idx), _ptr(counts), _ptr(sums), _ptr(err)), 'fb_uv_bin')
         return idx, counts, sums, err
 
-    def debug_j0(self, x):
+    def debug_j0(self, x, far=False):
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = np.empty_like(x)
-        self.check(self._lib.fb_debug_j0(self._h, x.size, _ptr(x), _ptr(out)), 'fb_debug_j0')
+        fn = self._lib.fb_debug_j0_far if far else self._lib.fb_debug_j0
+        self.check(fn(self._h, x.size, _ptr(x), _ptr(out)), 'fb_debug_j0')
         return out
 
 

@@ -36,7 +36,7 @@ int fb_ctx_destroy(fb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (void *p : {(void *)ctx->d_jk, (void *)ctx->d_ck, (void *)ctx->d_Y, (void *)ctx->d_tab, (void *)ctx->d_types,
                     (void *)ctx->d_tile_panel, (void *)ctx->d_panel_t0, (void *)ctx->d_panel_nt, (void *)ctx->d_pair_code,
-                    (void *)ctx->d_a, (void *)ctx->d_sw, (void *)ctx->d_swV, (void *)ctx->d_kz, (void *)ctx->d_red,
+                    (void *)ctx->d_a, (void *)ctx->d_sw, (void *)ctx->d_swV, (void *)ctx->d_kz, (void *)ctx->d_amid, (void *)ctx->d_red,
                     (void *)ctx->d_partial, (void *)ctx->d_H2, (void *)ctx->d_in, (void *)ctx->d_out,
                     (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist, (void *)ctx->d_work,
                     (void *)ctx->sv_D, (void *)ctx->sv_p, (void *)ctx->sv_mu, (void *)ctx->sv_tr2, (void *)ctx->sv_alpha,
@@ -82,55 +82,14 @@ int fb_dht_setup(fb_ctx *ctx, int N, double Qmax, const double *host_j_nk, const
         FB_CUDA(cudaMemcpy(ctx->d_Y, host_Ycoef, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice));
     }
 
-    // panel decomposition of the NT x NT tile grid
-    const int NT = ctx->NT;
-    const int P = (NT + FB_PT - 1) / FB_PT;
-    ctx->P = P;
-    std::vector<int> panel_t0(P), panel_nt(P), tile_panel(NT), pair_code((size_t)P * P, -1);
+    // block decomposition of the NT x NT tile grid (fb_gram.cu)
     {
-        const int base = NT / P, rem = NT % P;
-        int t = 0;
-        for (int p = 0; p < P; p++) {
-            panel_t0[p] = t;
-            panel_nt[p] = base + (p < rem ? 1 : 0);
-            for (int i = 0; i < panel_nt[p]; i++) tile_panel[t + i] = p;
-            t += panel_nt[p];
-        }
+        int rc = fb_build_gram_plan(ctx);
+        if (rc) return rc;
     }
-    // pair_code[(pa * P + pb) * 2 + half] = OFF type of that half of the rows of panel pa against panel pb (pa < pb);
-    // pair_code[(p * P + p) * 2] = DIAG type of panel p
-    pair_code.assign((size_t)P * P * 2, -1);
-    ctx->h_types.clear();
-    for (int pa = 0; pa < P; pa++)
-        for (int pb = pa + 1; pb < P; pb++) {
-            const int h0 = (panel_nt[pa] + 1) / 2;
-            pair_code[((size_t)pa * P + pb) * 2 + 0] = (int)ctx->h_types.size();
-            ctx->h_types.push_back({FB_KIND_OFF, panel_t0[pa], h0, panel_t0[pb], panel_nt[pb]});
-            if (panel_nt[pa] - h0 > 0) {
-                pair_code[((size_t)pa * P + pb) * 2 + 1] = (int)ctx->h_types.size();
-                ctx->h_types.push_back({FB_KIND_OFF, panel_t0[pa] + h0, panel_nt[pa] - h0, panel_t0[pb], panel_nt[pb]});
-            }
-        }
-    for (int p = 0; p < P; p++) {
-        pair_code[((size_t)p * P + p) * 2] = (int)ctx->h_types.size();
-        ctx->h_types.push_back({FB_KIND_DIAG, panel_t0[p], panel_nt[p], 0, 0});
-    }
-    ctx->ntypes = (int)ctx->h_types.size();
-    for (void **p : {(void **)&ctx->d_types, (void **)&ctx->d_tile_panel, (void **)&ctx->d_panel_t0,
-                     (void **)&ctx->d_panel_nt, (void **)&ctx->d_pair_code}) {
-        if (*p) FB_CUDA(cudaFree(*p));
-        *p = nullptr;
-    }
-    FB_CUDA(cudaMalloc(&ctx->d_types, sizeof(FbGramType) * ctx->ntypes));
-    FB_CUDA(cudaMalloc(&ctx->d_tile_panel, sizeof(int) * NT));
-    FB_CUDA(cudaMalloc(&ctx->d_panel_t0, sizeof(int) * P));
-    FB_CUDA(cudaMalloc(&ctx->d_panel_nt, sizeof(int) * P));
-    FB_CUDA(cudaMalloc(&ctx->d_pair_code, sizeof(int) * P * P * 2));
-    FB_CUDA(cudaMemcpy(ctx->d_types, ctx->h_types.data(), sizeof(FbGramType) * ctx->ntypes, cudaMemcpyHostToDevice));
-    FB_CUDA(cudaMemcpy(ctx->d_tile_panel, tile_panel.data(), sizeof(int) * NT, cudaMemcpyHostToDevice));
-    FB_CUDA(cudaMemcpy(ctx->d_panel_t0, panel_t0.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
-    FB_CUDA(cudaMemcpy(ctx->d_panel_nt, panel_nt.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
-    FB_CUDA(cudaMemcpy(ctx->d_pair_code, pair_code.data(), sizeof(int) * P * P * 2, cudaMemcpyHostToDevice));
+    // Baseline sort resolution: the arguments a * j_k of one stage must fit the validity window of one J0 table
+    // row (slack 1/32 either side), so a sort bin may span at most a fraction of it at the largest mode.
+    ctx->sort_bits = host_j_nk[N - 1] * 2.0 / 65536.0 > 0.03 ? 24 : 16;
 
     if (!(x_max > 0)) x_max = host_j_nk[N - 1];
     return fb_build_j0_table(ctx, x_max);
@@ -162,7 +121,7 @@ static int map_dev_impl(fb_ctx *ctx, int64_t n, const double *u, const double *v
         if (check_qbounds && q_last < host_qminmax[1]) FB_FAIL(FB_E_QRANGE, "last collocation point is at a shorter baseline than the longest deprojected baseline");
         // make sure the J0 table reaches the largest argument a_max * j_{N-1}
         const double xneed = host_qminmax[1] * ctx->invQmax * ctx->h_jk[ctx->N - 1];
-        if (xneed * 4.0 + 2.0 > (double)ctx->tab_rows) {
+        if (fb_j0_rows_for(xneed) > ctx->tab_rows) {
             rc = fb_build_j0_table(ctx, xneed * 1.05);
             if (rc) return rc;
         }

@@ -7,28 +7,26 @@
 #include <vector>
 
 #include "../../include/frankb200.h"
+#include "fb_j0_table.h"
 
 // ---- geometry of the fused J0 + Gram kernel -------------------------------------------------
-// One tile = FB_TV visibilities.  The design-matrix tile G[mode][vis] lives in shared memory with a
-// leading dimension FB_LDV = FB_TV + 4 doubles so that the m8n8k4 fragment pattern (8 modes x 4 vis)
-// touches all 32 banks exactly once per half-warp.
+// One tile = FB_TV visibilities.  The design-matrix tile G[mode][vis] lives in shared memory with a leading
+// dimension FB_LDV = FB_TV + 4 doubles so that the m8n8k4 fragment pattern (8 modes x 4 vis) touches all 32 banks
+// exactly once per half-warp.
 //
 // The symmetric (N+1)x(N+1) Gram matrix is cut into 8x8 tiles, the tiles into panels of <= FB_PT tiles, and
 // the upper triangle of the panel grid into work-item types:
-//   OFF  : <= FB_HT tile rows of panel A  x  all tile columns of panel B   (A < B; two halves per panel pair)
+//   OFF  : tile rows of panel A (all of them, or one of two halves)  x  all tile columns of panel B   (A < B)
 //   DIAG : the upper triangle of one panel, executed as the skewed strip (row r, offset d) -> column (r+d) mod n
-// so that every CTA holds <= 190 accumulator tiles (<= 15 per warp, 60 registers) and has to evaluate J0 only
-// for the <= 232 columns its block touches.
+// so that every warp holds <= FB_ACC accumulator tiles (a 4 x 4 warp grid covers the block) and J0 is evaluated
+// only for the <= FB_GCOLS columns the block touches.
 constexpr int FB_TV = 64;
 constexpr int FB_LDV = FB_TV + 4;
-constexpr int FB_PT = 19;              // max 8-column tiles per panel (152 modes)
-constexpr int FB_HT = 10;              // max tile rows of an OFF item: ceil(FB_PT / 2)
-constexpr int FB_DH = 10;              // skew offsets per triangle: floor(FB_PT / 2) + 1
-constexpr int FB_GCOLS = (FB_HT + FB_PT) * 8;    // columns of G held per tile
-constexpr int FB_PSZ = FB_PT * 10 * 64;          // doubles per work-item partial
-constexpr int FB_ACC = 15;             // accumulator tiles per warp
+constexpr int FB_PT = 20;              // max 8-column tiles per panel (160 modes)
+constexpr int FB_GCOLS = 256;          // columns of G held per tile
+constexpr int FB_ACC = 16;             // accumulator tiles per warp
+constexpr int FB_PSZ = 16 * FB_ACC * 64;         // doubles per work-item partial (16 warps x FB_ACC tiles)
 constexpr int FB_GRAM_THREADS = 512;
-constexpr int FB_J0_ROWLEN = 10;       // Taylor degree 9, rows centred on multiples of 1/4
 
 constexpr int FB_KIND_OFF = 0;
 constexpr int FB_KIND_DIAG = 1;
@@ -37,6 +35,7 @@ struct FbGramType {
     int kind;
     int a_t0, a_nt;   // OFF: tile rows [a_t0, a_t0 + a_nt)   DIAG: the panel
     int b_t0, b_nt;   // OFF: tile columns                     DIAG: unused (b_nt = 0)
+    int ld;           // tiles per row of the partial block: b_nt (OFF) | a_nt / 2 + 1 (DIAG)
 };
 
 struct fb_ctx {
@@ -55,12 +54,15 @@ struct fb_ctx {
     int P = 0, ntypes = 0;
     std::vector<FbGramType> h_types;
     FbGramType *d_types = nullptr;
-    int *d_tile_panel = nullptr, *d_panel_t0 = nullptr, *d_panel_nt = nullptr, *d_pair_code = nullptr;
-    int *d_work = nullptr;         // per launch: [3 * max_items] item -> (type, chunk, partial slot); then per type (C, first slot)
+    int *d_tile_panel = nullptr, *d_panel_t0 = nullptr, *d_panel_nt = nullptr;
+    int *d_pair_code = nullptr;    // [P * P * 3]: (first OFF type, second OFF type | -1, rows in the first) ; DIAG type on the diagonal
+    int *d_work = nullptr;         // per launch: per-CTA item ranges, items (type, chunk, partial slot), per type (chunks, first slot)
     int work_cap = 0;
     // workspaces
     int64_t cap = 0;
     double *d_a = nullptr, *d_sw = nullptr, *d_swV = nullptr, *d_kz = nullptr;   // sorted, padded, SoA
+    double *d_amid = nullptr;      // per tile of FB_TV sorted visibilities: (min a, max a)
+    int sort_bits = 16;            // key bits of the baseline sort (16 or 24)
     double *d_rec = nullptr;       // unsorted records (a, sqrt w, sqrt w * Re V, kz), 32 B each
     uint64_t *d_items = nullptr;   // 2 x cap sort buffers of (key << 32 | index)
     uint32_t *d_perm = nullptr;    // sorted position -> original index
@@ -118,5 +120,6 @@ int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, con
 int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, double *dev_M, double *dev_j);
 int fb_build_j0_table(fb_ctx *ctx, double x_max);
 int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max);
+int fb_build_gram_plan(fb_ctx *ctx);
 uint64_t *fb_radix_sort_items(fb_ctx *ctx, int64_t n, uint64_t *buf0, uint64_t *buf1, int nbits, int *status);
 int fb_items_from_keys(fb_ctx *ctx, int64_t n, const int32_t *dev_keys, uint64_t *items);

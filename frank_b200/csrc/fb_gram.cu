@@ -7,12 +7,17 @@
 //   * the symmetric (N+1)x(N+1) matrix  S = G^T G,
 //         G[i, k] = sqrt(w_i) J0(a_i j_k)  (k < N),   G[i, N] = sqrt(w_i) Re V_i,
 //     gives M = diag(c) S[:N,:N] diag(c), j = diag(c) S[:N, N], with c_k = norm * scale_factor_k * scale;
-//   * a CTA owns one block of S (work-item types OFF / DIAG, fb_common.cuh) with its accumulators in registers
-//     (<= 15 m8n8 tiles = 60 registers per thread, 16 warps);
-//   * per tile of 64 visibilities: (1) stage, per column, the row of the J0 Taylor table the tile needs (the
-//     visibilities are sorted by baseline so a whole warp shares it); (2) all warps evaluate J0 for the block's
-//     columns into shared memory G[mode][vis] (two visibilities per lane, coefficients broadcast from shared
-//     memory; |err| <= 0.5 ulp + 1e-17); (3) all warps run mma.sync.m8n8k4.f64 (DMMA) over the tile;
+//   * a CTA owns one block of S (work-item types OFF / DIAG, fb_common.cuh) for a chunk of the visibilities, with
+//     its accumulators in registers (<= 16 m8n8 tiles = 64 registers per thread, 16 warps);
+//   * per tile of 64 visibilities, two phases separated by barriers (the FP64 pipe serves DMMA and DFMA alike and
+//     starves a warp that issues DFMAs while others stream DMMAs -- profiles/r01_gram_ncu_summary.txt -- so the
+//     phases are not overlapped):
+//       (1) all warps evaluate J0 for the block's columns into shared memory G[mode][vis]: a lane owns one column
+//           (its polynomial row in registers), a warp a range of visibilities, four Horner chains per lane.  The
+//           visibilities are sorted by baseline, so ONE row of the J0 table per (column, tile) serves all of them
+//           (rows overlap, fb_j0_table.h); rows are staged by cp.async one tile ahead; visibilities outside a row's
+//           validity window are redone through a per-visibility gather (rare);
+//       (2) all warps run mma.sync.m8n8k4.f64 (DMMA) over the tile;
 //   * diagonal blocks are executed as skewed strips (row r, offset d -> column (r+d) mod n) so that only the
 //     upper triangle is computed while every warp still owns a dense register block;
 //   * work items (block, visibility chunk) write partial blocks; a second kernel sums the chunks in a fixed
@@ -22,22 +27,26 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <queue>
 
 namespace {
 
 struct GramArgs {
     const double *a, *sw, *swV, *kz;
+    const double2 *arange;    // per tile: (min a, max a)
     long long n_tiles;
     const double *jk;
     const double2 *tab;
     int tab_rows;
-    int N, n_items;
+    int N;
     const FbGramType *types;
-    const int *work;      // [3 * n_items] (type, chunk, partial slot), then [2 * ntypes] (C_t, first slot)
-    int work_types_off;   // offset of the per-type table inside work
+    const int *cta_off;   // [grid + 1] item range of each CTA
+    const int *items;     // [3 * n_items] (type, chunk, partial slot)
+    const int *type_tab;  // [2 * ntypes] (chunks, first slot)
     const double *H2;
     double *partial;
-    int debug_mode;       // 0 normal | 1 skip the DMMA phase | 2 skip J0 evaluation after the first tile (profiling aid)
+    long long *prof;      // optional [grid][2]: clocks thread 0 spent in the J0 phases / the DMMA phases
+    int debug_mode;       // 0 normal | 1 skip the DMMAs | 2 skip J0 evaluation after the first stage (profiling aid)
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
@@ -47,18 +56,17 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// J0(x), x >= 0: row m = round(4x) holds the Taylor coefficients about m/4, |t| <= 1/8.  Generic (gather) path.
+constexpr double J0_MAGIC = 6755399441055744.0;     // 1.5 * 2^52: adding it rounds to the nearest integer
+
+// J0(x), x >= 0, from the row nearest to x (|t| <= 1/32).  Generic (gather) path.
 __device__ __forceinline__ double j0_tab(double x, const double2 *__restrict__ tab, int last_row)
 {
-    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to the nearest integer
-    double s = fma(x, 4.0, MAGIC);
+    double s = fma(x, FB_J0_INVH, J0_MAGIC);
     int m = min(__double2loint(s), last_row);
-    double t = fma(s - MAGIC, -0.25, x);       // exact
+    double t = fma((double)m, -FB_J0_H, x);       // exact
     const double2 *row = tab + (size_t)m * (FB_J0_ROWLEN / 2);
-    double2 c01 = __ldg(row), c23 = __ldg(row + 1), c45 = __ldg(row + 2), c67 = __ldg(row + 3), c89 = __ldg(row + 4);
-    double y = fma(c89.y, t, c89.x);
-    y = fma(y, t, c67.y);
-    y = fma(y, t, c67.x);
+    double2 c01 = __ldg(row), c23 = __ldg(row + 1), c45 = __ldg(row + 2), c67 = __ldg(row + 3);
+    double y = fma(c67.y, t, c67.x);
     y = fma(y, t, c45.y);
     y = fma(y, t, c45.x);
     y = fma(y, t, c23.y);
@@ -81,300 +89,350 @@ __device__ __forceinline__ double2 lds_v2f64(uint32_t addr)
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ int lds_s32(uint32_t addr)
-{
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v)
 {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
-
-constexpr int GT = FB_TV;              // visibilities per tile (64)
+__device__ __forceinline__ void sts_v2f64(uint32_t addr, double x, double y)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+constexpr int GS = FB_TV;              // visibilities per tile (64)
 constexpr int GLD = FB_LDV;            // 68 = 4 mod 16: conflict-free m8n8k4 fragments
-constexpr int GKS = GT / 4;            // k-steps per tile
-constexpr int GCOLS = FB_GCOLS;        // columns held per tile (rows' columns | columns' columns)
+constexpr int GKS = GS / 4;            // k-steps per tile
+constexpr int GCOLS = FB_GCOLS;        // columns held per stage (rows' columns | columns' columns)
+constexpr int NW = FB_GRAM_THREADS / 32;
+constexpr int ROWB = FB_J0_ROWLEN * 8; // bytes per table row (64)
 
-// shared-memory carve-up (in doubles)
-constexpr int SM_G = 0;                                   // [GCOLS][GLD]        design-matrix tile
-constexpr int SM_JK = SM_G + GCOLS * GLD;                 // [GCOLS]             j_k (>= 0), -1 data column, -2 padding
-constexpr int SM_H2 = SM_JK + GCOLS;                      // [GCOLS]             debris H2_k
-constexpr int SM_ROW = SM_H2 + GCOLS;                     // [2][GCOLS][10]      staged J0 table rows (double buffered)
-constexpr int SM_ROWM = SM_ROW + 2 * GCOLS * FB_J0_ROWLEN;   // [2][GCOLS] int   staged row index
-constexpr int SM_DOUBLES = SM_ROWM + GCOLS;
-constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * SM_DOUBLES;
+// shared-memory carve-up (bytes)
+constexpr int SMB_G = 0;                                   // [GCOLS][GLD] doubles      design-matrix tile
+constexpr int SMB_ROW = SMB_G + GCOLS * GLD * 8;           // [2][4][GCOLS] double2     staged J0 table rows (coefficient pair major)
+constexpr int SMB_CEN = SMB_ROW + 2 * GCOLS * ROWB;        // [2][GCOLS] double2        (centre of the staged row, row serves the whole tile ? 1 : 0)
+constexpr int SMB_JK = SMB_CEN + 2 * GCOLS * 16;           // [GCOLS] doubles           j_k (>= 0), -1 data column, -2 padding
+constexpr int SMB_H2 = SMB_JK + GCOLS * 8;                 // [GCOLS] doubles           debris H2_k
+constexpr int SMB_VIS = SMB_H2 + GCOLS * 8;                // [2][GS][4] doubles        (a, sqrt w, kz, sqrt w Re V) per visibility of a tile
+constexpr int SMB_AR = SMB_VIS + 2 * GS * 32;               // [2] double2               (min a, max a) of the tiles being staged
+constexpr int GRAM_SMEM_BYTES = SMB_AR + 32;
 
 __host__ __device__ __forceinline__ int split4_size(int n, int i) { return n / 4 + (i < n % 4 ? 1 : 0); }
 __host__ __device__ __forceinline__ int split4_start(int n, int i) { return i * (n / 4) + (i < n % 4 ? i : n % 4); }
 
-// rectangular register block: acc[r * NC + c] += G_A[r0+r]^T G_B[c0+c] over one tile
-template <int NR, int NC>
-__device__ __forceinline__ void mma_off(double (&acc)[FB_ACC][2], const double *__restrict__ ap, const double *__restrict__ bp)
+// ---------------------------------------------------------------------------------------------
+// J0 evaluation
+// ---------------------------------------------------------------------------------------------
+// exp(x) for x <= 0, branch free: x = k ln2 + r, |r| <= ln2 / 2, degree-13 Taylor polynomial, 2^k through the exponent
+// field; results below the normal range flush to zero (the reference multiplies by np.exp, which denormalises
+// there: differences < 2.3e-308 in a factor of the design matrix).  Error <= 1 ulp.
+__device__ __forceinline__ double exp_neg(double x)
 {
-    static_assert(NR * NC <= FB_ACC, "register block too large");
-#pragma unroll 2
-    for (int ks = 0; ks < GKS; ks++) {
-        double af[NR];
-#pragma unroll
-        for (int r = 0; r < NR; r++) af[r] = ap[r * 8 * GLD + ks * 4];
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            const double b = bp[c * 8 * GLD + ks * 4];
-#pragma unroll
-            for (int r = 0; r < NR; r++) dmma(acc[r * NC + c], af[r], b);
+    const double t = fma(x, 1.4426950408889634, J0_MAGIC);
+    const int k = __double2loint(t);
+    const double kf = t - J0_MAGIC;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double q = 1.6059043836821613e-10;                      // 1/13!
+    q = fma(q, r, 2.08767569878681e-09);
+    q = fma(q, r, 2.505210838544172e-08);
+    q = fma(q, r, 2.755731922398589e-07);
+    q = fma(q, r, 2.7557319223985893e-06);
+    q = fma(q, r, 2.48015873015873e-05);
+    q = fma(q, r, 1.984126984126984e-04);
+    q = fma(q, r, 1.388888888888889e-03);
+    q = fma(q, r, 8.333333333333333e-03);
+    q = fma(q, r, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    const int hi = __double2hiint(q) + (k << 20);
+    const double y = __hiloint2double(hi, __double2loint(q));
+    return k > -1021 ? y : 0.0;
+}
+
+// J0 phase of one warp for one tile: columns sc = warp, warp + 16, ... of the block; a lane holds two visibilities
+// (lane, lane + 32), so the column's polynomial row is fetched once (broadcast loads from the staged rows) for two
+// Horner chains.  The thread that staged the row has verified that it serves the tile's whole range of arguments
+// (validity flag); a column that needs more than one row (sparse data, or very large j_k) takes the per-visibility
+// gather path (warp-uniform branch, rare).  The data column and the zero padding are not written here.
+template <bool DEBRIS>
+__device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sbase, const int buf, const int ncol,
+                                           const int warp, const int lane, const int last_row)
+{
+    const uint32_t s_vis = sbase + SMB_VIS + buf * (GS * 32);
+    const double2 aw0 = lds_v2f64(s_vis + lane * 32), aw1 = lds_v2f64(s_vis + (lane + 32) * 32);
+    double k0 = 0.0, k1 = 0.0;
+    if (DEBRIS) {
+        k0 = lds_f64(s_vis + lane * 32 + 16); k1 = lds_f64(s_vis + (lane + 32) * 32 + 16);
+        k0 = -k0 * k0; k1 = -k1 * k1;                     // -kz^2
+    }
+    uint32_t a_row = sbase + SMB_ROW + buf * (GCOLS * ROWB) + warp * 16;
+    uint32_t a_cen = sbase + SMB_CEN + (buf * GCOLS + warp) * 16;
+    uint32_t a_jk = sbase + SMB_JK + warp * 8;
+    uint32_t a_g = sbase + SMB_G + (warp * GLD + lane) * 8;
+#pragma unroll 1
+    for (int sc = warp; sc < ncol; sc += NW) {
+        const double jkc = lds_f64(a_jk);                            // j_k >= 0 | -1 data column | -2 padding
+        const double2 cv = lds_v2f64(a_cen);                         // (centre, row serves the whole tile)
+        const double2 c67 = lds_v2f64(a_row + 3 * GCOLS * 16), c45 = lds_v2f64(a_row + 2 * GCOLS * 16),
+                      c23 = lds_v2f64(a_row + GCOLS * 16), c01 = lds_v2f64(a_row);
+        const double jk = fmax(jkc, 0.0);
+        const double x0 = __dmul_rn(aw0.x, jk), x1 = __dmul_rn(aw1.x, jk);      // a * j_k as the reference rounds it
+        const double u0 = __dsub_rn(x0, cv.x), u1 = __dsub_rn(x1, cv.x);        // exact
+        double g0 = fma(c67.y, u0, c67.x), g1 = fma(c67.y, u1, c67.x);
+        g0 = fma(g0, u0, c45.y); g1 = fma(g1, u1, c45.y);
+        g0 = fma(g0, u0, c45.x); g1 = fma(g1, u1, c45.x);
+        g0 = fma(g0, u0, c23.y); g1 = fma(g1, u1, c23.y);
+        g0 = fma(g0, u0, c23.x); g1 = fma(g1, u1, c23.x);
+        g0 = fma(g0, u0, c01.y); g1 = fma(g1, u1, c01.y);
+        g0 = fma(g0, u0, c01.x); g1 = fma(g1, u1, c01.x);
+        if (cv.y == 0.0) {                                           // warp-uniform, rare
+            g0 = j0_tab(x0, p.tab, last_row);
+            g1 = j0_tab(x1, p.tab, last_row);
         }
+        if (DEBRIS) {
+            const double h2 = lds_f64(sbase + SMB_H2 + sc * 8);
+            g0 *= exp_neg(k0 * h2);
+            g1 *= exp_neg(k1 * h2);
+        }
+        if (jkc >= 0.0) {                                            // the data column and the padding are written elsewhere
+            sts_f64(a_g, g0 * aw0.y);
+            sts_f64(a_g + 32 * 8, g1 * aw1.y);
+        }
+        a_row += NW * 16; a_cen += NW * 16; a_jk += NW * 8; a_g += NW * GLD * 8;
     }
 }
 
-// skewed strip of a triangle: acc[r * ND + d] += G[r0+r]^T G[(r0+r + d0+d) mod n] over one tile
-template <int NR, int ND>
-__device__ __forceinline__ void mma_diag(double (&acc)[FB_ACC][2], const double *__restrict__ ap, const double *__restrict__ tp,
-                                         int cbase, int nmod)
+// ---------------------------------------------------------------------------------------------
+// One work item for one warp: per stage, the DMMAs of stage s, then the warp's J0 segments of stage s + 1
+// ---------------------------------------------------------------------------------------------
+struct ItemCtx {
+    uint32_t sbase;
+    const double *G;       // generic pointer to the G stages
+    int r0, c0, ncolA, nmod, ncol;
+    long long q0;
+    int nst;
+    int ld;
+    double *out;
+    double my_jk;          // column code of column tid (tid < ncol): row-staging duty of this thread
+    int dcol;              // local index of the data column in this block, -1 if absent
+};
+
+// DMMAs of one tile for one warp.  G: generic pointer to the tile; fr[p]: this lane's fragment offset inside a
+// tile row of parity p (the swizzle depends on the parity of the local tile index); ta / tb: first local tile index of
+// the A rows / B columns of this warp's register block.
+template <int KIND, int NR, int NC>
+__device__ __forceinline__ void stage_dmma(double (&acc)[NR * NC > 0 ? NR * NC : 1][2], const double *__restrict__ G,
+                                           const int fr0, const int fr1, const int ta, const int tb, const int cbase,
+                                           const int nmod)
 {
-    static_assert(NR * ND <= FB_ACC, "register block too large");
+    if (NR * NC == 0) return;
+    const double *A0 = G + ta * 8 * GLD + ((ta & 1) ? fr1 : fr0);          // tile rows ta, ta + 2, ...
+    const double *A1 = G + ta * 8 * GLD + ((ta & 1) ? fr0 : fr1);          // tile rows ta + 1, ta + 3, ...
+    const double *B0 = G + tb * 8 * GLD + ((tb & 1) ? fr1 : fr0);
+    const double *B1 = G + tb * 8 * GLD + ((tb & 1) ? fr0 : fr1);
 #pragma unroll 2
     for (int ks = 0; ks < GKS; ks++) {
-        double af[NR];
+        double af[NR > 0 ? NR : 1];
 #pragma unroll
-        for (int r = 0; r < NR; r++) af[r] = ap[r * 8 * GLD + ks * 4];
+        for (int r = 0; r < NR; r++) af[r] = ((r & 1) ? A1 : A0)[r * 8 * GLD + ks * 4];
+        if (KIND == FB_KIND_OFF) {
 #pragma unroll
-        for (int s = 0; s < NR + ND - 1; s++) {
-            int ct = cbase + s;
-            ct = ct >= nmod ? ct - nmod : ct;
-            const double b = tp[ct * 8 * GLD + ks * 4];
+            for (int c = 0; c < NC; c++) {
+                const double bf = ((c & 1) ? B1 : B0)[c * 8 * GLD + ks * 4];
 #pragma unroll
-            for (int r = 0; r < NR; r++) {
-                const int d = s - r;
-                if (d >= 0 && d < ND) dmma(acc[r * ND + d], af[r], b);
+                for (int r = 0; r < NR; r++) dmma(acc[r * NC + c], af[r], bf);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < NR + NC - 1; s++) {
+                int ct = cbase + s;
+                ct = ct >= nmod ? ct - nmod : ct;
+                const double bf = G[ct * 8 * GLD + ((ct & 1) ? fr1 : fr0) + ks * 4];
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    const int dd = s - r;
+                    if (dd >= 0 && dd < NC) dmma(acc[r * NC + dd], af[r], bf);
+                }
             }
         }
     }
 }
 
-template <int NR, int NC>
-__device__ __forceinline__ void store_block(const double (&acc)[FB_ACC][2], double *__restrict__ out, int r0, int c0, int ld, int lane)
+template <bool DEBRIS, int KIND, int NR, int NC>
+__device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, const int tid, const int lane)
 {
+    double acc[NR * NC > 0 ? NR * NC : 1][2];
+#pragma unroll
+    for (int i = 0; i < (NR * NC > 0 ? NR * NC : 1); i++) acc[i][0] = acc[i][1] = 0.0;
+    const int last_row = p.tab_rows - 1;
+    const int fr0 = (lane >> 2) * GLD + (lane & 3), fr1 = fr0;     // fragment offset of this lane inside a tile row
+    const int ta = it.r0, tb = KIND == FB_KIND_OFF ? it.ncolA / 8 + it.c0 : 0;
+    const int cbase = KIND == FB_KIND_OFF ? 0 : (it.r0 + it.c0) % it.nmod;
+    const uint32_t sbase = it.sbase;
+
+    // stage_tile(ar, buf, q, q2): everything the J0 phase of tile q needs, fetched with cp.async (no registers held):
+    //   * per column, the table row that serves arguments [ar.x j_k, ar.y j_k] (lane <-> column for the arithmetic, then
+    //     four lanes copy the four 16-byte pieces of a row, so that a warp-wide copy touches 8 rows, not 32), its
+    //     centre and whether that one row covers the whole tile;
+    //   * the per-visibility scalars (a, sqrt w, kz, sqrt w Re V) of tile q;
+    //   * the range (min a, max a) of tile q2 (used by the next call).
+    auto stage_tile = [&](const double2 ar, const int buf, const long long q, const long long q2) {
+        const int w = tid >> 5;
+        if (w * 32 < it.ncol) {                              // warp-uniform
+            int m = 0;
+            if (it.my_jk >= 0.0) {
+                const double xlo = __dmul_rn(ar.x, it.my_jk), xhi = __dmul_rn(ar.y, it.my_jk);
+                m = min(__double2loint(fma(xlo + xhi, 0.5 * FB_J0_INVH, J0_MAGIC)), last_row);
+                const double cen = (double)m * FB_J0_H;
+                const double valid = (fabs(xlo - cen) < FB_J0_ACCEPT && fabs(xhi - cen) < FB_J0_ACCEPT) ? 1.0 : 0.0;
+                sts_v2f64(sbase + SMB_CEN + (buf * GCOLS + tid) * 16, cen, valid);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int src_lane = 8 * r + (lane >> 2);
+                const int mm = __shfl_sync(0xffffffffu, m, src_lane);
+                const int col = w * 32 + src_lane;
+                if (col < it.ncol) {
+                    const double2 *src = p.tab + (size_t)mm * (FB_J0_ROWLEN / 2) + (lane & 3);
+                    const uint32_t dst = sbase + SMB_ROW + buf * (GCOLS * ROWB) + (lane & 3) * (GCOLS * 16) + col * 16;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                }
+            }
+        }
+        if (tid < GS) {
+            const size_t v = (size_t)q * GS + tid;
+            const uint32_t d = sbase + SMB_VIS + buf * (GS * 32) + tid * 32;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(p.a + v) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8), "l"(p.sw + v) : "memory");
+            if (DEBRIS) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 16), "l"(p.kz + v) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 24), "l"(p.swV + v) : "memory");
+        }
+        if (tid == GS && q2 >= 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sbase + SMB_AR + (buf ^ 1) * 16), "l"(p.arange + q2) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // J0 phase of this warp
+    auto produce = [&](const int buf) {
+        if (it.dcol >= 0 && tid < GS)        // data column: G[N][v] = sqrt(w_v) Re V_v
+            sts_f64(sbase + SMB_G + (it.dcol * GLD + tid) * 8, lds_f64(sbase + SMB_VIS + buf * (GS * 32) + tid * 32 + 24));
+        j0_columns<DEBRIS>(p, sbase, buf, it.ncol, tid >> 5, lane, last_row);
+    };
+
+    const long long q0 = it.q0;
+    const int nst = it.nst;
+    // ---- prologue: rows and scalars of the first tile, range of the second --------------------------------------
+    stage_tile(p.arange[q0], 0, q0, nst > 1 ? q0 + 1 : -1);
+    // ---- main loop: J0 phase, DMMA phase ------------------------------------------------------------------------
+    long long t_j0 = 0, t_mma = 0, t_last = clock64();
+    for (int s = 0; s < nst; s++) {
+        const int b = s & 1;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                     // tile s staged; DMMAs of tile s - 1 done
+        if (p.prof && tid == 0) { const long long t = clock64(); t_mma += t - t_last; t_last = t; }
+        if (p.debug_mode != 2 || s == 0) produce(b);
+        __syncthreads();
+        if (p.prof && tid == 0) { const long long t = clock64(); t_j0 += t - t_last; t_last = t; }
+        if (s + 1 < nst)                                     // next tile's staging flies during the DMMAs
+            stage_tile(lds_v2f64(sbase + SMB_AR + (b ^ 1) * 16), b ^ 1, q0 + s + 1, s + 2 < nst ? q0 + s + 2 : -1);
+        if (p.debug_mode != 1) stage_dmma<KIND, NR, NC>(acc, it.G, fr0, fr1, ta, tb, cbase, it.nmod);
+    }
+    if (p.prof && tid == 0) {
+        t_mma += clock64() - t_last;
+        atomicAdd((unsigned long long *)&p.prof[2 * blockIdx.x], (unsigned long long)t_j0);
+        atomicAdd((unsigned long long *)&p.prof[2 * blockIdx.x + 1], (unsigned long long)t_mma);
+
+    }
+    // ---- write the partial block ------------------------------------------------------------------------------------
 #pragma unroll
     for (int r = 0; r < NR; r++)
 #pragma unroll
         for (int c = 0; c < NC; c++)
-            *reinterpret_cast<double2 *>(out + ((size_t)((r0 + r) * ld + (c0 + c)) * 64 + lane * 2)) =
+            *reinterpret_cast<double2 *>(it.out + ((size_t)((it.r0 + r) * it.ld + (it.c0 + c)) * 64 + lane * 2)) =
                 make_double2(acc[r * NC + c][0], acc[r * NC + c][1]);
 }
 
-// compile-time dispatch over the register-block shape (NR * NC <= FB_ACC)
-#define FB_DISPATCH_SHAPE(nr, nc, CALL)                                               \
-    switch ((nr) * 8 + (nc)) {                                                        \
-        case 1 * 8 + 1: { CALL(1, 1); } break; case 1 * 8 + 2: { CALL(1, 2); } break; \
-        case 1 * 8 + 3: { CALL(1, 3); } break; case 1 * 8 + 4: { CALL(1, 4); } break; \
-        case 1 * 8 + 5: { CALL(1, 5); } break; case 2 * 8 + 1: { CALL(2, 1); } break; \
-        case 2 * 8 + 2: { CALL(2, 2); } break; case 2 * 8 + 3: { CALL(2, 3); } break; \
-        case 2 * 8 + 4: { CALL(2, 4); } break; case 2 * 8 + 5: { CALL(2, 5); } break; \
-        case 3 * 8 + 1: { CALL(3, 1); } break; case 3 * 8 + 2: { CALL(3, 2); } break; \
-        case 3 * 8 + 3: { CALL(3, 3); } break; case 3 * 8 + 4: { CALL(3, 4); } break; \
-        case 3 * 8 + 5: { CALL(3, 5); } break; case 4 * 8 + 1: { CALL(4, 1); } break; \
-        case 4 * 8 + 2: { CALL(4, 2); } break; case 4 * 8 + 3: { CALL(4, 3); } break; \
-        case 5 * 8 + 1: { CALL(5, 1); } break; case 5 * 8 + 2: { CALL(5, 2); } break; \
-        case 5 * 8 + 3: { CALL(5, 3); } break;                                        \
-        default: break;                                                               \
+// compile-time dispatch over the register-block shape (NR * NC <= FB_ACC, NR, NC <= 5)
+#define FB_SHAPE_CASE(K, NR, NC) \
+    case NR * 8 + NC: run_item<DEBRIS, K, NR, NC>(p, it, tid, lane); break;
+#define FB_DISPATCH_SHAPE(K)                                                                                   \
+    switch (nr * 8 + nc) {                                                                                     \
+        FB_SHAPE_CASE(K, 1, 1) FB_SHAPE_CASE(K, 1, 2) FB_SHAPE_CASE(K, 1, 3) FB_SHAPE_CASE(K, 1, 4) FB_SHAPE_CASE(K, 1, 5) \
+        FB_SHAPE_CASE(K, 2, 1) FB_SHAPE_CASE(K, 2, 2) FB_SHAPE_CASE(K, 2, 3) FB_SHAPE_CASE(K, 2, 4) FB_SHAPE_CASE(K, 2, 5) \
+        FB_SHAPE_CASE(K, 3, 1) FB_SHAPE_CASE(K, 3, 2) FB_SHAPE_CASE(K, 3, 3) FB_SHAPE_CASE(K, 3, 4) FB_SHAPE_CASE(K, 3, 5) \
+        FB_SHAPE_CASE(K, 4, 1) FB_SHAPE_CASE(K, 4, 2) FB_SHAPE_CASE(K, 4, 3) FB_SHAPE_CASE(K, 4, 4)                      \
+        FB_SHAPE_CASE(K, 5, 1) FB_SHAPE_CASE(K, 5, 2) FB_SHAPE_CASE(K, 5, 3)                                            \
+        FB_SHAPE_CASE(K, 0, 0)                                                                                 \
     }
 
-// Evaluate the staged polynomial for two visibilities of one column (shared coefficient loads, all five
-// coefficient pairs requested before the first use).
-__device__ __forceinline__ void horner2(const double2 *__restrict__ rb, double t0, double t1, double &g0, double &g1)
-{
-    const double2 c4 = rb[4], c3 = rb[3], c2 = rb[2], c1 = rb[1], c0 = rb[0];
-    g0 = fma(c4.y, t0, c4.x);         g1 = fma(c4.y, t1, c4.x);
-    g0 = fma(g0, t0, c3.y);           g1 = fma(g1, t1, c3.y);
-    g0 = fma(g0, t0, c3.x);           g1 = fma(g1, t1, c3.x);
-    g0 = fma(g0, t0, c2.y);           g1 = fma(g1, t1, c2.y);
-    g0 = fma(g0, t0, c2.x);           g1 = fma(g1, t1, c2.x);
-    g0 = fma(g0, t0, c1.y);           g1 = fma(g1, t1, c1.y);
-    g0 = fma(g0, t0, c1.x);           g1 = fma(g1, t1, c1.x);
-    g0 = fma(g0, t0, c0.y);           g1 = fma(g1, t1, c0.y);
-    g0 = fma(g0, t0, c0.x);           g1 = fma(g1, t1, c0.x);
-}
-
 template <bool DEBRIS>
-__global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(GramArgs p)
+__global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
 {
-    extern __shared__ double smem[];
-    double *G = smem + SM_G;
-    double *col_jk = smem + SM_JK;
-    double *col_h2 = smem + SM_H2;
-    double *rowbuf = smem + SM_ROW;
-    int *rowm = reinterpret_cast<int *>(smem + SM_ROWM);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int last_row = p.tab_rows - 1;
-    const double MAGIC = 6755399441055744.0;
-    const uint32_t s_G = (uint32_t)__cvta_generic_to_shared(G), s_jk = (uint32_t)__cvta_generic_to_shared(col_jk);
-    const uint32_t s_row = (uint32_t)__cvta_generic_to_shared(rowbuf), s_rowm = (uint32_t)__cvta_generic_to_shared(rowm);
-
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int type = p.work[3 * item], chunk = p.work[3 * item + 1], slot_out = p.work[3 * item + 2];
-        const int Ct = p.work[p.work_types_off + 2 * type];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k_end = p.cta_off[blockIdx.x + 1];
+    for (int k = p.cta_off[blockIdx.x]; k < k_end; ++k) {
+        const int type = p.items[3 * k], chunk = p.items[3 * k + 1], slot_out = p.items[3 * k + 2];
+        const int Ct = p.type_tab[2 * type];
         const FbGramType ty = p.types[type];
-        const int t0 = (int)((p.n_tiles * chunk) / Ct), t1 = (int)((p.n_tiles * (chunk + 1)) / Ct);
-        const int ncolA = ty.a_nt * 8, ncol = (ty.a_nt + ty.b_nt) * 8;
+        const long long q0 = (p.n_tiles * chunk) / Ct, q1 = (p.n_tiles * (chunk + 1)) / Ct;
+        if (q0 >= q1) continue;
+        ItemCtx it;
+        it.sbase = sbase;
+        it.G = reinterpret_cast<const double *>(smem_raw + SMB_G);
+        it.q0 = q0;
+        it.nst = (int)(q1 - q0);
+        it.ncolA = ty.a_nt * 8;
+        it.ncol = (ty.a_nt + ty.b_nt) * 8;
+        it.ld = ty.ld;
+        it.out = p.partial + (size_t)slot_out * FB_PSZ;
 
-        __syncthreads();
-        for (int lc = tid; lc < ncol; lc += FB_GRAM_THREADS) {
-            const int g = lc < ncolA ? ty.a_t0 * 8 + lc : ty.b_t0 * 8 + (lc - ncolA);
-            col_jk[lc] = g < p.N ? p.jk[g] : (g == p.N ? -1.0 : -2.0);
-            if (DEBRIS) col_h2[lc] = g < p.N ? p.H2[g] : 0.0;
+        // column tables of this block
+        __syncthreads();                      // every warp is done with the previous item
+        it.my_jk = -2.0;
+        if (tid < GCOLS) {
+            double v = -2.0, h = 0.0;
+            if (tid < it.ncol) {
+                const int g = tid < it.ncolA ? ty.a_t0 * 8 + tid : ty.b_t0 * 8 + (tid - it.ncolA);
+                if (g < p.N) { v = p.jk[g]; if (DEBRIS) h = p.H2[g]; }
+                else if (g == p.N) v = -1.0;
+            }
+            it.my_jk = v;
+            sts_f64(sbase + SMB_JK + tid * 8, v);
+            if (DEBRIS) sts_f64(sbase + SMB_H2 + tid * 8, h);
+            if (v == -2.0 && tid < it.ncol) {            // zero padding columns stay zero for the whole item
+                for (int x = 0; x < GS; x++) sts_f64(sbase + SMB_G + (tid * GLD + x) * 8, 0.0);
+            }
         }
-
-        double acc[FB_ACC][2];
-#pragma unroll
-        for (int i = 0; i < FB_ACC; i++) acc[i][0] = acc[i][1] = 0.0;
+        {
+            const int gA = p.N - ty.a_t0 * 8, gB = p.N - ty.b_t0 * 8;
+            it.dcol = (gA >= 0 && gA < it.ncolA) ? gA : ((gB >= 0 && gB < it.ncol - it.ncolA) ? it.ncolA + gB : -1);
+        }
 
         // this warp's register block (warp-uniform).  Latin-square assignment of (row group, column group) to
         // (slot, sub-partition) balances the DMMA count of the four SM sub-partitions.
         const int smsp = warp & 3, slot = warp >> 2;
-        const int kind = ty.kind;
-        int r0, c0, nr, nc, nmod;
-        if (kind == FB_KIND_OFF) {
-            nmod = 1;
-            r0 = split4_start(ty.a_nt, slot);
+        int nr, nc;
+        if (ty.kind == FB_KIND_OFF) {
+            it.nmod = 1;
+            it.r0 = split4_start(ty.a_nt, slot);
             nr = split4_size(ty.a_nt, slot);
-            c0 = split4_start(ty.b_nt, (slot + smsp) & 3);
+            it.c0 = split4_start(ty.b_nt, (slot + smsp) & 3);
             nc = split4_size(ty.b_nt, (slot + smsp) & 3);
         } else {
-            nmod = ty.a_nt;
-            const int D = nmod / 2 + 1;
-            r0 = split4_start(nmod, slot);
-            nr = split4_size(nmod, slot);
-            c0 = split4_start(D, (slot + smsp) & 3);       // first skew offset d
+            it.nmod = ty.a_nt;
+            const int D = it.nmod / 2 + 1;
+            it.r0 = split4_start(it.nmod, slot);
+            nr = split4_size(it.nmod, slot);
+            it.c0 = split4_start(D, (slot + smsp) & 3);       // first skew offset d
             nc = split4_size(D, (slot + smsp) & 3);
         }
         if (nr == 0 || nc == 0) { nr = 0; nc = 0; }
-        const int frag = (lane >> 2) * GLD + (lane & 3);
-        const double *ap = G + (r0 * 8) * GLD + frag;
-        const double *bp = kind == FB_KIND_OFF ? G + (ncolA + c0 * 8) * GLD + frag : G + frag;
-        const int cbase = (r0 + c0) % nmod;
-
-        // Software pipeline over tiles: while the DMMAs of tile t run, the table rows of tile t+1 stream into the
-        // other half of rowbuf (cp.async) and its per-visibility scalars into registers.
-        // stage_rows(tile, buf): thread tid < ncol copies the row its column needs at the tile's first visibility.
-        auto stage_rows = [&](double aref, int buf) {
-            if (tid < ncol) {
-                const double jk = col_jk[tid];
-                int m = 0;
-                if (jk >= 0.0) m = min(__double2loint(fma(__dmul_rn(aref, jk), 4.0, MAGIC)), last_row);
-                rowm[buf * GCOLS + tid] = m;
-                const double2 *row = p.tab + (size_t)m * (FB_J0_ROWLEN / 2);
-                const uint32_t dst = s_row + (buf * GCOLS + tid) * (FB_J0_ROWLEN * 8);
-#pragma unroll
-                for (int k = 0; k < FB_J0_ROWLEN / 2; k++)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * k), "l"(row + k) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        double na0 = 0.0, na1 = 0.0, nw0 = 0.0, nw1 = 0.0, nk0 = 0.0, nk1 = 0.0, aref_next = 0.0;
-        if (t0 < t1) {
-            const size_t v0 = (size_t)t0 * GT;
-            stage_rows(p.a[v0], 0);
-            na0 = p.a[v0 + lane]; na1 = p.a[v0 + lane + 32];
-            nw0 = p.sw[v0 + lane]; nw1 = p.sw[v0 + lane + 32];
-            if (DEBRIS) { nk0 = p.kz[v0 + lane]; nk1 = p.kz[v0 + lane + 32]; }
-            if (t0 + 1 < t1) aref_next = p.a[v0 + GT];
+        if (ty.kind == FB_KIND_OFF) {
+            FB_DISPATCH_SHAPE(FB_KIND_OFF)
+        } else {
+            FB_DISPATCH_SHAPE(FB_KIND_DIAG)
         }
-
-        for (int tile = t0; tile < t1; ++tile) {
-            const size_t v0 = (size_t)tile * GT;
-            const int buf = (tile - t0) & 1;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();          // rows of this tile staged; every warp is done with the previous tile's DMMAs
-            // ---- (2) J0 evaluation ------------------------------------------------------------------
-            if (p.debug_mode != 2 || tile == t0) {
-                const double a0 = na0, a1 = na1, w0 = nw0, w1 = nw1;
-                double k0 = 0.0, k1 = 0.0;
-                if (DEBRIS) { k0 = -nk0 * nk0; k1 = -nk1 * nk1; }
-                // One column per iteration, two visibilities per lane.  The column's j_k and staged row
-                // index are fetched one iteration ahead; the polynomial is evaluated from the staged row
-                // unconditionally and redone through the gather path only if some lane needs another row,
-                // so neither the loads nor the vote sit on the dependency chain.
-                uint32_t a_jk = s_jk + warp * 8, a_rm = s_rowm + (buf * GCOLS + warp) * 4;
-                uint32_t a_rb = s_row + (buf * GCOLS + warp) * (FB_J0_ROWLEN * 8);
-                uint32_t a_g = s_G + (warp * GLD + lane) * 8;
-                double jk_n = 0.0;
-                int mref_n = 0;
-                if (warp < ncol) { jk_n = lds_f64(a_jk); mref_n = lds_s32(a_rm); }
-#pragma unroll 1
-                for (int sc = warp; sc < ncol; sc += FB_GRAM_THREADS / 32) {
-                    const double jk = jk_n;
-                    const int mref = mref_n;
-                    if (sc + FB_GRAM_THREADS / 32 < ncol) {
-                        jk_n = lds_f64(a_jk + (FB_GRAM_THREADS / 32) * 8);
-                        mref_n = lds_s32(a_rm + (FB_GRAM_THREADS / 32) * 4);
-                    }
-                    const double2 c4 = lds_v2f64(a_rb + 64), c3 = lds_v2f64(a_rb + 48), c2 = lds_v2f64(a_rb + 32),
-                                  c1 = lds_v2f64(a_rb + 16), c0 = lds_v2f64(a_rb);
-                    const double x0 = __dmul_rn(a0, jk), x1 = __dmul_rn(a1, jk);
-                    const double s0 = fma(x0, 4.0, MAGIC), s1 = fma(x1, 4.0, MAGIC);
-                    const double u0 = fma(s0 - MAGIC, -0.25, x0), u1 = fma(s1 - MAGIC, -0.25, x1);
-                    double g0 = fma(c4.y, u0, c4.x), g1 = fma(c4.y, u1, c4.x);
-                    g0 = fma(g0, u0, c3.y);           g1 = fma(g1, u1, c3.y);
-                    g0 = fma(g0, u0, c3.x);           g1 = fma(g1, u1, c3.x);
-                    g0 = fma(g0, u0, c2.y);           g1 = fma(g1, u1, c2.y);
-                    g0 = fma(g0, u0, c2.x);           g1 = fma(g1, u1, c2.x);
-                    g0 = fma(g0, u0, c1.y);           g1 = fma(g1, u1, c1.y);
-                    g0 = fma(g0, u0, c1.x);           g1 = fma(g1, u1, c1.x);
-                    g0 = fma(g0, u0, c0.y);           g1 = fma(g1, u1, c0.y);
-                    g0 = fma(g0, u0, c0.x);           g1 = fma(g1, u1, c0.x);
-                    const bool same = (jk < 0.0) | ((__double2loint(s0) == mref) & (__double2loint(s1) == mref));
-                    if (!__all_sync(0xffffffffu, same)) {          // rare: some lane straddles a table row
-                        g0 = j0_tab(x0, p.tab, last_row);
-                        g1 = j0_tab(x1, p.tab, last_row);
-                    }
-                    if (DEBRIS) {
-                        const double h2 = col_h2[sc];
-                        g0 *= exp(k0 * h2);
-                        g1 *= exp(k1 * h2);
-                    }
-                    g0 *= w0;
-                    g1 *= w1;
-                    if (jk < 0.0) {                                 // data column / zero padding (warp-uniform)
-                        g0 = jk == -1.0 ? p.swV[v0 + lane] : 0.0;
-                        g1 = jk == -1.0 ? p.swV[v0 + lane + 32] : 0.0;
-                    }
-                    sts_f64(a_g, g0);
-                    sts_f64(a_g + 32 * 8, g1);
-                    a_jk += (FB_GRAM_THREADS / 32) * 8;
-                    a_rm += (FB_GRAM_THREADS / 32) * 4;
-                    a_rb += (FB_GRAM_THREADS / 32) * (FB_J0_ROWLEN * 8);
-                    a_g += (FB_GRAM_THREADS / 32) * GLD * 8;
-                }
-            }
-            // ---- prefetch for tile + 1 (in flight during the DMMA phase) -------------------------------
-            if (tile + 1 < t1 && p.debug_mode != 2) {
-                stage_rows(aref_next, buf ^ 1);
-                na0 = p.a[v0 + GT + lane]; na1 = p.a[v0 + GT + lane + 32];
-                nw0 = p.sw[v0 + GT + lane]; nw1 = p.sw[v0 + GT + lane + 32];
-                if (DEBRIS) { nk0 = p.kz[v0 + GT + lane]; nk1 = p.kz[v0 + GT + lane + 32]; }
-                if (tile + 2 < t1) aref_next = p.a[v0 + 2 * GT];
-            }
-            __syncthreads();
-            // ---- (3) DMMA over the tile -----------------------------------------------------------
-            if (p.debug_mode != 1 && nr > 0) {
-                if (kind == FB_KIND_OFF) {
-#define FB_CALL_OFF(NR, NC) mma_off<NR, NC>(acc, ap, bp)
-                    FB_DISPATCH_SHAPE(nr, nc, FB_CALL_OFF)
-                } else {
-#define FB_CALL_DIAG(NR, ND) mma_diag<NR, ND>(acc, ap, bp, cbase, nmod)
-                    FB_DISPATCH_SHAPE(nr, nc, FB_CALL_DIAG)
-                }
-            }
-        }
-
-        // ---------------- write the partial block ------------------------------------------------
-        double *out = p.partial + (size_t)slot_out * FB_PSZ;
-        const int ld = kind == FB_KIND_OFF ? FB_PT : FB_DH;
-#define FB_CALL_STORE(NR, NC) store_block<NR, NC>(acc, out, r0, c0, ld, lane)
-        FB_DISPATCH_SHAPE(nr, nc, FB_CALL_STORE)
     }
 }
 
@@ -382,8 +440,8 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(GramArgs p)
 __global__ void __launch_bounds__(64)
 k_gram_finalize(int N, int NT, int P, long long n_tiles, const int *__restrict__ tile_panel,
                 const int *__restrict__ panel_t0, const int *__restrict__ panel_nt, const int *__restrict__ pair_code,
-                const int *__restrict__ type_tab, const double *__restrict__ partial, const double *__restrict__ ck,
-                double scale, double *__restrict__ M, double *__restrict__ jvec)
+                const FbGramType *__restrict__ types, const int *__restrict__ type_tab, const double *__restrict__ partial,
+                const double *__restrict__ ck, double scale, double *__restrict__ M, double *__restrict__ jvec)
 {
     // decode the upper-triangular tile pair (tr <= tc) from blockIdx.x
     int rem = blockIdx.x, tr = 0;
@@ -396,25 +454,26 @@ k_gram_finalize(int N, int NT, int P, long long n_tiles, const int *__restrict__
     const int e_direct = (i * 4 + (jx >> 1)) * 2 + (jx & 1);        // C-fragment slot of element (i, jx)
     const int e_transp = (jx * 4 + (i >> 1)) * 2 + (i & 1);         // ... of element (jx, i)
     int type, idx;
+    const int *pc = pair_code + (pa * P + pb) * 3;
     if (pa < pb) {
-        const int lrp = tr - panel_t0[pa], h0 = (panel_nt[pa] + 1) / 2;
+        const int lrp = tr - panel_t0[pa], h0 = pc[2];
         const int half = lrp >= h0 ? 1 : 0;
-        type = pair_code[(pa * P + pb) * 2 + half];
-        idx = ((lrp - half * h0) * FB_PT + (tc - panel_t0[pb])) * 64 + e_direct;
+        type = pc[half];
+        idx = ((lrp - half * h0) * types[type].ld + (tc - panel_t0[pb])) * 64 + e_direct;
     } else {
-        type = pair_code[(pa * P + pa) * 2];
+        type = pc[0];
         const int n = panel_nt[pa], D = n / 2 + 1;
         const int lr = tr - panel_t0[pa], lc = tc - panel_t0[pa], d = lc - lr;
         if (d < D)
-            idx = (lr * FB_DH + d) * 64 + e_direct;
+            idx = (lr * D + d) * 64 + e_direct;
         else   // stored as the transposed tile (row tile lc, offset n - d)
-            idx = (lc * FB_DH + (n - d)) * 64 + e_transp;
+            idx = (lc * D + (n - d)) * 64 + e_transp;
     }
     const int Ct = type_tab[2 * type], first = type_tab[2 * type + 1];
     double s = 0.0;
     for (int c = 0; c < Ct; c++) {
-        const long long t0 = (n_tiles * c) / Ct, t1 = (n_tiles * (c + 1)) / Ct;
-        if (t1 > t0) s += partial[(size_t)(first + c) * FB_PSZ + idx];
+        const long long q0 = (n_tiles * c) / Ct, q1 = (n_tiles * (c + 1)) / Ct;
+        if (q1 > q0) s += partial[(size_t)(first + c) * FB_PSZ + idx];
     }
     if (col < N) {           // row <= col < N
         const double val = ((ck[row] * scale) * (ck[col] * scale)) * s;
@@ -449,10 +508,28 @@ k_predict(int64_t n, int N, const double *__restrict__ q, const double *__restri
     if (lane == 0) V[i] = acc;
 }
 
-__global__ void k_j0_debug(int64_t n, const double *__restrict__ x, double *__restrict__ out, const double2 *tab, int rows)
+// far = 0: the row nearest to x (|t| <= 1/32, the gather path); far = 1: the neighbouring row on the other side
+// (1/32 <= |t| <= 1/16), i.e. the worst case the producers accept
+__global__ void k_j0_debug(int64_t n, const double *__restrict__ x, double *__restrict__ out, const double2 *tab, int rows, int far)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = j0_tab(x[i], tab, rows - 1);
+    if (i >= n) return;
+    if (!far) { out[i] = j0_tab(x[i], tab, rows - 1); return; }
+    const double xv = x[i];
+    int m = min(__double2loint(fma(xv, FB_J0_INVH, J0_MAGIC)), rows - 1);
+    double t = fma((double)m, -FB_J0_H, xv);
+    int m2 = t >= 0.0 ? m + 1 : m - 1;
+    if (m2 < 0 || m2 > rows - 1) m2 = m;
+    t = fma((double)m2, -FB_J0_H, xv);
+    const double2 *row = tab + (size_t)m2 * (FB_J0_ROWLEN / 2);
+    const double2 c01 = row[0], c23 = row[1], c45 = row[2], c67 = row[3];
+    double y = fma(c67.y, t, c67.x);
+    y = fma(y, t, c45.y);
+    y = fma(y, t, c45.x);
+    y = fma(y, t, c23.y);
+    y = fma(y, t, c23.x);
+    y = fma(y, t, c01.y);
+    out[i] = fma(y, t, c01.x);
 }
 
 }  // namespace
@@ -462,38 +539,123 @@ __global__ void k_j0_debug(int64_t n, const double *__restrict__ x, double *__re
 // ---------------------------------------------------------------------------------------------
 int fb_build_j0_table(fb_ctx *ctx, double x_max)
 {
-    // Rows centred on m/4; Taylor coefficients from the Bessel ODE  x y'' + y' + x y = 0:
-    //   a_{k+2} = -[(k+1)^2 a_{k+1} + c a_k + a_{k-1}] / (c (k+2)(k+1)),  a_0 = J0(c), a_1 = -J1(c),
-    // seeded with glibc's 80-bit j0l / j1l and run in long double, then rounded to double.
-    const int rows = (int)std::ceil(x_max * 4.0) + 3;
-    std::vector<double> tab((size_t)rows * FB_J0_ROWLEN);
-    for (int m = 0; m < rows; m++) {
-        long double a[FB_J0_ROWLEN + 2];
-        if (m == 0) {
-            // J0(t) = sum_k (-1/4)^k t^(2k) / (k!)^2
-            long double term = 1.0L;
-            for (int k = 0; k < FB_J0_ROWLEN; k++) a[k] = 0.0L;
-            for (int k = 0; 2 * k < FB_J0_ROWLEN; k++) {
-                a[2 * k] = term;
-                term *= -0.25L / ((long double)(k + 1) * (long double)(k + 1));
-            }
-        } else {
-            const long double c = 0.25L * (long double)m;
-            a[0] = j0l(c);
-            a[1] = -j1l(c);
-            for (int k = 0; k + 2 < FB_J0_ROWLEN; k++) {
-                const long double prev = k == 0 ? 0.0L : a[k - 1];
-                a[k + 2] = -(((long double)(k + 1) * (k + 1)) * a[k + 1] + c * a[k] + prev) /
-                           (c * (long double)((k + 2) * (k + 1)));
-            }
-        }
-        for (int k = 0; k < FB_J0_ROWLEN; k++) tab[(size_t)m * FB_J0_ROWLEN + k] = (double)a[k];
-    }
+    std::vector<double> tab;
+    fb_j0_build(x_max, tab);
     if (ctx->d_tab) FB_CUDA(cudaFree(ctx->d_tab));
     ctx->d_tab = nullptr;
     FB_CUDA(cudaMalloc(&ctx->d_tab, tab.size() * sizeof(double)));
     FB_CUDA(cudaMemcpy(ctx->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-    ctx->tab_rows = rows;
+    ctx->tab_rows = fb_j0_rows_for(x_max);
+    return 0;
+}
+
+namespace {
+
+int cdiv4(int n) { return (n + 3) / 4; }
+bool off_fits(int a, int b) { return cdiv4(a) * cdiv4(b) <= FB_ACC && cdiv4(a) <= 5 && cdiv4(b) <= 5 && (a + b) * 8 <= FB_GCOLS; }
+bool diag_fits(int n) { return cdiv4(n) * cdiv4(n / 2 + 1) <= FB_ACC && cdiv4(n) <= 5 && n * 8 <= FB_GCOLS; }
+
+// Cost of a block per tile of FB_TV visibilities, in FP64-pipe clocks of the busiest SM sub-partition:
+// a DMMA holds the pipe for 16 clocks, a J0 evaluation is ~10 FP64 instructions of 2 clocks for 32 lanes.
+double block_cost(const FbGramType &ty)
+{
+    const int nrows = ty.a_nt, ncols = ty.kind == FB_KIND_OFF ? ty.b_nt : ty.a_nt / 2 + 1;
+    int worst = 0;
+    for (int s = 0; s < 4; s++) {
+        int t = 0;
+        for (int slot = 0; slot < 4; slot++) t += split4_size(nrows, slot) * split4_size(ncols, (slot + s) & 3);
+        worst = std::max(worst, t);
+    }
+    const int cols = 8 * (ty.kind == FB_KIND_OFF ? ty.a_nt + ty.b_nt : ty.a_nt);
+    static const double j0w = getenv("FB_J0_COST") ? atof(getenv("FB_J0_COST")) : 12.0;
+    return 16.0 * (FB_TV / 4) * worst + j0w * cols;
+}
+
+struct GramPlan {
+    int P = 0;
+    std::vector<int> panel_t0, panel_nt;
+    std::vector<FbGramType> types;
+    std::vector<int> pair_code;
+    double cost = 0.0;
+    bool ok = false;
+};
+
+GramPlan make_plan(int NT, int P)
+{
+    GramPlan pl;
+    pl.P = P;
+    pl.panel_t0.resize(P);
+    pl.panel_nt.resize(P);
+    const int base = NT / P, rem = NT % P;
+    int t = 0;
+    for (int p = 0; p < P; p++) {
+        pl.panel_t0[p] = t;
+        pl.panel_nt[p] = base + (p < rem ? 1 : 0);
+        t += pl.panel_nt[p];
+    }
+    pl.pair_code.assign((size_t)P * P * 3, -1);
+    for (int pa = 0; pa < P; pa++)
+        for (int pb = pa + 1; pb < P; pb++) {
+            int *pc = &pl.pair_code[((size_t)pa * P + pb) * 3];
+            const int na = pl.panel_nt[pa], nb = pl.panel_nt[pb];
+            if (off_fits(na, nb)) {
+                pc[0] = (int)pl.types.size(); pc[1] = -1; pc[2] = na;
+                pl.types.push_back({FB_KIND_OFF, pl.panel_t0[pa], na, pl.panel_t0[pb], nb, nb});
+            } else {
+                const int h0 = (na + 1) / 2;
+                if (!off_fits(h0, nb) || na - h0 < 1) return pl;
+                pc[0] = (int)pl.types.size(); pc[2] = h0;
+                pl.types.push_back({FB_KIND_OFF, pl.panel_t0[pa], h0, pl.panel_t0[pb], nb, nb});
+                pc[1] = (int)pl.types.size();
+                pl.types.push_back({FB_KIND_OFF, pl.panel_t0[pa] + h0, na - h0, pl.panel_t0[pb], nb, nb});
+            }
+        }
+    for (int p = 0; p < P; p++) {
+        if (!diag_fits(pl.panel_nt[p])) return pl;
+        pl.pair_code[((size_t)p * P + p) * 3] = (int)pl.types.size();
+        pl.types.push_back({FB_KIND_DIAG, pl.panel_t0[p], pl.panel_nt[p], 0, 0, pl.panel_nt[p] / 2 + 1});
+    }
+    for (const FbGramType &ty : pl.types) pl.cost += block_cost(ty);
+    pl.ok = true;
+    return pl;
+}
+
+}  // namespace
+
+// Choose the panel decomposition of the NT x NT tile grid (cheapest of a few panel counts) and upload it.
+int fb_build_gram_plan(fb_ctx *ctx)
+{
+    const int NT = ctx->NT;
+    GramPlan best;
+    const int Pmin = (NT + FB_PT - 1) / FB_PT;
+    for (int P = Pmin; P <= std::min(NT, Pmin + 3); P++) {
+        GramPlan pl = make_plan(NT, P);
+        if (pl.ok && (!best.ok || pl.cost < best.cost)) best = pl;
+    }
+    if (!best.ok) FB_FAIL(-16, "fb_dht_setup: no feasible block decomposition");
+    const int P = best.P;
+    ctx->P = P;
+    ctx->h_types = best.types;
+    ctx->ntypes = (int)best.types.size();
+    std::vector<int> tile_panel(NT);
+    for (int p = 0; p < P; p++)
+        for (int i = 0; i < best.panel_nt[p]; i++) tile_panel[best.panel_t0[p] + i] = p;
+    for (void **p : {(void **)&ctx->d_types, (void **)&ctx->d_tile_panel, (void **)&ctx->d_panel_t0,
+                     (void **)&ctx->d_panel_nt, (void **)&ctx->d_pair_code}) {
+        if (*p) FB_CUDA(cudaFree(*p));
+        *p = nullptr;
+    }
+    FB_CUDA(cudaMalloc(&ctx->d_types, sizeof(FbGramType) * ctx->ntypes));
+    FB_CUDA(cudaMalloc(&ctx->d_tile_panel, sizeof(int) * NT));
+    FB_CUDA(cudaMalloc(&ctx->d_panel_t0, sizeof(int) * P));
+    FB_CUDA(cudaMalloc(&ctx->d_panel_nt, sizeof(int) * P));
+    FB_CUDA(cudaMalloc(&ctx->d_pair_code, sizeof(int) * P * P * 3));
+    FB_CUDA(cudaMemcpy(ctx->d_types, ctx->h_types.data(), sizeof(FbGramType) * ctx->ntypes, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_tile_panel, tile_panel.data(), sizeof(int) * NT, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_panel_t0, best.panel_t0.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_panel_nt, best.panel_nt.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(ctx->d_pair_code, best.pair_code.data(), sizeof(int) * P * P * 3, cudaMemcpyHostToDevice));
+
     return 0;
 }
 
@@ -501,54 +663,59 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
 {
     const long long n_tiles = (n + FB_TV - 1) / FB_TV;
     const int ntypes = ctx->ntypes;
-    // Chunks per type, proportional to the type's cost per visibility on the FP64 pipe
-    // (64 FMA-lanes per accumulator tile, ~14 per J0 evaluation) so that all SMs finish together.
+    const int grid = ctx->num_sms;
+    // Work items = (type, chunk of the visibilities).  Chunks per type proportional to the type's cost, about
+    // three items per SM in total; the items are then dealt to the CTAs longest-first (deterministic).
     std::vector<double> cost(ntypes);
     double total = 0.0;
-    for (int t = 0; t < ntypes; t++) {
-        const FbGramType &ty = ctx->h_types[t];
-        double tiles, cols;
-        if (ty.kind == FB_KIND_OFF) { tiles = (double)ty.a_nt * ty.b_nt; cols = 8.0 * (ty.a_nt + ty.b_nt); }
-        else { tiles = (double)ty.a_nt * (ty.a_nt / 2 + 1); cols = 8.0 * ty.a_nt; }
-        cost[t] = 64.0 * tiles + 14.0 * cols;
-        total += cost[t];
-    }
+    for (int t = 0; t < ntypes; t++) { cost[t] = block_cost(ctx->h_types[t]); total += cost[t]; }
+    const double target = 3.0 * grid;
     std::vector<int> C(ntypes, 1);
-    if (ntypes < ctx->num_sms) {
-        int used = 0;
-        for (int t = 0; t < ntypes; t++) {
-            C[t] = std::max(1, (int)std::floor(ctx->num_sms * cost[t] / total));
-            used += C[t];
-        }
-        // hand the left-over SMs to the types with the largest cost per chunk
-        while (used < ctx->num_sms) {
-            int best = 0;
-            for (int t = 1; t < ntypes; t++)
-                if (cost[t] / C[t] > cost[best] / C[best]) best = t;
-            C[best]++;
-            used++;
-        }
+    for (int t = 0; t < ntypes; t++) {
+        long long c = (long long)std::llround(target * cost[t] / total);
+        c = std::max<long long>(1, std::min<long long>(c, std::max<long long>(1, n_tiles)));
+        C[t] = (int)c;
     }
-    for (int t = 0; t < ntypes; t++)
-        if ((long long)C[t] > n_tiles) C[t] = (int)std::max<long long>(1, n_tiles);
-    std::vector<int> work;
     std::vector<int> type_tab(2 * ntypes);
     int n_items = 0;
     for (int t = 0; t < ntypes; t++) { type_tab[2 * t] = C[t]; type_tab[2 * t + 1] = n_items; n_items += C[t]; }
-    work.resize(3 * (size_t)n_items);
+    struct Item { double cost; int type, chunk; };
+    std::vector<Item> order;
+    order.reserve(n_items);
+    for (int t = 0; t < ntypes; t++)
+        for (int c = 0; c < C[t]; c++) {
+            const long long q0 = (n_tiles * c) / C[t], q1 = (n_tiles * (c + 1)) / C[t];
+            order.push_back({cost[t] * (double)(q1 - q0), t, c});
+        }
+    std::stable_sort(order.begin(), order.end(), [](const Item &x, const Item &y) { return x.cost > y.cost; });
+    std::vector<std::vector<int>> per_cta(grid);
     {
-        // costliest chunks first; types interleaved
-        std::vector<std::pair<double, std::pair<int, int>>> order;
-        for (int t = 0; t < ntypes; t++)
-            for (int c = 0; c < C[t]; c++) order.push_back({-cost[t] / C[t], {c, t}});
-        std::stable_sort(order.begin(), order.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+        typedef std::pair<double, int> Load;     // (load, cta), smallest load first, ties by CTA index
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+        for (int b = 0; b < grid; b++) heap.push({0.0, b});
         for (int i = 0; i < n_items; i++) {
-            const int t = order[i].second.second, c = order[i].second.first;
-            work[3 * i] = t; work[3 * i + 1] = c; work[3 * i + 2] = type_tab[2 * t + 1] + c;
+            Load l = heap.top();
+            heap.pop();
+            per_cta[l.second].push_back(i);
+            heap.push({l.first + order[i].cost, l.second});
         }
     }
-    const int types_off = 3 * n_items;
-    work.insert(work.end(), type_tab.begin(), type_tab.end());
+    // work buffer: [grid + 1] CTA offsets | [3 * n_items] items | [2 * ntypes] type table
+    std::vector<int> work(grid + 1 + 3 * (size_t)n_items + 2 * ntypes);
+    {
+        int pos = 0;
+        for (int b = 0; b < grid; b++) {
+            work[b] = pos;
+            for (int i : per_cta[b]) {
+                const Item &it = order[i];
+                int *w = &work[grid + 1 + 3 * (size_t)pos];
+                w[0] = it.type; w[1] = it.chunk; w[2] = type_tab[2 * it.type + 1] + it.chunk;
+                pos++;
+            }
+        }
+        work[grid] = pos;
+        std::copy(type_tab.begin(), type_tab.end(), work.begin() + grid + 1 + 3 * (size_t)n_items);
+    }
     if ((int)work.size() > ctx->work_cap) {
         if (ctx->d_work) FB_CUDA(cudaFree(ctx->d_work));
         ctx->d_work = nullptr;
@@ -567,37 +734,57 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
     FB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 
     GramArgs args;
-    args.a = ctx->d_a; args.sw = ctx->d_sw; args.swV = ctx->d_swV; args.kz = ctx->d_kz;
+    args.a = ctx->d_a; args.sw = ctx->d_sw; args.swV = ctx->d_swV; args.kz = ctx->d_kz; args.arange = (const double2 *)ctx->d_amid;
     args.n_tiles = n_tiles;
     args.jk = ctx->d_jk; args.tab = ctx->d_tab; args.tab_rows = ctx->tab_rows;
-    args.N = ctx->N; args.n_items = n_items;
-    args.types = ctx->d_types; args.work = ctx->d_work; args.work_types_off = types_off;
+    args.N = ctx->N;
+    args.types = ctx->d_types;
+    args.cta_off = ctx->d_work; args.items = ctx->d_work + grid + 1; args.type_tab = ctx->d_work + grid + 1 + 3 * (size_t)n_items;
     args.H2 = ctx->d_H2; args.partial = ctx->d_partial;
     {
         const char *dbg = getenv("FB_GRAM_DEBUG");
         args.debug_mode = dbg ? atoi(dbg) : 0;
+        args.prof = nullptr;
+        if (getenv("FB_GRAM_PROF")) {
+            FB_CUDA(cudaMalloc(&args.prof, sizeof(long long) * 2 * grid));
+            FB_CUDA(cudaMemsetAsync(args.prof, 0, sizeof(long long) * 2 * grid, ctx->stream));
+        }
     }
-    int grid = std::min(n_items, ctx->num_sms);
     if (n_tiles > 0) {
         if (vis_model == FB_MODEL_DEBRIS) {
-            FB_CUDA(cudaFuncSetAttribute(k_gram<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM_BYTES));
+            FB_CUDA(cudaFuncSetAttribute(k_gram<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
             k_gram<true><<<grid, FB_GRAM_THREADS, GRAM_SMEM_BYTES, ctx->stream>>>(args);
         } else {
-            FB_CUDA(cudaFuncSetAttribute(k_gram<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM_BYTES));
+            FB_CUDA(cudaFuncSetAttribute(k_gram<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
             k_gram<false><<<grid, FB_GRAM_THREADS, GRAM_SMEM_BYTES, ctx->stream>>>(args);
         }
         FB_CUDA(cudaGetLastError());
     }
     FB_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (args.prof) {
+        std::vector<long long> h(2 * grid);
+        FB_CUDA(cudaStreamSynchronize(ctx->stream));
+        FB_CUDA(cudaMemcpy(h.data(), args.prof, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
+        long long j0_sum = 0, mma_sum = 0, j0_max = 0, mma_max = 0, tot_max = 0, tot_min = -1;
+        for (int b = 0; b < grid; b++) {
+            j0_sum += h[2 * b]; mma_sum += h[2 * b + 1];
+            j0_max = std::max(j0_max, h[2 * b]); mma_max = std::max(mma_max, h[2 * b + 1]);
+            tot_max = std::max(tot_max, h[2 * b] + h[2 * b + 1]);
+            tot_min = tot_min < 0 ? h[2 * b] + h[2 * b + 1] : std::min(tot_min, h[2 * b] + h[2 * b + 1]);
+        }
+        fprintf(stderr, "[fb_gram prof] tiles=%lld  per-CTA clocks: J0 avg %.0f max %lld | DMMA avg %.0f max %lld | total min %lld max %lld\n",
+                n_tiles, (double)j0_sum / grid, j0_max, (double)mma_sum / grid, mma_max, tot_min, tot_max);
+        cudaFree(args.prof);
+    }
     const int npairs = ctx->NT * (ctx->NT + 1) / 2;
     k_gram_finalize<<<npairs, 64, 0, ctx->stream>>>(ctx->N, ctx->NT, ctx->P, n_tiles, ctx->d_tile_panel, ctx->d_panel_t0,
-                                                    ctx->d_panel_nt, ctx->d_pair_code, ctx->d_work + types_off,
+                                                    ctx->d_panel_nt, ctx->d_pair_code, ctx->d_types, args.type_tab,
                                                     ctx->d_partial, ctx->d_ck, model_scale, dev_M, dev_j);
     FB_CUDA(cudaGetLastError());
     return 0;
 }
 
-extern "C" int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out)
+static int debug_j0_impl(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out, int far)
 {
     if (!ctx || !ctx->d_tab) return -1;
     double *dx = nullptr, *dout = nullptr;
@@ -605,13 +792,23 @@ extern "C" int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double 
     FB_CUDA(cudaMalloc(&dx, sizeof(double) * n));
     FB_CUDA(cudaMalloc(&dout, sizeof(double) * n));
     FB_CUDA(cudaMemcpy(dx, host_x, sizeof(double) * n, cudaMemcpyHostToDevice));
-    k_j0_debug<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, dx, dout, ctx->d_tab, ctx->tab_rows);
+    k_j0_debug<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, dx, dout, ctx->d_tab, ctx->tab_rows, far);
     FB_CUDA(cudaGetLastError());
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
     FB_CUDA(cudaMemcpy(host_out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
     cudaFree(dx);
     cudaFree(dout);
     return 0;
+}
+
+extern "C" int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out)
+{
+    return debug_j0_impl(ctx, n, host_x, host_out, 0);
+}
+
+extern "C" int fb_debug_j0_far(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out)
+{
+    return debug_j0_impl(ctx, n, host_x, host_out, 1);
 }
 
 extern "C" int fb_predict_visibilities(fb_ctx *ctx, int64_t n, const double *host_q, const double *host_kz, const double *host_I,
@@ -627,7 +824,7 @@ extern "C" int fb_predict_visibilities(fb_ctx *ctx, int64_t n, const double *hos
     double qmax = 0.0;
     for (int64_t i = 0; i < n; i++) qmax = host_q[i] > qmax ? host_q[i] : qmax;
     const double xneed = qmax * ctx->invQmax * ctx->h_jk[N - 1];
-    if (xneed * 4.0 + 2.0 > (double)ctx->tab_rows) {
+    if (fb_j0_rows_for(xneed) > ctx->tab_rows) {
         int rc = fb_build_j0_table(ctx, xneed * 1.05);
         if (rc) return rc;
     }

@@ -153,7 +153,9 @@ int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, con
         if (ctx->d_rec) FB_CUDA(cudaFree(ctx->d_rec));
         if (ctx->d_items) FB_CUDA(cudaFree(ctx->d_items));
         if (ctx->d_perm) FB_CUDA(cudaFree(ctx->d_perm));
-        ctx->d_rec = nullptr; ctx->d_items = nullptr; ctx->d_perm = nullptr;
+        if (ctx->d_amid) FB_CUDA(cudaFree(ctx->d_amid));
+        ctx->d_rec = nullptr; ctx->d_items = nullptr; ctx->d_perm = nullptr; ctx->d_amid = nullptr;
+        FB_CUDA(cudaMalloc(&ctx->d_amid, sizeof(double) * 2 * (cap / FB_TV + 1)));
         FB_CUDA(cudaMalloc(&ctx->d_rec, sizeof(double) * 4 * cap));
         FB_CUDA(cudaMalloc(&ctx->d_items, sizeof(uint64_t) * 2 * cap));
         FB_CUDA(cudaMalloc(&ctx->d_perm, sizeof(uint32_t) * cap));

@@ -6,8 +6,9 @@
 // uv-binning pass (frank/utilities.py:300-367 accumulates with np.bincount; here bins become contiguous
 // segments).
 //
-// Key = floor(a * key_scale) clipped to 16 bits (Gram) or the uv-bin index (binner); payload = original index.
-// 8-bit digits, 2 passes for the Gram, ceil(bits / 8) for the binner.  Each pass: per-block digit histograms -> exclusive scan over (digit, block) ->
+// Key = floor(a * key_scale) clipped to 16 or 24 bits (Gram; 24 when the modes reach arguments so large that a
+// 16-bit bin would span more than the validity window of a J0 table row) or the uv-bin index (binner); payload =
+// original index.  8-bit digits, ceil(bits / 8) passes.  Each pass: per-block digit histograms -> exclusive scan over (digit, block) ->
 // stable scatter.  Stability (and therefore bit-reproducible sums downstream) comes from ranking inside a
 // block with __match_any_sync in a fixed element order.
 #include "fb_common.cuh"
@@ -25,14 +26,14 @@ __device__ __forceinline__ int64_t elem_index(int64_t base, int warp, int round,
     return base + (int64_t)warp * (32 * SORT_ROUNDS) + round * 32 + lane;
 }
 
-// key = floor(a * key_scale) clipped to 16 bits, payload = index
+// key = floor(a * key_scale) clipped to [0, kmax], payload = index
 __global__ void __launch_bounds__(256)
-k_items_from_rec(int64_t n, const double4 *__restrict__ rec, double key_scale, uint64_t *__restrict__ items)
+k_items_from_rec(int64_t n, const double4 *__restrict__ rec, double key_scale, int kmax, uint64_t *__restrict__ items)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         int k = __double2int_rz(rec[i].x * key_scale);
-        k = k < 0 ? 0 : (k > 65535 ? 65535 : k);
+        k = k < 0 ? 0 : (k > kmax ? kmax : k);
         items[i] = ((uint64_t)k << 32) | (uint64_t)(uint32_t)i;
     }
 }
@@ -163,20 +164,43 @@ k_sort_scatter(int64_t n, const uint64_t *__restrict__ items, int shift, const u
     }
 }
 
-// permute the records into the structure-of-arrays layout the Gram kernel reads; zero padding to n_pad
+// permute the records into the structure-of-arrays layout the Gram kernel reads; zero padding to n_pad.
+// A block covers 4 tiles of FB_TV = 64 sorted visibilities: it also records each tile's range (min a, max a), from
+// which the Gram kernel picks one J0 table row per (mode, tile).
 __global__ void __launch_bounds__(256)
 k_sort_gather(int64_t n, int64_t n_pad, const uint64_t *__restrict__ items, const double4 *__restrict__ rec,
               double *__restrict__ a, double *__restrict__ sw, double *__restrict__ swV, double *__restrict__ kz,
-              uint32_t *__restrict__ perm)
+              uint32_t *__restrict__ perm, double *__restrict__ amid)
 {
+    static_assert(FB_TV == 64, "two warps per tile");
+    __shared__ double s_lo[8], s_hi[8];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double lo = INFINITY, hi = -INFINITY;
     if (i < n) {
         const uint32_t src = (uint32_t)(items[i] & 0xffffffffull);
         const double4 r = rec[src];
         a[i] = r.x; sw[i] = r.y; swV[i] = r.z; kz[i] = r.w;
         perm[i] = src;
+        lo = hi = r.x;
     } else if (i < n_pad) {
         a[i] = 0.0; sw[i] = 0.0; swV[i] = 0.0; kz[i] = 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int64_t tile = (int64_t)blockIdx.x * 4 + threadIdx.x;
+        if (tile * FB_TV < n_pad) {
+            const double l = fmin(s_lo[2 * threadIdx.x], s_lo[2 * threadIdx.x + 1]);
+            const double h = fmax(s_hi[2 * threadIdx.x], s_hi[2 * threadIdx.x + 1]);
+            amid[2 * tile] = h >= l ? l : 0.0;
+            amid[2 * tile + 1] = h >= l ? h : 0.0;
+        }
     }
 }
 
@@ -217,15 +241,17 @@ int fb_items_from_keys(fb_ctx *ctx, int64_t n, const int32_t *dev_keys, uint64_t
 int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max)
 {
     if (n <= 0) return 0;
-    const double key_scale = a_max > 0 ? 65535.5 / a_max : 0.0;
+    const int nbits = ctx->sort_bits;
+    const int kmax = (1 << nbits) - 1;
+    const double key_scale = a_max > 0 ? ((double)kmax + 0.5) / a_max : 0.0;
     const double4 *rec = (const double4 *)ctx->d_rec;
     uint64_t *buf0 = ctx->d_items, *buf1 = ctx->d_items + ctx->cap;
-    k_items_from_rec<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, rec, key_scale, buf0);
+    k_items_from_rec<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, rec, key_scale, kmax, buf0);
     int st = 0;
-    uint64_t *sorted = fb_radix_sort_items(ctx, n, buf0, buf1, 16, &st);
+    uint64_t *sorted = fb_radix_sort_items(ctx, n, buf0, buf1, nbits, &st);
     if (st) return st;
     k_sort_gather<<<(unsigned)((n_pad + 255) / 256), 256, 0, ctx->stream>>>(n, n_pad, sorted, rec, ctx->d_a, ctx->d_sw, ctx->d_swV,
-                                                                         ctx->d_kz, ctx->d_perm);
+                                                                         ctx->d_kz, ctx->d_perm, ctx->d_amid);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -165,8 +165,11 @@ int fb_uv_bin(fb_ctx *ctx, int64_t n, const double *host_uv, const double *host_
 int fb_predict_visibilities(fb_ctx *ctx, int64_t n, const double *host_q, const double *host_kz, const double *host_I,
                             int vis_model, double model_scale, const double *host_H2, double *host_V);
 
-/* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]). */
+/* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]).
+ * fb_debug_j0 uses the table row nearest to x (the per-visibility gather path); fb_debug_j0_far uses the
+ * neighbouring row on the far side of x, the worst case of the one-row-per-stage path. */
 int fb_debug_j0(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out);
+int fb_debug_j0_far(fb_ctx *ctx, int64_t n, const double *host_x, double *host_out);
 
 #ifdef __cplusplus
 }
