@@ -107,8 +107,8 @@ constexpr int ROWB = FB_J0_ROWLEN * 8; // bytes per table row (64)
 // shared-memory carve-up (bytes)
 constexpr int SMB_G = 0;                                   // [GCOLS][GLD] doubles      design-matrix tile
 constexpr int SMB_ROW = SMB_G + GCOLS * GLD * 8;           // [2][4][GCOLS] double2     staged J0 table rows (coefficient pair major)
-constexpr int SMB_CEN = SMB_ROW + 2 * GCOLS * ROWB;        // [2][GCOLS] double2        (centre of the staged row, row serves the whole tile ? 1 : 0)
-constexpr int SMB_JK = SMB_CEN + 2 * GCOLS * 16;           // [GCOLS] doubles           j_k (>= 0), -1 data column, -2 padding
+constexpr int SMB_CEN = SMB_ROW + 2 * GCOLS * ROWB;        // [2][GCOLS] double2        (centre of the staged row, 1 row serves the tile | 0 gather | -1 special column)
+constexpr int SMB_JK = SMB_CEN + 2 * GCOLS * 16;           // [GCOLS] doubles           j_k (0 for the data column and the padding)
 constexpr int SMB_H2 = SMB_JK + GCOLS * 8;                 // [GCOLS] doubles           debris H2_k
 constexpr int SMB_VIS = SMB_H2 + GCOLS * 8;                // [2][GS][4] doubles        (a, sqrt w, kz, sqrt w Re V) per visibility of a tile
 constexpr int SMB_AR = SMB_VIS + 2 * GS * 32;               // [2] double2               (min a, max a) of the tiles being staged
@@ -171,11 +171,10 @@ __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sba
     uint32_t a_g = sbase + SMB_G + (warp * GLD + lane) * 8;
 #pragma unroll 1
     for (int sc = warp; sc < ncol; sc += NW) {
-        const double jkc = lds_f64(a_jk);                            // j_k >= 0 | -1 data column | -2 padding
-        const double2 cv = lds_v2f64(a_cen);                         // (centre, row serves the whole tile)
+        const double jk = lds_f64(a_jk);                             // j_k (0 for the data column and the padding)
+        const double2 cv = lds_v2f64(a_cen);                         // (centre, 1 row serves the tile | 0 gather | -1 no store)
         const double2 c67 = lds_v2f64(a_row + 3 * GCOLS * 16), c45 = lds_v2f64(a_row + 2 * GCOLS * 16),
                       c23 = lds_v2f64(a_row + GCOLS * 16), c01 = lds_v2f64(a_row);
-        const double jk = fmax(jkc, 0.0);
         const double x0 = __dmul_rn(aw0.x, jk), x1 = __dmul_rn(aw1.x, jk);      // a * j_k as the reference rounds it
         const double u0 = __dsub_rn(x0, cv.x), u1 = __dsub_rn(x1, cv.x);        // exact
         double g0 = fma(c67.y, u0, c67.x), g1 = fma(c67.y, u1, c67.x);
@@ -185,7 +184,8 @@ __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sba
         g0 = fma(g0, u0, c23.x); g1 = fma(g1, u1, c23.x);
         g0 = fma(g0, u0, c01.y); g1 = fma(g1, u1, c01.y);
         g0 = fma(g0, u0, c01.x); g1 = fma(g1, u1, c01.x);
-        if (cv.y == 0.0) {                                           // warp-uniform, rare
+        const int flag = __double2hiint(cv.y);                       // 0x3ff00000 | 0 | 0xbff00000
+        if (flag == 0) {                                             // warp-uniform, rare
             g0 = j0_tab(x0, p.tab, last_row);
             g1 = j0_tab(x1, p.tab, last_row);
         }
@@ -194,7 +194,7 @@ __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sba
             g0 *= exp_neg(k0 * h2);
             g1 *= exp_neg(k1 * h2);
         }
-        if (jkc >= 0.0) {                                            // the data column and the padding are written elsewhere
+        if (flag >= 0) {                                             // the data column and the padding are written elsewhere
             sts_f64(a_g, g0 * aw0.y);
             sts_f64(a_g + 32 * 8, g1 * aw1.y);
         }
@@ -286,6 +286,8 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
                 const double cen = (double)m * FB_J0_H;
                 const double valid = (fabs(xlo - cen) < FB_J0_ACCEPT && fabs(xhi - cen) < FB_J0_ACCEPT) ? 1.0 : 0.0;
                 sts_v2f64(sbase + SMB_CEN + (buf * GCOLS + tid) * 16, cen, valid);
+            } else if (tid < it.ncol) {
+                sts_v2f64(sbase + SMB_CEN + (buf * GCOLS + tid) * 16, 0.0, -1.0);
             }
 #pragma unroll
             for (int r = 0; r < 4; r++) {
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
                 else if (g == p.N) v = -1.0;
             }
             it.my_jk = v;
-            sts_f64(sbase + SMB_JK + tid * 8, v);
+            sts_f64(sbase + SMB_JK + tid * 8, v >= 0.0 ? v : 0.0);
             if (DEBRIS) sts_f64(sbase + SMB_H2 + tid * 8, h);
             if (v == -2.0 && tid < it.ncol) {            // zero padding columns stay zero for the whole item
                 for (int x = 0; x < GS; x++) sts_f64(sbase + SMB_G + (tid * GLD + x) * 8, 0.0);
@@ -635,6 +637,11 @@ int fb_build_gram_plan(fb_ctx *ctx)
     if (!best.ok) FB_FAIL(-16, "fb_dht_setup: no feasible block decomposition");
     const int P = best.P;
     ctx->P = P;
+    if (getenv("FB_GRAM_PROF")) {
+        fprintf(stderr, "[fb_gram plan] NT=%d P=%d types=%d cost=%.0f :", NT, P, (int)best.types.size(), best.cost);
+        for (const FbGramType &ty : best.types) fprintf(stderr, " %s%dx%d", ty.kind == FB_KIND_OFF ? "O" : "D", ty.a_nt, ty.kind == FB_KIND_OFF ? ty.b_nt : ty.a_nt / 2 + 1);
+        fprintf(stderr, "\n");
+    }
     ctx->h_types = best.types;
     ctx->ntypes = (int)best.types.size();
     std::vector<int> tile_panel(NT);
@@ -664,17 +671,31 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
     const long long n_tiles = (n + FB_TV - 1) / FB_TV;
     const int ntypes = ctx->ntypes;
     const int grid = ctx->num_sms;
-    // Work items = (type, chunk of the visibilities).  Chunks per type proportional to the type's cost, about
-    // three items per SM in total; the items are then dealt to the CTAs longest-first (deterministic).
+    // Work items = (type, chunk of the visibilities).  Chunks per type proportional to the type's cost; the items
+    // are then dealt to the CTAs longest-first (deterministic).
     std::vector<double> cost(ntypes);
     double total = 0.0;
     for (int t = 0; t < ntypes; t++) { cost[t] = block_cost(ctx->h_types[t]); total += cost[t]; }
-    const double target = 3.0 * grid;
+    // number of items: a multiple of the grid (6 per SM, more when there are many types), split over the types by
+    // largest remainders so that the total is exact
+    long long target = std::max<long long>(6LL * grid, 4LL * ntypes);
+    target = (target + grid - 1) / grid * grid;
     std::vector<int> C(ntypes, 1);
-    for (int t = 0; t < ntypes; t++) {
-        long long c = (long long)std::llround(target * cost[t] / total);
-        c = std::max<long long>(1, std::min<long long>(c, std::max<long long>(1, n_tiles)));
-        C[t] = (int)c;
+    {
+        std::vector<std::pair<double, int>> rem(ntypes);
+        long long sum = 0;
+        for (int t = 0; t < ntypes; t++) {
+            const double x = (double)target * cost[t] / total;
+            long long c = std::max<long long>(1, (long long)std::floor(x));
+            C[t] = (int)c;
+            sum += c;
+            rem[t] = {x - std::floor(x), t};
+        }
+        std::sort(rem.begin(), rem.end(), [](const std::pair<double, int> &x, const std::pair<double, int> &y) {
+            return x.first != y.first ? x.first > y.first : x.second < y.second;
+        });
+        for (int i = 0; sum < target && i < ntypes; i++, sum++) C[rem[i].second]++;
+        for (int t = 0; t < ntypes; t++) C[t] = (int)std::max<long long>(1, std::min<long long>(C[t], std::max<long long>(1, n_tiles)));
     }
     std::vector<int> type_tab(2 * ntypes);
     int n_items = 0;
