@@ -36,6 +36,18 @@ GEOM = (30., 40., 1e-3, -2e-3)
 FP64_DMMA_PEAK_TFLOPS = 37.1
 
 
+def gram_traffic(n, N):
+    """DRAM bytes of one k_gram launch from the committed ncu --set full capture of this workload, else None."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_gram_traffic.json')) as fh:
+            t = json.load(fh)
+        if t['n_vis'] == n and t['N'] == N:
+            return t['dram_bytes_read'] + t['dram_bytes_write']
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -280,11 +292,12 @@ def main():
                                  'k_gram', 'k_gram_finalize'],
             'roofline': {'bound': 'tensor', 'kernel': 'k_gram (fused J0 + FP64 DMMA Gram)', 'achieved': achieved,
                          'peak': FP64_DMMA_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_DMMA_PEAK_TFLOPS,
-                         'traffic': None, 'kernel_ms': g_ms,
+                         'traffic': gram_traffic(n, N), 'traffic_unit': 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_gram_traffic.json)',
+                         'algorithmic_bytes': 4 * 24 * n, 'kernel_ms': g_ms,
                          'flop_count': 'useful FP64 flops N(N+1)+2N per visibility (upper triangle of H^T W H plus H^T W V; SURVEY 8d)',
                          'executed_dmma_tflops': executed / (g_ms * 1e-3) / 1e12,
                          'full_matrix_equivalent_tflops': (2 * N * N + 2 * N) * n / (g_ms * 1e-3) / 1e12,
-                         'j0_evaluations_per_s': 760 * n / (g_ms * 1e-3),
+                         'j0_evaluations_per_s': 760 * n / (g_ms * 1e-3) if N == 300 else None,
                          'peak_source': 'FP64 mma.sync m8n8k4 issue rate measured on this pool (profiles/r01_fp64_probe.txt); '
                                         'MEASURED_PEAKS.json has no FP64 entry'},
             'stage_ms': {'prepass_and_sort': float(np.mean(prep_ms)), 'gram': g_ms, 'finalize': float(np.mean(fin_ms)),
