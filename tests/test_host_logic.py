@@ -1,4 +1,5 @@
 """CPU-only tests of the host-side mirror: DHT tables, geometry helpers, smoothing-matrix bands, API surface."""
+import os
 import numpy as np
 import pytest
 
@@ -84,3 +85,20 @@ def test_fitter_constructor_errors():
     assert vm.check_hash([False, FF._DHT, g, 'opt_thick', None])
     assert not vm.check_hash([True, FF._DHT, g, 'opt_thick', None])
     assert not vm.check_hash([False, FF._DHT, FixedGeometry(31, 40), 'opt_thick', None])
+
+
+def test_j0_table_accuracy(tmp_path):
+    """The overlapping degree-7 J0 table of the Gram kernel (frank_b200/csrc/fb_j0_table.h), built and evaluated on
+    the host: nearest row (gather path, |t| <= 1/32) and the far neighbour (|t| up to 1/16, the worst case of the
+    one-row-per-tile path) against glibc's 80-bit j0l.  SciPy's own J0 -- what the reference calls -- is within
+    4.4e-16 (x <= 30) / 5.6e-17 (x > 30) of the exact function; the table has to stay inside that."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'j0_table_check')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(root, 'tests', 'native', 'j0_table_check.cpp')])
+    out = subprocess.check_output([exe, '6400', '3000000']).decode().split()
+    near, far = [float(v) for v in out[:4]], [float(v) for v in out[4:]]
+    # ranges: x < 5, < 30, < 200, < 6400 (N = 2000 reaches j_N = 6283)
+    # (half an ulp of the value itself is 1.1e-16 / 5.6e-17 / 2.8e-17 / 1.4e-17 at the top of these ranges)
+    assert near[0] <= 1.2e-16 and near[1] <= 7e-17 and near[2] <= 3.5e-17 and near[3] <= 1.5e-17
+    assert far[0] <= 1.3e-16 and far[1] <= 7e-17 and far[2] <= 3.5e-17 and far[3] <= 1.5e-17
