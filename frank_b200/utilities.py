@@ -1,4 +1,4 @@
-"""Data utilities on the hot path's edge: the uv-plane binner.
+"""Data utilities on the hot path's edge: the uv-plane binner and the weight estimate built on it.
 
 API mirror of frank.utilities.UVDataBinner (frank/utilities.py:180-400).  Bin indices, counts and the weighted
 sums come from the GPU (frank_b200/csrc/fb_bin.cu: bit-exact index arithmetic, stable sort by bin, fixed-order
@@ -8,7 +8,9 @@ import numpy as np
 
 from frank_b200 import _lib
 
-__all__ = ['UVDataBinner']
+import logging
+
+__all__ = ['UVDataBinner', 'estimate_weights']
 
 
 class UVDataBinner(object):
@@ -84,3 +86,68 @@ class UVDataBinner(object):
     error = property(lambda self: self._Verr, doc="Uncertainty on the binned visibilities, Jy")
     bin_counts = property(lambda self: self._count, doc="Number of points in each bin")
     bin_edges = property(lambda self: [self._uv_left, self._uv_right], doc="Edges of the histogram bins")
+
+
+def estimate_weights(u, v=None, V=None, nbins=300, log=True, use_median=False, verbose=True, device=None):
+    r"""Estimate the weights from the variance of the binned visibilities (frank/utilities.py:515-631).
+
+    Same call forms as the reference: ``estimate_weights(u, v, V)``, ``estimate_weights(u, V)``,
+    ``estimate_weights(u, V=V)``.  The binning (indices, counts, weighted sums, variance sums) runs on the GPU
+    through :class:`UVDataBinner`; the O(nbins) post-processing below follows the reference line by line.
+
+    Reference behaviour kept on purpose: the reference tests ``np.iscomplex(V.dtype)`` (utilities.py:598), which is
+    False for every dtype object, so the variance of the REAL part alone is used even for complex visibilities
+    (the docstring's "average of real and imaginary variance" branch is never taken).
+    """
+    if verbose:
+        logging.info('  Estimating visibility weights')
+
+    if V is None:                                                        # utilities.py:577-586
+        if v is not None:
+            V = v
+            q = np.abs(u)
+        else:
+            raise ValueError("The visibilities, V, must be supplied")
+    elif v is not None:
+        q = np.hypot(u, v)
+    else:
+        q = np.abs(u)
+
+    if log:                                                              # :588-590
+        q = np.log(q)
+        q -= q.min()
+
+    bin_width = (q.max() - q.min()) / nbins                              # :592
+
+    uvBin = UVDataBinner(q, V, np.ones_like(q), bin_width, device=device)
+
+    if uvBin.bin_counts.max() == 1:                                      # :596-598
+        raise ValueError("No bin contains more than one uv point, can't"
+                         " estimate the variance. Use fewer bins.")
+
+    var = uvBin.error.real ** 2 * uvBin.bin_counts                       # :600-603 (see the docstring)
+
+    if use_median:                                                       # :605-609
+        if verbose:
+            logging.info('    Setting all weights as median binned visibility '
+                         'variance')
+        return np.full(len(u), 1 / np.ma.median(var[uvBin.bin_counts > 1]))
+    else:
+        if verbose:
+            logging.info('    Setting weights according to baseline-dependent '
+                         'binned visibility variance')
+        # For bins with 1 uv point, use the average of the adjacent bins (:614-625)
+        no_var = np.argwhere(uvBin.bin_counts == 1).reshape(-1)
+        if len(no_var) > 0:
+            good_var = np.argwhere(uvBin.bin_counts > 1).reshape(-1)
+            loc = np.searchsorted(good_var, no_var, side='right')
+            im = good_var[np.maximum(loc - 1, 0)]
+            ip = good_var[np.minimum(loc, len(good_var) - 1)]
+            var[no_var] = 0.5 * (var[im] + var[ip])
+
+        bin_id = uvBin.determine_uv_bin(q)
+        assert np.all(bin_id != -1), "Error in binning"  # Should never occur
+
+        weights = 1 / var[bin_id]
+
+        return weights

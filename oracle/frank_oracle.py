@@ -560,6 +560,56 @@ def uv_bin(uv, V, weights, bin_width):
             'counts': counts, 'error': bin_err, 'mask': ~has}
 
 
+def uv_determine_bin(uv, bins, nbins, bin_width):
+    """UVDataBinner.determine_uv_bin (utilities.py:267-298): bin index, -1 beyond the last edge."""
+    norm = 1 / bin_width
+    idx = np.floor(uv * norm).astype('int32')
+    idx[uv < bins[np.clip(idx, 0, nbins)]] -= 1
+    idx[uv == bins[nbins]] -= 1
+    too_high = idx >= nbins
+    idx[too_high] = -1
+    tmp = idx[~too_high]
+    inc = (uv[~too_high] >= bins[tmp + 1]) & (tmp + 1 != nbins)
+    tmp[inc] += 1
+    idx[~too_high] = tmp
+    return idx
+
+
+def estimate_weights(u, v=None, V=None, nbins=300, log=True, use_median=False):
+    """estimate_weights (utilities.py:515-631) on top of uv_bin.  The reference's `np.iscomplex(V.dtype)`
+    (:598) is False for any dtype object, so only the variance of the real part is ever used."""
+    if V is None:
+        if v is None:
+            raise ValueError("The visibilities, V, must be supplied")
+        V = v
+        q = np.abs(u)
+    elif v is not None:
+        q = np.hypot(u, v)
+    else:
+        q = np.abs(u)
+    if log:
+        q = np.log(q)
+        q -= q.min()
+    bin_width = (q.max() - q.min()) / nbins
+    b = uv_bin(q, V, np.ones_like(q), bin_width)
+    counts = b['counts']
+    if counts.max() == 1:
+        raise ValueError("No bin contains more than one uv point, can't estimate the variance. Use fewer bins.")
+    var = b['error'].real ** 2 * counts                                  # nan where counts <= 1
+    if use_median:
+        return np.full(len(u), 1 / np.median(var[counts > 1]))
+    no_var = np.argwhere(counts == 1).reshape(-1)
+    if len(no_var) > 0:
+        good_var = np.argwhere(counts > 1).reshape(-1)
+        loc = np.searchsorted(good_var, no_var, side='right')
+        im = good_var[np.maximum(loc - 1, 0)]
+        ip = good_var[np.minimum(loc, len(good_var) - 1)]
+        var[no_var] = 0.5 * (var[im] + var[ip])
+    bin_id = uv_determine_bin(q, b['bins'], b['nbins'], bin_width)
+    assert np.all(bin_id != -1)
+    return 1 / var[bin_id]
+
+
 # --------------------------------------------------------------------------------------
 # Synthetic workload of SURVEY.md section 8(d) / BASELINE.md section 3
 # --------------------------------------------------------------------------------------

@@ -18,6 +18,8 @@ whatever the reference's public API returns for them:
   fit_lognormal.npz  FrankFitter(method='LogNormal').fit
   fit_as209sub.npz   FrankFitter on the 196-visibility AS 209 subsample, N=20
   uvbin.npz          UVDataBinner bin indices, counts, means, errors (utilities.py:180-400)
+  estweights.npz     estimate_weights in its five call forms (utilities.py:515-631)
+  geomfit.npz        FitGeometryGaussian / FitGeometryFourierBessel results (geometry.py:404-763)
   gauss_kat.npz      the reference's analytic Gaussian Hankel-pair test inputs (tests.py:37-130)
 """
 import os
@@ -34,12 +36,12 @@ warnings.filterwarnings('ignore')
 import scipy.special  # noqa: E402
 import frank  # noqa: E402
 from frank.constants import rad_to_arcsec, deg_to_rad  # noqa: E402
-from frank.geometry import FixedGeometry  # noqa: E402
+from frank.geometry import FixedGeometry, FitGeometryGaussian, FitGeometryFourierBessel  # noqa: E402
 from frank.hankel import DiscreteHankelTransform  # noqa: E402
 from frank.radial_fitters import FrankFitter, FourierBesselFitter  # noqa: E402
 from frank.debris_fitters import FrankDebrisFitter  # noqa: E402
 from frank.statistical_models import VisibilityMapping  # noqa: E402
-from frank.utilities import UVDataBinner  # noqa: E402
+from frank.utilities import UVDataBinner, estimate_weights  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 assert frank.__version__ == '1.2.3', frank.__version__
@@ -78,7 +80,59 @@ def self_noise(make_fitter, u, v, V, w, MAP, nperm=3):
     return worst
 
 
+def gen_geomfit():
+    """Geometry fitters (geometry.py:404-763) on a noisy Gaussian disc seen at inc=32, PA=47 with an offset source."""
+    rng = np.random.default_rng(777)
+    n = 3000
+    gt = FixedGeometry(32.0, 47.0, dRA=0.021, dDec=-0.034)
+    q = 1.2e6 * np.sqrt(rng.uniform(1e-4, 1, n))
+    th = rng.uniform(0, 2 * np.pi, n)
+    ud, vd = q * np.cos(th), q * np.sin(th)
+    sig = 0.25 / rad_to_arcsec
+    Vd = np.cos(32.0 * deg_to_rad) * 2 * np.pi * sig * sig * 4e10 * np.exp(-2 * np.pi ** 2 * sig * sig * q * q)
+    u, v, V = gt.undo_correction(ud, vd, Vd.astype(complex))
+    w = np.full(n, 2.5e3)
+    V = V + (rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(w)
+    gg = FitGeometryGaussian()
+    gg.fit(u, v, V, w)
+    gg2 = FitGeometryGaussian(phase_centre=(0.021, -0.034), guess=[20., 60., 0., 0.])
+    gg2.fit(u, v, V, w)
+    gf = FitGeometryFourierBessel(1.6, 20, guess=[28., 44., 0.015, -0.03])
+    gf.fit(u, v, V, w)
+    gf2 = FitGeometryFourierBessel(1.6, 20, inc_pa=(32.0, 47.0), guess=[0., 0., 0.015, -0.03])
+    gf2.fit(u, v, V, w)
+    np.savez_compressed(os.path.join(OUT, 'geomfit.npz'), u=u, v=v, V=V, w=w,
+                        gauss=np.array([gg.inc, gg.PA, gg.dRA, gg.dDec]),
+                        gauss_fixed_centre=np.array([gg2.inc, gg2.PA, gg2.dRA, gg2.dDec]),
+                        fb=np.array([gf.inc, gf.PA, gf.dRA, gf.dDec]),
+                        fb_fixed_incpa=np.array([gf2.inc, gf2.PA, gf2.dRA, gf2.dDec]))
+    print('geomfit:', gg.inc, gg.PA, gg.dRA, gg.dDec, '|', gf.inc, gf.PA, gf.dRA, gf.dDec, '|', gf2.dRA, gf2.dDec)
+
+
+def gen_estweights():
+    # ---- estimate_weights (utilities.py:515-631) on deprojected baselines ---------------------------
+    rng_w = np.random.default_rng(2024)
+    ne = 20000
+    ue = rng_w.uniform(-2e6, 2e6, ne)
+    ve = rng_w.uniform(-2e6, 2e6, ne)
+    sig = 0.02 * (1 + np.hypot(ue, ve) / 1e6)                          # baseline-dependent noise
+    Ve = np.exp(-(np.hypot(ue, ve) / 8e5) ** 2) + sig * (rng_w.standard_normal(ne) + 1j * 2 * rng_w.standard_normal(ne))
+    ew = {}
+    ew['log'] = np.ma.filled(estimate_weights(ue, ve, Ve, nbins=300, verbose=False), np.nan)
+    ew['lin'] = np.ma.filled(estimate_weights(ue, ve, Ve, nbins=300, log=False, verbose=False), np.nan)
+    ew['fine'] = np.ma.filled(estimate_weights(ue, ve, Ve, nbins=8000, verbose=False), np.nan)      # many single-count bins
+    ew['median'] = np.ma.filled(estimate_weights(ue, ve, Ve, nbins=300, use_median=True, verbose=False), np.nan)
+    ew['uV'] = np.ma.filled(estimate_weights(np.hypot(ue, ve), Ve.real, nbins=100, verbose=False), np.nan)   # (u, V) call form, real V
+    np.savez_compressed(os.path.join(OUT, 'estweights.npz'), u=ue, v=ve, V=Ve, **ew)
+
+
 def main():
+    if sys.argv[1:] == ['estweights']:           # regenerate this fixture alone
+        gen_estweights()
+        return
+    if sys.argv[1:] == ['geomfit']:
+        gen_geomfit()
+        return
     # ---- J0 -------------------------------------------------------------------------------
     rng = np.random.default_rng(7)
     x = np.concatenate([rng.uniform(0, 1e-5, 200), rng.uniform(0, 5, 3000), rng.uniform(5, 30, 3000),
@@ -208,6 +262,9 @@ def main():
                         idx=b.determine_uv_bin(uvx), uv=b.uv.filled(0), V=b.V.filled(0),
                         weights=b.weights.filled(0), counts=b.bin_counts.filled(0),
                         error=b.error.filled(np.nan), mask=np.ma.getmaskarray(b.uv))
+
+    gen_estweights()
+    gen_geomfit()
 
     # ---- analytic Gaussian pair (frank/tests.py:37-130) --------------------------------------
     def gauss_vis(q, inc):

@@ -46,3 +46,20 @@ def test_binner_large_vs_oracle():
     # deterministic
     b2 = UVDataBinner(uv, V, w, 1e3)
     assert np.array_equal(b.V.filled(0), b2.V.filled(0)) and np.array_equal(b.error.filled(0), b2.error.filled(0), equal_nan=True)
+
+
+def test_estimate_weights_vs_reference_golden(golden):
+    """estimate_weights on top of the GPU binner against the unmodified reference (tests/golden/make_golden.py):
+    bin membership is exact, so the weights agree to the round-off of the per-bin variance sums."""
+    from frank_b200.utilities import estimate_weights
+    g = golden('estweights.npz')
+    u, v, V = g['u'], g['v'], g['V']
+    for tag, kw in [('log', dict(nbins=300)), ('lin', dict(nbins=300, log=False)), ('fine', dict(nbins=8000)),
+                    ('median', dict(nbins=300, use_median=True))]:
+        got = np.ma.filled(estimate_weights(u, v, V, verbose=False, **kw), np.nan)
+        assert got.shape == g[tag].shape
+        assert np.allclose(got, g[tag], rtol=1e-11, atol=0), tag
+    got = np.ma.filled(estimate_weights(np.hypot(u, v), V.real, nbins=100, verbose=False), np.nan)
+    assert np.allclose(got, g['uV'], rtol=1e-11, atol=0)
+    with pytest.raises(ValueError):
+        estimate_weights(u)

@@ -183,3 +183,16 @@ def test_uv_binner(golden, tag):
     for name in ['uv', 'V', 'weights']:
         assert np.array_equal(b[name][ok], g[name][ok]), name
     assert np.array_equal(b['error'][ok], g['error'][ok], equal_nan=True)
+
+
+def test_estimate_weights(golden):
+    """estimate_weights (utilities.py:515-631) in its call forms, incl. the reference's real-part-only variance
+    (np.iscomplex(dtype) quirk) and the neighbour fill of single-count bins."""
+    g = golden('estweights.npz')
+    u, v, V = g['u'], g['v'], g['V']
+    for tag, kw in [('log', dict(nbins=300)), ('lin', dict(nbins=300, log=False)), ('fine', dict(nbins=8000)),
+                    ('median', dict(nbins=300, use_median=True))]:
+        got = fo.estimate_weights(u, v, V, **kw)
+        assert np.allclose(got, g[tag], rtol=1e-12, atol=0), tag
+    got = fo.estimate_weights(np.hypot(u, v), V.real, nbins=100)
+    assert np.allclose(got, g['uV'], rtol=1e-12, atol=0)
