@@ -45,8 +45,7 @@ struct GramArgs {
     const int *type_tab;  // [2 * ntypes] (chunks, first slot)
     const double *H2;
     double *partial;
-    long long *prof;      // optional [grid][2]: clocks thread 0 spent in the J0 phases / the DMMA phases
-    int debug_mode;       // 0 normal | 1 skip the DMMAs | 2 skip J0 evaluation after the first stage (profiling aid)
+    long long *prof;      // optional (FB_GRAM_PROF=1) [grid][2]: clocks thread 0 spent in the J0 / DMMA phases; results unaffected
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
@@ -331,12 +330,12 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                     // tile s staged; DMMAs of tile s - 1 done
         if (p.prof && tid == 0) { const long long t = clock64(); t_mma += t - t_last; t_last = t; }
-        if (p.debug_mode != 2 || s == 0) produce(b);
+        produce(b);
         __syncthreads();
         if (p.prof && tid == 0) { const long long t = clock64(); t_j0 += t - t_last; t_last = t; }
         if (s + 1 < nst)                                     // next tile's staging flies during the DMMAs
             stage_tile(lds_v2f64(sbase + SMB_AR + (b ^ 1) * 16), b ^ 1, q0 + s + 1, s + 2 < nst ? q0 + s + 2 : -1);
-        if (p.debug_mode != 1) stage_dmma<KIND, NR, NC>(acc, it.G, fr0, fr1, ta, tb, cbase, it.nmod);
+        stage_dmma<KIND, NR, NC>(acc, it.G, fr0, fr1, ta, tb, cbase, it.nmod);
     }
     if (p.prof && tid == 0) {
         t_mma += clock64() - t_last;
@@ -763,8 +762,6 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
     args.cta_off = ctx->d_work; args.items = ctx->d_work + grid + 1; args.type_tab = ctx->d_work + grid + 1 + 3 * (size_t)n_items;
     args.H2 = ctx->d_H2; args.partial = ctx->d_partial;
     {
-        const char *dbg = getenv("FB_GRAM_DEBUG");
-        args.debug_mode = dbg ? atoi(dbg) : 0;
         args.prof = nullptr;
         if (getenv("FB_GRAM_PROF")) {
             FB_CUDA(cudaMalloc(&args.prof, sizeof(long long) * 2 * grid));
