@@ -102,12 +102,13 @@ constexpr int GKS = GS / 4;            // k-steps per tile
 constexpr int GCOLS = FB_GCOLS;        // columns held per stage (rows' columns | columns' columns)
 constexpr int NW = FB_GRAM_THREADS / 32;
 constexpr int ROWB = FB_J0_ROWLEN * 8; // bytes per table row (64)
+static_assert(FB_GRAM_THREADS == 2 * FB_GCOLS && FB_J0_ROWLEN == 8, "staging assigns thread 256 + c to column c and four threads to a row");
 
 // shared-memory carve-up (bytes)
 constexpr int SMB_G = 0;                                   // [GCOLS][GLD] doubles      design-matrix tile
 constexpr int SMB_ROW = SMB_G + GCOLS * GLD * 8;           // [2][4][GCOLS] double2     staged J0 table rows (coefficient pair major)
-constexpr int SMB_CEN = SMB_ROW + 2 * GCOLS * ROWB;        // [2][GCOLS] double2        (centre of the staged row, 1 row serves the tile | 0 gather | -1 special column)
-constexpr int SMB_JK = SMB_CEN + 2 * GCOLS * 16;           // [GCOLS] doubles           j_k (0 for the data column and the padding)
+constexpr int SMB_CEN = SMB_ROW + 2 * GCOLS * ROWB;        // [2][GCOLS] double2        (centre of the staged row, +j_k row serves the tile | -j_k gather | -0 special column)
+constexpr int SMB_JK = SMB_CEN + 2 * GCOLS * 16;           // [GCOLS] ints (+ pad)      table row chosen for the tile being staged
 constexpr int SMB_H2 = SMB_JK + GCOLS * 8;                 // [GCOLS] doubles           debris H2_k
 constexpr int SMB_VIS = SMB_H2 + GCOLS * 8;                // [2][GS][4] doubles        (a, sqrt w, kz, sqrt w Re V) per visibility of a tile
 constexpr int SMB_AR = SMB_VIS + 2 * GS * 32;               // [2] double2               (min a, max a) of the tiles being staged
@@ -166,14 +167,13 @@ __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sba
     }
     uint32_t a_row = sbase + SMB_ROW + buf * (GCOLS * ROWB) + warp * 16;
     uint32_t a_cen = sbase + SMB_CEN + (buf * GCOLS + warp) * 16;
-    uint32_t a_jk = sbase + SMB_JK + warp * 8;
     uint32_t a_g = sbase + SMB_G + (warp * GLD + lane) * 8;
 #pragma unroll 1
     for (int sc = warp; sc < ncol; sc += NW) {
-        const double jk = lds_f64(a_jk);                             // j_k (0 for the data column and the padding)
-        const double2 cv = lds_v2f64(a_cen);                         // (centre, 1 row serves the tile | 0 gather | -1 no store)
+        const double2 cv = lds_v2f64(a_cen);                         // (centre, +j_k | -j_k: gather | -0: no store)
         const double2 c67 = lds_v2f64(a_row + 3 * GCOLS * 16), c45 = lds_v2f64(a_row + 2 * GCOLS * 16),
                       c23 = lds_v2f64(a_row + GCOLS * 16), c01 = lds_v2f64(a_row);
+        const double jk = fabs(cv.y);
         const double x0 = __dmul_rn(aw0.x, jk), x1 = __dmul_rn(aw1.x, jk);      // a * j_k as the reference rounds it
         const double u0 = __dsub_rn(x0, cv.x), u1 = __dsub_rn(x1, cv.x);        // exact
         double g0 = fma(c67.y, u0, c67.x), g1 = fma(c67.y, u1, c67.x);
@@ -183,21 +183,22 @@ __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sba
         g0 = fma(g0, u0, c23.x); g1 = fma(g1, u1, c23.x);
         g0 = fma(g0, u0, c01.y); g1 = fma(g1, u1, c01.y);
         g0 = fma(g0, u0, c01.x); g1 = fma(g1, u1, c01.x);
-        const int flag = __double2hiint(cv.y);                       // 0x3ff00000 | 0 | 0xbff00000
-        if (flag == 0) {                                             // warp-uniform, rare
+        bool store = __double2hiint(cv.y) >= 0;
+        if (!store && cv.y != 0.0) {                                 // warp-uniform, rare: one row does not serve the tile
             g0 = j0_tab(x0, p.tab, last_row);
             g1 = j0_tab(x1, p.tab, last_row);
+            store = true;
         }
         if (DEBRIS) {
             const double h2 = lds_f64(sbase + SMB_H2 + sc * 8);
             g0 *= exp_neg(k0 * h2);
             g1 *= exp_neg(k1 * h2);
         }
-        if (flag >= 0) {                                             // the data column and the padding are written elsewhere
+        if (store) {                                                 // the data column and the padding are written elsewhere
             sts_f64(a_g, g0 * aw0.y);
             sts_f64(a_g + 32 * 8, g1 * aw1.y);
         }
-        a_row += NW * 16; a_cen += NW * 16; a_jk += NW * 8; a_g += NW * GLD * 8;
+        a_row += NW * 16; a_cen += NW * 16; a_g += NW * GLD * 8;
     }
 }
 
@@ -212,7 +213,7 @@ struct ItemCtx {
     int nst;
     int ld;
     double *out;
-    double my_jk;          // column code of column tid (tid < ncol): row-staging duty of this thread
+    double my_jk;          // column code (j_k | -1 data column | -2 padding) of column tid - 256: staging duty of this thread
     int dcol;              // local index of the data column in this block, -1 if absent
 };
 
@@ -269,35 +270,37 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
     const int cbase = KIND == FB_KIND_OFF ? 0 : (it.r0 + it.c0) % it.nmod;
     const uint32_t sbase = it.sbase;
 
-    // stage_tile(ar, buf, q, q2): everything the J0 phase of tile q needs, fetched with cp.async (no registers held):
-    //   * per column, the table row that serves arguments [ar.x j_k, ar.y j_k] (lane <-> column for the arithmetic, then
-    //     four lanes copy the four 16-byte pieces of a row, so that a warp-wide copy touches 8 rows, not 32), its
-    //     centre and whether that one row covers the whole tile;
-    //   * the per-visibility scalars (a, sqrt w, kz, sqrt w Re V) of tile q;
-    //   * the range (min a, max a) of tile q2 (used by the next call).
-    auto stage_tile = [&](const double2 ar, const int buf, const long long q, const long long q2) {
-        const int w = tid >> 5;
-        if (w * 32 < it.ncol) {                              // warp-uniform
+    // Staging of everything the J0 phase of a tile needs, in two parts.
+    // stage_math(ar, buf) -- threads 256.. (the warps with one column less in the J0 phase), one column each: the table
+    //   row that serves arguments [ar.x j_k, ar.y j_k], its centre, and whether that one row covers the whole tile.
+    // stage_copy(buf, q, q2) -- all threads, cp.async only (no registers held, nothing for the FP64 pipe, so it can fly
+    //   during the DMMAs): four lanes copy the four 16-byte pieces of a row, so that a warp-wide copy touches 8 rows,
+    //   not 32; the per-visibility scalars (a, sqrt w, kz, sqrt w Re V) of tile q; the range (min a, max a) of tile q2.
+    auto stage_math = [&](const double2 ar, const int buf) {
+        const int col = tid - 256;
+        if (col >= 0 && col < it.ncol) {
             int m = 0;
+            double cen = 0.0, jks = -0.0;
             if (it.my_jk >= 0.0) {
                 const double xlo = __dmul_rn(ar.x, it.my_jk), xhi = __dmul_rn(ar.y, it.my_jk);
                 m = min(__double2loint(fma(xlo + xhi, 0.5 * FB_J0_INVH, J0_MAGIC)), last_row);
-                const double cen = (double)m * FB_J0_H;
-                const double valid = (fabs(xlo - cen) < FB_J0_ACCEPT && fabs(xhi - cen) < FB_J0_ACCEPT) ? 1.0 : 0.0;
-                sts_v2f64(sbase + SMB_CEN + (buf * GCOLS + tid) * 16, cen, valid);
-            } else if (tid < it.ncol) {
-                sts_v2f64(sbase + SMB_CEN + (buf * GCOLS + tid) * 16, 0.0, -1.0);
+                cen = (double)m * FB_J0_H;
+                jks = (fabs(xlo - cen) < FB_J0_ACCEPT && fabs(xhi - cen) < FB_J0_ACCEPT) ? it.my_jk : -it.my_jk;
             }
+            sts_v2f64(sbase + SMB_CEN + (buf * GCOLS + col) * 16, cen, jks);
+            asm volatile("st.shared.s32 [%0], %1;" ::"r"(sbase + SMB_JK + col * 4), "r"(m) : "memory");
+        }
+    };
+    auto stage_copy = [&](const int buf, const long long q, const long long q2) {
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int src_lane = 8 * r + (lane >> 2);
-                const int mm = __shfl_sync(0xffffffffu, m, src_lane);
-                const int col = w * 32 + src_lane;
-                if (col < it.ncol) {
-                    const double2 *src = p.tab + (size_t)mm * (FB_J0_ROWLEN / 2) + (lane & 3);
-                    const uint32_t dst = sbase + SMB_ROW + buf * (GCOLS * ROWB) + (lane & 3) * (GCOLS * 16) + col * 16;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                }
+        for (int h = 0; h < 2; h++) {
+            const int col = (tid >> 2) + 128 * h, piece = tid & 3;
+            if (col < it.ncol) {
+                int m;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(m) : "r"(sbase + SMB_JK + col * 4));
+                const double2 *src = p.tab + (size_t)m * (FB_J0_ROWLEN / 2) + piece;
+                const uint32_t dst = sbase + SMB_ROW + buf * (GCOLS * ROWB) + piece * (GCOLS * 16) + col * 16;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
             }
         }
         if (tid < GS) {
@@ -314,15 +317,19 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
     };
     // J0 phase of this warp
     auto produce = [&](const int buf) {
-        if (it.dcol >= 0 && tid < GS)        // data column: G[N][v] = sqrt(w_v) Re V_v
-            sts_f64(sbase + SMB_G + (it.dcol * GLD + tid) * 8, lds_f64(sbase + SMB_VIS + buf * (GS * 32) + tid * 32 + 24));
+        if (it.dcol >= 0 && tid >= FB_GRAM_THREADS - GS) {       // data column: G[N][v] = sqrt(w_v) Re V_v
+            const int vv = tid - (FB_GRAM_THREADS - GS);
+            sts_f64(sbase + SMB_G + (it.dcol * GLD + vv) * 8, lds_f64(sbase + SMB_VIS + buf * (GS * 32) + vv * 32 + 24));
+        }
         j0_columns<DEBRIS>(p, sbase, buf, it.ncol, tid >> 5, lane, last_row);
     };
 
     const long long q0 = it.q0;
     const int nst = it.nst;
     // ---- prologue: rows and scalars of the first tile, range of the second --------------------------------------
-    stage_tile(p.arange[q0], 0, q0, nst > 1 ? q0 + 1 : -1);
+    stage_math(p.arange[q0], 0);
+    __syncthreads();
+    stage_copy(0, q0, nst > 1 ? q0 + 1 : -1);
     // ---- main loop: J0 phase, DMMA phase ------------------------------------------------------------------------
     long long t_j0 = 0, t_mma = 0, t_last = clock64();
     for (int s = 0; s < nst; s++) {
@@ -331,10 +338,10 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
         __syncthreads();                                     // tile s staged; DMMAs of tile s - 1 done
         if (p.prof && tid == 0) { const long long t = clock64(); t_mma += t - t_last; t_last = t; }
         produce(b);
+        if (s + 1 < nst) stage_math(lds_v2f64(sbase + SMB_AR + (b ^ 1) * 16), b ^ 1);
         __syncthreads();
         if (p.prof && tid == 0) { const long long t = clock64(); t_j0 += t - t_last; t_last = t; }
-        if (s + 1 < nst)                                     // next tile's staging flies during the DMMAs
-            stage_tile(lds_v2f64(sbase + SMB_AR + (b ^ 1) * 16), b ^ 1, q0 + s + 1, s + 2 < nst ? q0 + s + 2 : -1);
+        if (s + 1 < nst) stage_copy(b ^ 1, q0 + s + 1, s + 2 < nst ? q0 + s + 2 : -1);     // flies during the DMMAs
         stage_dmma<KIND, NR, NC>(acc, it.G, fr0, fr1, ta, tb, cbase, it.nmod);
     }
     if (p.prof && tid == 0) {
@@ -391,18 +398,21 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
         // column tables of this block
         __syncthreads();                      // every warp is done with the previous item
         it.my_jk = -2.0;
-        if (tid < GCOLS) {
+        {
+            const int col = tid < GCOLS ? tid : tid - GCOLS;          // both halves of the CTA look at column code `col`
             double v = -2.0, h = 0.0;
-            if (tid < it.ncol) {
-                const int g = tid < it.ncolA ? ty.a_t0 * 8 + tid : ty.b_t0 * 8 + (tid - it.ncolA);
+            if (col < it.ncol) {
+                const int g = col < it.ncolA ? ty.a_t0 * 8 + col : ty.b_t0 * 8 + (col - it.ncolA);
                 if (g < p.N) { v = p.jk[g]; if (DEBRIS) h = p.H2[g]; }
                 else if (g == p.N) v = -1.0;
             }
-            it.my_jk = v;
-            sts_f64(sbase + SMB_JK + tid * 8, v >= 0.0 ? v : 0.0);
-            if (DEBRIS) sts_f64(sbase + SMB_H2 + tid * 8, h);
-            if (v == -2.0 && tid < it.ncol) {            // zero padding columns stay zero for the whole item
-                for (int x = 0; x < GS; x++) sts_f64(sbase + SMB_G + (tid * GLD + x) * 8, 0.0);
+            if (tid >= GCOLS) {
+                it.my_jk = v;                                          // staging duty (stage_math)
+            } else {
+                if (DEBRIS) sts_f64(sbase + SMB_H2 + col * 8, h);
+                if (v == -2.0 && col < it.ncol) {                      // zero padding columns stay zero for the whole item
+                    for (int x = 0; x < GS; x++) sts_f64(sbase + SMB_G + (col * GLD + x) * 8, 0.0);
+                }
             }
         }
         {
