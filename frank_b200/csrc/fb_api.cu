@@ -38,7 +38,7 @@ int fb_ctx_destroy(fb_ctx *ctx)
                     (void *)ctx->d_tile_panel, (void *)ctx->d_panel_t0, (void *)ctx->d_panel_nt, (void *)ctx->d_pair_code,
                     (void *)ctx->d_a, (void *)ctx->d_sw, (void *)ctx->d_swV, (void *)ctx->d_kz, (void *)ctx->d_amid, (void *)ctx->d_red,
                     (void *)ctx->d_partial, (void *)ctx->d_H2, (void *)ctx->d_in, (void *)ctx->d_out,
-                    (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist, (void *)ctx->d_work,
+                    (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist, (void *)ctx->d_work, (void *)ctx->d_work2,
                     (void *)ctx->sv_D, (void *)ctx->sv_p, (void *)ctx->sv_mu, (void *)ctx->sv_tr2, (void *)ctx->sv_alpha,
                     (void *)ctx->sv_p0, (void *)ctx->sv_Tinv, (void *)ctx->sv_M, (void *)ctx->sv_j, (void *)ctx->sv_Z,
                     (void *)ctx->sv_flags, (void *)ctx->sv_rdiag, (void *)ctx->ln_S, (void *)ctx->ln_vec})
@@ -95,14 +95,39 @@ int fb_dht_setup(fb_ctx *ctx, int N, double Qmax, const double *host_j_nk, const
     return fb_build_j0_table(ctx, x_max);
 }
 
-static int map_dev_impl(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
-                        int w_stride, const int32_t *chan, int nchan, const fb_geometry *geom, int vis_model,
-                        double model_scale, const double *host_H2, int check_qbounds, double q_last, double *dev_M,
-                        double *dev_j, double *dev_H0, double *host_qminmax)
+// One part of a mapping call: pre-pass + sort + Gram kernel over n visibilities already on the device.
+// Accumulates H0 and the range of q on the host (fixed order over the parts -> deterministic).
+static int map_part(fb_ctx *ctx, int part, int nparts, int64_t n, const double *u, const double *v, const double *V,
+                    const double *w, int w_stride, const fb_geometry *geom, int vis_model, int check_qbounds, double q_last,
+                    double *host_H0, double *host_qminmax)
 {
-    if (!ctx) return -1;
+    double qmm[2], h0 = 0.0;
+    int rc = fb_launch_prep(ctx, n, u, v, V, w, w_stride, geom, nullptr, qmm, &h0);
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(part == 0 ? ctx->ev[1] : ctx->pev[0], ctx->stream));
+    if (part == 0) { *host_H0 = h0; host_qminmax[0] = qmm[0]; host_qminmax[1] = qmm[1]; }
+    else {
+        *host_H0 += h0;
+        if (n > 0) { host_qminmax[0] = fmin(host_qminmax[0], qmm[0]); host_qminmax[1] = fmax(host_qminmax[1], qmm[1]); }
+    }
+    if (n > 0) {
+        // statistical_models.py:526: raise when the last collocation point is inside the data
+        if (check_qbounds && q_last < qmm[1]) FB_FAIL(FB_E_QRANGE, "last collocation point is at a shorter baseline than the longest deprojected baseline");
+        // make sure the J0 table reaches the largest argument a_max * j_{N-1}
+        const double xneed = qmm[1] * ctx->invQmax * ctx->h_jk[ctx->N - 1];
+        if (fb_j0_rows_for(xneed) > ctx->tab_rows) {
+            rc = fb_build_j0_table(ctx, xneed * 1.05);
+            if (rc) return rc;
+        }
+    }
+    return fb_launch_gram_part(ctx, part, nparts, n, vis_model);
+}
+
+static int map_check_args(fb_ctx *ctx, int64_t n, const fb_geometry *geom, const void *M, const void *j, const void *H0,
+                          const double *host_qminmax, const int32_t *chan, int nchan, int vis_model, const double *host_H2)
+{
     if (ctx->N == 0) FB_FAIL(-11, "fb_map_visibilities: fb_dht_setup has not been called");
-    if (n < 0 || !geom || !dev_M || !dev_j || !dev_H0 || !host_qminmax) FB_FAIL(-12, "fb_map_visibilities: bad arguments");
+    if (n < 0 || !geom || !M || !j || !H0 || !host_qminmax) FB_FAIL(-12, "fb_map_visibilities: bad arguments");
     if (nchan != 1 || chan != nullptr) FB_FAIL(-13, "fb_map_visibilities: multi-channel input must be split by the caller");
     if (vis_model < 0 || vis_model > 2) FB_FAIL(-14, "fb_map_visibilities: vis_model must be 0, 1 or 2");
     if (vis_model == FB_MODEL_DEBRIS) {
@@ -112,29 +137,8 @@ static int map_dev_impl(fb_ctx *ctx, int64_t n, const double *u, const double *v
         FB_CUDA(cudaMemcpyAsync(ctx->d_H2, h2.data(), sizeof(double) * ctx->NC, cudaMemcpyHostToDevice, ctx->stream));
         FB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    FB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    int rc = fb_launch_prep(ctx, n, u, v, V, w, w_stride, geom, dev_H0, host_qminmax);
-    if (rc) return rc;
-    FB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (n > 0) {
-        // statistical_models.py:526: raise when the last collocation point is inside the data
-        if (check_qbounds && q_last < host_qminmax[1]) FB_FAIL(FB_E_QRANGE, "last collocation point is at a shorter baseline than the longest deprojected baseline");
-        // make sure the J0 table reaches the largest argument a_max * j_{N-1}
-        const double xneed = host_qminmax[1] * ctx->invQmax * ctx->h_jk[ctx->N - 1];
-        if (fb_j0_rows_for(xneed) > ctx->tab_rows) {
-            rc = fb_build_j0_table(ctx, xneed * 1.05);
-            if (rc) return rc;
-        }
-    }
-    rc = fb_launch_gram(ctx, n, vis_model, model_scale, dev_M, dev_j);
-    if (rc) return rc;
-    FB_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
-    FB_CUDA(cudaStreamSynchronize(ctx->stream));
-    float t01 = 0, t12 = 0, t23 = 0;
-    cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[3]);
-    ctx->timing[0] = t01; ctx->timing[1] = t12; ctx->timing[2] = t23; ctx->timing[3] = 0;
+    if (!ctx->pev[0])
+        for (auto &e : ctx->pev) FB_CUDA(cudaEventCreate(&e));
     return 0;
 }
 
@@ -145,9 +149,30 @@ int fb_map_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const d
 {
     if (!ctx) return -1;
     FB_CUDA(cudaSetDevice(ctx->device));
-    return map_dev_impl(ctx, n, dev_u, dev_v, dev_V_reim, dev_w, w_stride, dev_chan, nchan, geom, vis_model, model_scale,
-                        host_H2, check_qbounds, q_last, dev_M, dev_j, dev_H0, host_qminmax);
+    int rc = map_check_args(ctx, n, geom, dev_M, dev_j, dev_H0, host_qminmax, dev_chan, nchan, vis_model, host_H2);
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    double h0 = 0.0;
+    rc = map_part(ctx, 0, 1, n, dev_u, dev_v, dev_V_reim, dev_w, w_stride, geom, vis_model, check_qbounds, q_last, &h0, host_qminmax);
+    if (rc) return rc;
+    rc = fb_launch_gram_finalize(ctx, 1, model_scale, dev_M, dev_j);
+    if (rc) return rc;
+    FB_CUDA(cudaMemcpyAsync(dev_H0, &h0, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float t01 = 0, t12 = 0, t23 = 0;
+    cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[3]);
+    ctx->timing[0] = t01; ctx->timing[1] = t12; ctx->timing[2] = t23; ctx->timing[3] = 0;
+    return 0;
 }
+
+// Host entry point.  From FB_SPLIT_MIN visibilities on, the call runs as two halves so that the host-to-device
+// copy of the second half (on a second stream) overlaps the kernels of the first; the partial blocks of both halves
+// are summed in a fixed order, so the result is deterministic (it differs from the one-pass result of the device
+// entry point in the last bits, like any other change of the summation order).
+constexpr int64_t FB_SPLIT_MIN = 4000000;
 
 int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const double *host_v, const double *host_V_reim,
                              const double *host_w, int w_stride, const int32_t *host_chan, int nchan, const fb_geometry *geom,
@@ -155,9 +180,9 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
                              double *host_M, double *host_j, double *host_H0, double *host_qminmax)
 {
     if (!ctx) return -1;
-    if (ctx->N == 0) FB_FAIL(-11, "fb_map_visibilities: fb_dht_setup has not been called");
-    if (host_chan != nullptr || nchan != 1) FB_FAIL(-13, "fb_map_visibilities: multi-channel input must be split by the caller");
     FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = map_check_args(ctx, n, geom, host_M, host_j, host_H0, host_qminmax, host_chan, nchan, vis_model, host_H2);
+    if (rc) return rc;
     const int64_t nw = w_stride ? n : 1;
     const int64_t need = 4 * n + nw + 8;
     if (need > ctx->in_cap) {
@@ -173,27 +198,56 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
         FB_CUDA(cudaMalloc(&ctx->d_out, sizeof(double) * nout));
         ctx->out_cap = nout;
     }
+    if (!ctx->stream2) FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     double *du = ctx->d_in, *dv = du + n, *dV = dv + n, *dw = dV + 2 * n;
+    const int nparts = n >= FB_SPLIT_MIN ? 2 : 1;
+    const int64_t n0 = nparts == 2 ? (n / 2) / FB_TV * FB_TV : n, n1 = n - n0;
+    auto copy_part = [&](int64_t off, int64_t cnt, cudaStream_t st) -> int {
+        FB_CUDA(cudaMemcpyAsync(du + off, host_u + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+        FB_CUDA(cudaMemcpyAsync(dv + off, host_v + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+        FB_CUDA(cudaMemcpyAsync(dV + 2 * off, host_V_reim + 2 * off, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, st));
+        if (w_stride) FB_CUDA(cudaMemcpyAsync(dw + off, host_w + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
     FB_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
-    FB_CUDA(cudaMemcpyAsync(du, host_u, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    FB_CUDA(cudaMemcpyAsync(dv, host_v, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    FB_CUDA(cudaMemcpyAsync(dV, host_V_reim, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
-    FB_CUDA(cudaMemcpyAsync(dw, host_w, sizeof(double) * nw, cudaMemcpyHostToDevice, ctx->stream));
+    if (!w_stride) FB_CUDA(cudaMemcpyAsync(dw, host_w, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = copy_part(0, n0, ctx->stream);
+    if (rc) return rc;
     FB_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+    if (nparts == 2) {
+        FB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev[4], 0));           // not before this call's start (buffer reuse)
+        rc = copy_part(n0, n1, ctx->stream2);
+        if (rc) return rc;
+        FB_CUDA(cudaEventRecord(ctx->pev[3], ctx->stream2));
+    }
+    FB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     double *dM = ctx->d_out, *dj = dM + N * N, *dH0 = dj + N;
-    int rc = map_dev_impl(ctx, n, du, dv, dV, dw, w_stride, nullptr, 1, geom, vis_model, model_scale, host_H2, check_qbounds,
-                          q_last, dM, dj, dH0, host_qminmax);
+    double h0 = 0.0;
+    rc = map_part(ctx, 0, nparts, n0, du, dv, dV, dw, w_stride, geom, vis_model, check_qbounds, q_last, &h0, host_qminmax);
+    if (rc) { if (nparts == 2) cudaStreamSynchronize(ctx->stream2); return rc; }
+    if (nparts == 2) {
+        FB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pev[3], 0));
+        rc = map_part(ctx, 1, 2, n1, du + n0, dv + n0, dV + 2 * n0, w_stride ? dw + n0 : dw, w_stride, geom, vis_model,
+                      check_qbounds, q_last, &h0, host_qminmax);
+        if (rc) return rc;
+    }
+    rc = fb_launch_gram_finalize(ctx, nparts, model_scale, dM, dj);
     if (rc) return rc;
     FB_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
     FB_CUDA(cudaMemcpyAsync(host_M, dM, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(host_j, dj, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
-    FB_CUDA(cudaMemcpyAsync(host_H0, dH0, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FB_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
-    float h2d = 0, d2h = 0;
+    *host_H0 = h0;
+    (void)dH0;
+    float h2d = 0, d2h = 0, t01 = 0, t12 = 0, t23 = 0, p12 = 0;
     cudaEventElapsedTime(&h2d, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&d2h, ctx->ev[6], ctx->ev[7]);
-    ctx->timing[3] = h2d + d2h;
+    cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[6]);
+    if (nparts == 2) cudaEventElapsedTime(&p12, ctx->pev[1], ctx->pev[2]);
+    ctx->timing[0] = t01; ctx->timing[1] = t12 + p12; ctx->timing[2] = t23 - p12; ctx->timing[3] = h2d + d2h;
     return 0;
 }
 

@@ -56,6 +56,14 @@ struct fb_ctx {
     FbGramType *d_types = nullptr;
     int *d_tile_panel = nullptr, *d_panel_t0 = nullptr, *d_panel_nt = nullptr;
     int *d_pair_code = nullptr;    // [P * P * 3]: (first OFF type, second OFF type | -1, rows in the first) ; DIAG type on the diagonal
+    // a mapping call may run as two parts (host entry point: the copy of the second half overlaps the first half's
+    // kernels); each part has its own work tables and its own range of partial slots
+    int *d_work2 = nullptr;
+    int work2_cap = 0;
+    long long part_tiles[2] = {0, 0};
+    const int *part_typetab[2] = {nullptr, nullptr};
+    int part_slot0[2] = {0, 0};
+    cudaEvent_t pev[4] = {};
     int *d_work = nullptr;         // per launch: per-CTA item ranges, items (type, chunk, partial slot), per type (chunks, first slot)
     int work_cap = 0;
     // workspaces
@@ -116,8 +124,9 @@ struct fb_ctx {
 
 // kernels / launchers implemented in the .cu files
 int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
-                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax);
-int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, double *dev_M, double *dev_j);
+                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax, double *host_H0);
+int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_model);
+int fb_launch_gram_finalize(fb_ctx *ctx, int nparts, double model_scale, double *dev_M, double *dev_j);
 int fb_build_j0_table(fb_ctx *ctx, double x_max);
 int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max);
 int fb_build_gram_plan(fb_ctx *ctx);

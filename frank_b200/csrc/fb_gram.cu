@@ -449,10 +449,11 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
 
 // Sum the chunk partials in a fixed order, scale, mirror.  One 64-thread block per upper tile pair.
 __global__ void __launch_bounds__(64)
-k_gram_finalize(int N, int NT, int P, long long n_tiles, const int *__restrict__ tile_panel,
+k_gram_finalize(int N, int NT, int P, int nparts, long long n_tiles0, long long n_tiles1, const int *__restrict__ tile_panel,
                 const int *__restrict__ panel_t0, const int *__restrict__ panel_nt, const int *__restrict__ pair_code,
-                const FbGramType *__restrict__ types, const int *__restrict__ type_tab, const double *__restrict__ partial,
-                const double *__restrict__ ck, double scale, double *__restrict__ M, double *__restrict__ jvec)
+                const FbGramType *__restrict__ types, const int *__restrict__ type_tab0, const int *__restrict__ type_tab1,
+                int slot0_1, const double *__restrict__ partial, const double *__restrict__ ck, double scale,
+                double *__restrict__ M, double *__restrict__ jvec)
 {
     // decode the upper-triangular tile pair (tr <= tc) from blockIdx.x
     int rem = blockIdx.x, tr = 0;
@@ -480,11 +481,15 @@ k_gram_finalize(int N, int NT, int P, long long n_tiles, const int *__restrict__
         else   // stored as the transposed tile (row tile lc, offset n - d)
             idx = (lc * D + (n - d)) * 64 + e_transp;
     }
-    const int Ct = type_tab[2 * type], first = type_tab[2 * type + 1];
     double s = 0.0;
-    for (int c = 0; c < Ct; c++) {
-        const long long q0 = (n_tiles * c) / Ct, q1 = (n_tiles * (c + 1)) / Ct;
-        if (q1 > q0) s += partial[(size_t)(first + c) * FB_PSZ + idx];
+    for (int part = 0; part < nparts; part++) {               // fixed order: part 0's chunks, then part 1's
+        const int *type_tab = part == 0 ? type_tab0 : type_tab1;
+        const long long n_tiles = part == 0 ? n_tiles0 : n_tiles1;
+        const int Ct = type_tab[2 * type], first = type_tab[2 * type + 1] + (part == 0 ? 0 : slot0_1);
+        for (int c = 0; c < Ct; c++) {
+            const long long q0 = (n_tiles * c) / Ct, q1 = (n_tiles * (c + 1)) / Ct;
+            if (q1 > q0) s += partial[(size_t)(first + c) * FB_PSZ + idx];
+        }
     }
     if (col < N) {           // row <= col < N
         const double val = ((ck[row] * scale) * (ck[col] * scale)) * s;
@@ -552,6 +557,7 @@ int fb_build_j0_table(fb_ctx *ctx, double x_max)
 {
     std::vector<double> tab;
     fb_j0_build(x_max, tab);
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));          // a kernel of an earlier part may still read the old table
     if (ctx->d_tab) FB_CUDA(cudaFree(ctx->d_tab));
     ctx->d_tab = nullptr;
     FB_CUDA(cudaMalloc(&ctx->d_tab, tab.size() * sizeof(double)));
@@ -675,7 +681,8 @@ int fb_build_gram_plan(fb_ctx *ctx)
     return 0;
 }
 
-int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, double *dev_M, double *dev_j)
+// Plan and launch k_gram over the currently sorted visibilities as part `part` of `nparts` (1 or 2) of a mapping call.
+int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_model)
 {
     const long long n_tiles = (n + FB_TV - 1) / FB_TV;
     const int ntypes = ctx->ntypes;
@@ -746,22 +753,35 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
         work[grid] = pos;
         std::copy(type_tab.begin(), type_tab.end(), work.begin() + grid + 1 + 3 * (size_t)n_items);
     }
-    if ((int)work.size() > ctx->work_cap) {
-        if (ctx->d_work) FB_CUDA(cudaFree(ctx->d_work));
-        ctx->d_work = nullptr;
-        FB_CUDA(cudaMalloc(&ctx->d_work, sizeof(int) * (work.size() + 1024)));
-        ctx->work_cap = (int)work.size() + 1024;
+    int *&d_work = part == 0 ? ctx->d_work : ctx->d_work2;
+    int &work_cap = part == 0 ? ctx->work_cap : ctx->work2_cap;
+    if ((int)work.size() > work_cap) {
+        if (d_work) FB_CUDA(cudaFree(d_work));
+        d_work = nullptr;
+        FB_CUDA(cudaMalloc(&d_work, sizeof(int) * (work.size() + 1024)));
+        work_cap = (int)work.size() + 1024;
     }
-    FB_CUDA(cudaMemcpyAsync(ctx->d_work, work.data(), sizeof(int) * work.size(), cudaMemcpyHostToDevice, ctx->stream));
+    // (this synchronisation also orders the table rewrite after the previous part's kernel)
+    FB_CUDA(cudaMemcpyAsync(d_work, work.data(), sizeof(int) * work.size(), cudaMemcpyHostToDevice, ctx->stream));
     FB_CUDA(cudaStreamSynchronize(ctx->stream));     // `work` is a stack object
-    const size_t need = (size_t)n_items * FB_PSZ;
-    if (need > ctx->partial_cap) {
-        if (ctx->d_partial) FB_CUDA(cudaFree(ctx->d_partial));
-        ctx->d_partial = nullptr;
-        FB_CUDA(cudaMalloc(&ctx->d_partial, need * sizeof(double)));
-        ctx->partial_cap = need;
+    // partial slots: part 1 follows part 0; room for every part is reserved by part 0 (no reallocation under a
+    // running kernel: the item count does not depend on the part's size unless it is tiny)
+    if (part == 0) {
+        const size_t need = (size_t)n_items * nparts * FB_PSZ + (nparts > 1 ? (size_t)ctx->num_sms * FB_PSZ : 0);
+        if (need > ctx->partial_cap) {
+            if (ctx->d_partial) FB_CUDA(cudaFree(ctx->d_partial));
+            ctx->d_partial = nullptr;
+            FB_CUDA(cudaMalloc(&ctx->d_partial, need * sizeof(double)));
+            ctx->partial_cap = need;
+        }
+        ctx->part_slot0[0] = 0;
+        ctx->part_slot0[1] = n_items;
+    } else if ((size_t)(ctx->part_slot0[1] + n_items) * FB_PSZ > ctx->partial_cap) {
+        FB_FAIL(-18, "fb_map_visibilities: partial buffer too small for the second part");
     }
-    FB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->part_tiles[part] = n_tiles;
+    ctx->part_typetab[part] = d_work + grid + 1 + 3 * (size_t)n_items;
+    FB_CUDA(cudaEventRecord(part == 0 ? ctx->ev[1] : ctx->pev[1], ctx->stream));
 
     GramArgs args;
     args.a = ctx->d_a; args.sw = ctx->d_sw; args.swV = ctx->d_swV; args.kz = ctx->d_kz; args.arange = (const double2 *)ctx->d_amid;
@@ -769,8 +789,8 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
     args.jk = ctx->d_jk; args.tab = ctx->d_tab; args.tab_rows = ctx->tab_rows;
     args.N = ctx->N;
     args.types = ctx->d_types;
-    args.cta_off = ctx->d_work; args.items = ctx->d_work + grid + 1; args.type_tab = ctx->d_work + grid + 1 + 3 * (size_t)n_items;
-    args.H2 = ctx->d_H2; args.partial = ctx->d_partial;
+    args.cta_off = d_work; args.items = d_work + grid + 1; args.type_tab = d_work + grid + 1 + 3 * (size_t)n_items;
+    args.H2 = ctx->d_H2; args.partial = ctx->d_partial + (size_t)ctx->part_slot0[part] * FB_PSZ;
     {
         args.prof = nullptr;
         if (getenv("FB_GRAM_PROF")) {
@@ -788,7 +808,7 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
         }
         FB_CUDA(cudaGetLastError());
     }
-    FB_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    FB_CUDA(cudaEventRecord(part == 0 ? ctx->ev[2] : ctx->pev[2], ctx->stream));
     if (args.prof) {
         std::vector<long long> h(2 * grid);
         FB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -804,10 +824,17 @@ int fb_launch_gram(fb_ctx *ctx, int64_t n, int vis_model, double model_scale, do
                 n_tiles, (double)j0_sum / grid, j0_max, (double)mma_sum / grid, mma_max, tot_min, tot_max);
         cudaFree(args.prof);
     }
+    return 0;
+}
+
+// Sum the partial blocks of all parts in a fixed order -> M, j.
+int fb_launch_gram_finalize(fb_ctx *ctx, int nparts, double model_scale, double *dev_M, double *dev_j)
+{
     const int npairs = ctx->NT * (ctx->NT + 1) / 2;
-    k_gram_finalize<<<npairs, 64, 0, ctx->stream>>>(ctx->N, ctx->NT, ctx->P, n_tiles, ctx->d_tile_panel, ctx->d_panel_t0,
-                                                    ctx->d_panel_nt, ctx->d_pair_code, ctx->d_types, args.type_tab,
-                                                    ctx->d_partial, ctx->d_ck, model_scale, dev_M, dev_j);
+    k_gram_finalize<<<npairs, 64, 0, ctx->stream>>>(ctx->N, ctx->NT, ctx->P, nparts, ctx->part_tiles[0], ctx->part_tiles[1],
+                                                    ctx->d_tile_panel, ctx->d_panel_t0, ctx->d_panel_nt, ctx->d_pair_code,
+                                                    ctx->d_types, ctx->part_typetab[0], ctx->part_typetab[nparts > 1 ? 1 : 0],
+                                                    ctx->part_slot0[1], ctx->d_partial, ctx->d_ck, model_scale, dev_M, dev_j);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

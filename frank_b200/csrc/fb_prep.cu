@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(1024) k_prep_reduce(int nblocks, const double 
 }  // namespace
 
 int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
-                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax)
+                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax, double *host_H0)
 {
     const int64_t n_pad = ((n + FB_TV - 1) / FB_TV) * FB_TV;
     if (n_pad > ctx->cap) {
@@ -167,8 +167,9 @@ int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, con
     if (nblocks > ctx->red_cap) {
         if (ctx->d_red) FB_CUDA(cudaFree(ctx->d_red));
         ctx->d_red = nullptr;
-        FB_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * (3 * (size_t)nblocks + 8)));
-        ctx->red_cap = nblocks;
+        const int cap = nblocks + nblocks / 4 + 16;
+        FB_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * (3 * (size_t)cap + 8)));
+        ctx->red_cap = cap;
     }
     k_prep<<<nblocks, PREP_THREADS, 0, ctx->stream>>>(n, u, v, (const double2 *)V, w, w_stride, *g, ctx->invQmax,
                                                       (double4 *)ctx->d_rec, ctx->d_red);
@@ -178,10 +179,11 @@ int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, con
     FB_CUDA(cudaGetLastError());
     double h[3];
     FB_CUDA(cudaMemcpyAsync(h, fin, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    FB_CUDA(cudaMemcpyAsync(dev_H0, fin, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dev_H0) FB_CUDA(cudaMemcpyAsync(dev_H0, fin, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
     host_qminmax[0] = h[1];
     host_qminmax[1] = h[2];
+    if (host_H0) *host_H0 = h[0];
     ctx->last_n = n;
     // order the visibilities by baseline bin (stable) and lay them out for the Gram kernel
     return fb_launch_sort(ctx, n, n_pad, n > 0 ? h[2] * ctx->invQmax : 0.0);

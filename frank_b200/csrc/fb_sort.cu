@@ -216,8 +216,9 @@ uint64_t *fb_radix_sort_items(fb_ctx *ctx, int64_t n, uint64_t *buf0, uint64_t *
     if (hist_need > ctx->hist_cap) {
         if (ctx->d_hist) cudaFree(ctx->d_hist);
         ctx->d_hist = nullptr;
-        if (cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * hist_need) != cudaSuccess) { *status = -50; ctx->err = "radix sort: out of memory"; return nullptr; }
-        ctx->hist_cap = hist_need;
+        const size_t cap = hist_need + hist_need / 4 + 4096;       // slack: the second half of a split call is a little larger
+        if (cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * cap) != cudaSuccess) { *status = -50; ctx->err = "radix sort: out of memory"; return nullptr; }
+        ctx->hist_cap = cap;
     }
     uint64_t *src = buf0, *dst = buf1;
     for (int shift = 32; shift < 32 + nbits; shift += 8) {

@@ -187,7 +187,8 @@ def test_device_and_host_entry_points_agree(fb):
 def test_full_size_properties(fb):
     """BASELINE.json config 2 shape (1e7 visibilities, N = 300) through size-independent properties:
     linearity in the weights, additivity over a split of the visibilities, symmetry, positive diagonal,
-    and agreement of a 2e4-visibility slice with the oracle."""
+    agreement of the (split) host entry point with the device entry point, and agreement of a 2e4-visibility slice
+    with the oracle."""
     import torch
     n, N = 10_000_000, 300
     gen = torch.Generator(device='cuda').manual_seed(3)
@@ -213,6 +214,16 @@ def test_full_size_properties(fb):
     assert abs(a['null_likelihood'] + b['null_likelihood'] - full['null_likelihood']) < 1e-12 * abs(full['null_likelihood'])
     w2 = vm.map_visibilities(u, v, V, 2.0 * w)
     assert np.array_equal(w2['M'], 2.0 * M) or np.max(np.abs(w2['M'] - 2.0 * M) / np.outer(d, d)) < SUM_TOL
+    # the host entry point runs this size as two overlapped halves (copy of the second under the kernels of the
+    # first): same result up to the summation order, and the same bits on every call
+    uh, vh, Vh, wh = [x.cpu().numpy() for x in (u, v, V, w)]
+    host = vm.map_visibilities(uh, vh, Vh, wh)
+    assert np.max(np.abs(host['M'] - M) / np.outer(d, d)) < SUM_TOL
+    assert np.max(np.abs(host['j'] - full['j'])) < 1e-12 * np.max(np.abs(full['j']))
+    assert abs(host['null_likelihood'] - full['null_likelihood']) < 1e-12 * abs(full['null_likelihood'])
+    host2 = vm.map_visibilities(uh, vh, Vh, wh)
+    assert np.array_equal(host['M'], host2['M']) and np.array_equal(host['j'], host2['j'])
+    del uh, vh, Vh, wh
     k = 20000
     us, vs, Vs, ws = [x[:k].cpu().numpy() for x in (u, v, V, w)]
     ref = fo.map_visibilities(fo.DHTTables(1.6 / fo.RAD_TO_ARCSEC, N), us, vs, Vs, ws, 30., 40., 1e-3, -2e-3, check_qbounds=False)
