@@ -81,9 +81,14 @@ k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restri
 
 // ---- Cholesky panel: factor A_kk, then U_kj = U_kk^-T A_kj for the block row ----------------------------------------
 // grid (nb - k, B): block x = 0 factors and stores the diagonal block, x > 0 solves block column k + x (and repeats
-// the 64 x 64 factorisation, which is cheaper than waiting for it).  Both the factorisation and the triangular
-// solve keep their 64 x 64 operand in registers (a 4 x 4 sub-block per thread); each of the 64 dependent steps
-// broadcasts one row through shared memory and costs one __syncthreads.
+// the 64 x 64 factorisation, which is cheaper than waiting for it).  The 64 dependent pivot steps are the critical
+// path of the whole solver loop, so they are kept as cheap as possible: the diagonal block is processed in four
+// sub-blocks of 16; the 16 pivot steps of a sub-block are done by ONE warp with warp-level barriers only (shared
+// memory, no CTA barrier per pivot); what follows per sub-block is embarrassingly parallel and needs three CTA
+// barriers: 16-step forward substitutions with one thread per column (registers), and the rank-16 update of the
+// trailing rows of both blocks.
+constexpr int SB = 16;                 // pivot sub-block
+
 __global__ void __launch_bounds__(256)
 k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active, int *__restrict__ info,
              double *__restrict__ rdiag_all)
@@ -92,108 +97,110 @@ k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__rest
     if (active && !active[b]) return;
     double *A = A_all + (size_t)b * N * N;
     extern __shared__ double dyn_sm[];
-    double (*D)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm);              // rows of U_kk as they become final
-    double (*X)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm + NB * SLD);   // rows of the solved block
+    double (*S)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm);              // diagonal block (upper triangle)
+    double (*X)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm + NB * SLD);   // block A_kj -> U_kj
     __shared__ double rinv[NB];                                                // 1 / U_cc
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j = k + blockIdx.x;
+    const bool off = blockIdx.x > 0;
     const int r0 = k * NB, c0 = j * NB;
     const int nk = min(NB, N - r0), nj = min(NB, N - c0);
-    // ---- diagonal block into registers: rows ty*4.., columns tx*4.. (identity padding beyond nk)
-    double a[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int i = ty * 4 + r, jj = tx * 4 + c;
-            a[r][c] = (i < nk && jj < nk && jj >= i) ? A[(size_t)(r0 + i) * N + r0 + jj] : (i == jj ? 1.0 : 0.0);
-        }
-    for (int c = 0; c < NB; c++) {
-        // the owners of row c publish it (unscaled); everybody scales it locally
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-            if (ty * 4 + r == c) {
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) D[c][tx * 4 + cc] = a[r][cc];
-            }
-        __syncthreads();
-        const double piv = D[c][c];
-        if (tid == 0 && blockIdx.x == 0 && c < nk && !(piv > 0.0)) atomicCAS(&info[b], 0, r0 + c + 1);
-        // 1/sqrt(pivot) in one short dependency chain (MUFU seed + Newton) instead of an IEEE sqrt and a division:
-        // this chain is the critical path of the 64 dependent steps
-        const double inv = rsqrt(piv), d = piv * inv;
-        if (tid == 0) rinv[c] = inv;
-        double ui[4], uj[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) { ui[r] = D[c][ty * 4 + r] * inv; uj[r] = D[c][tx * 4 + r] * inv; }
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
-                const int i = ty * 4 + r, jj = tx * 4 + cc;
-                if (i > c && jj >= i) a[r][cc] = fma(-ui[r], uj[cc], a[r][cc]);
-                else if (i == c) a[r][cc] = jj > c ? uj[cc] : (jj == c ? d : a[r][cc]);
-            }
-        // no second barrier: row c of D is never written again, and row c + 1 is published only after every
-        // thread has passed this step's barrier... but a fast thread could publish row c + 1 while a slow one
-        // still reads row c -- different rows, no hazard.
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 6, jj = e & 63;
+        S[i][jj] = (i < nk && jj < nk && jj >= i) ? A[(size_t)(r0 + i) * N + r0 + jj] : (i == jj ? 1.0 : 0.0);   // identity padding
+        if (off) X[i][jj] = (i < nk && jj < nj) ? A[(size_t)(r0 + i) * N + c0 + jj] : 0.0;
     }
     __syncthreads();
-    // final U_kk rows into shared memory (scaled) for the triangular solve, and to global memory from CTA 0
+    for (int kb = 0; kb < NB; kb += SB) {
+        // (1) pivots of the sub-block: one warp, lane <-> column, the column in registers, rows of U broadcast by
+        //     shuffles -- no shared-memory round trip on the dependent chain (lanes 16..31 mirror lanes 0..15)
+        if (warp == 0) {
+            const int col = lane & 15;
+            double a[SB];
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+            for (int i = 0; i < SB; i++) a[i] = S[kb + i][kb + col];           // the lower triangle of S is zero
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) D[ty * 4 + r][tx * 4 + cc] = a[r][cc];
-    __syncthreads();
-    if (blockIdx.x == 0) {
+            for (int c = 0; c < SB; c++) {
+                const double piv = __shfl_sync(0xffffffffu, a[c], c);
+                if (lane == 0 && !off && kb + c < nk && !(piv > 0.0)) atomicCAS(&info[b], 0, r0 + kb + c + 1);
+                // 1/sqrt(pivot) in one short dependency chain (MUFU seed + Newton) instead of an IEEE sqrt and a division
+                const double inv = rsqrt(piv);
+                const double u = a[c] * inv;                                   // U[c][col] (zero for col < c)
+                a[c] = col == c ? piv * inv : u;
+                if (lane == c) rinv[kb + c] = inv;
 #pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
-                const int i = ty * 4 + r, jj = tx * 4 + cc;
-                if (i < nk && jj < nk && jj >= i) A[(size_t)(r0 + i) * N + r0 + jj] = a[r][cc];
-            }
-        if (tid < nk) rdiag_all[(size_t)b * N + r0 + tid] = rinv[tid];
-        return;
-    }
-    // ---- forward substitution U_kk^T X = R with R in registers (rows ty*4.., columns tx*4..)
-    double rr_[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-            const int i = ty * 4 + r, jj = tx * 4 + cc;
-            rr_[r][cc] = (i < nk && jj < nj) ? A[(size_t)(r0 + i) * N + c0 + jj] : 0.0;
-        }
-    for (int r = 0; r < NB; r++) {
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (ty * 4 + q == r) {
-                const double dinv = rinv[r];
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
-                    const double x = rr_[q][cc] * dinv;
-                    rr_[q][cc] = x;
-                    X[r][tx * 4 + cc] = x;
+                for (int i = c + 1; i < SB; i++) {
+                    const double ui = __shfl_sync(0xffffffffu, u, i);          // U[c][i]
+                    if (col >= i) a[i] = fma(-ui, u, a[i]);
                 }
             }
-        __syncthreads();
-        double xr[4], ur[4];
+            if (lane < SB) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) { xr[q] = X[r][tx * 4 + q]; ur[q] = D[r][ty * 4 + q]; }
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (ty * 4 + q > r)
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) rr_[q][cc] = fma(-ur[q], xr[cc], rr_[q][cc]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-            const int i = ty * 4 + r, jj = tx * 4 + cc;
-            if (i < nk && jj < nj) A[(size_t)(r0 + i) * N + c0 + jj] = rr_[r][cc];
+                for (int i = 0; i < SB; i++)
+                    if (i <= col) S[kb + i][kb + col] = a[i];
+            }
         }
+        __syncthreads();
+        // (2) forward substitution U_bb^T x = b for the columns to the right of the sub-block (rows kb .. kb+15):
+        //     threads 0..63 take the columns of X, threads 64.. the remaining columns of S
+        {
+            double *base = nullptr;
+            if (tid < NB) { if (off) base = &X[kb][tid]; }
+            else if (tid - NB < NB - kb - SB) base = &S[kb][kb + SB + (tid - NB)];
+            if (base) {
+                double x[SB];
+#pragma unroll
+                for (int r = 0; r < SB; r++) x[r] = base[r * SLD];
+#pragma unroll
+                for (int r = 0; r < SB; r++) {
+                    double acc = x[r];
+#pragma unroll
+                    for (int i = 0; i < r; i++) acc = fma(-S[kb + i][kb + r], x[i], acc);
+                    x[r] = acc * rinv[kb + r];
+                }
+#pragma unroll
+                for (int r = 0; r < SB; r++) base[r * SLD] = x[r];
+            }
+        }
+        __syncthreads();
+        // (3) rank-16 update of the trailing rows kb+16 .. 63: S (upper triangle) and X
+        {
+            const int nt = NB - kb - SB;                      // trailing rows
+            const int tx = tid & 15, ty = tid >> 4;           // 16 x 16 threads, each a strided set of entries
+            for (int i = ty; i < nt; i += 16) {
+                const int ri = kb + SB + i;
+                double ui[SB];
+#pragma unroll
+                for (int c = 0; c < SB; c++) ui[c] = S[kb + c][ri];
+                for (int jj = ri + tx; jj < NB; jj += 16) {   // upper triangle of S
+                    double acc = S[ri][jj];
+#pragma unroll
+                    for (int c = 0; c < SB; c++) acc = fma(-ui[c], S[kb + c][jj], acc);
+                    S[ri][jj] = acc;
+                }
+                if (off)
+                    for (int jj = tx; jj < NB; jj += 16) {
+                        double acc = X[ri][jj];
+#pragma unroll
+                        for (int c = 0; c < SB; c++) acc = fma(-ui[c], X[kb + c][jj], acc);
+                        X[ri][jj] = acc;
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    if (!off) {
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int i = e >> 6, jj = e & 63;
+            if (i < nk && jj < nk && jj >= i) A[(size_t)(r0 + i) * N + r0 + jj] = S[i][jj];
+        }
+        if (tid < nk) rdiag_all[(size_t)b * N + r0 + tid] = rinv[tid];
+    } else {
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int i = e >> 6, jj = e & 63;
+            if (i < nk && jj < nj) A[(size_t)(r0 + i) * N + c0 + jj] = X[i][jj];
+        }
+    }
 }
 
 // ---- trailing update A_ij -= U_ki^T U_kj, k < i <= j -----------------------------------------------------------------
