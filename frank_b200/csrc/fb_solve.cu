@@ -287,6 +287,103 @@ k_trsm_tr2(int N, int TP, const double *__restrict__ U_all, const double *__rest
     if (lane == 0 && c < N) tr2_all[(size_t)b * N + c] = ssq;
 }
 
+// ---- Tr2, blocked: the same forward substitution for RB right-hand sides per CTA, with the whole N x RB solution in
+// shared memory.  Left-looking over block rows of 64: Z_k = Y_k - sum_{i<k} U_ik^T Z_i is a sequence of 64 x 64 x RB
+// products (all threads, 4 x RB/16 outputs each), and the triangular solve with U_kk proceeds 16 rows at a time:
+// one thread per right-hand side does the 16 dependent steps in registers, then all threads apply the rank-16 update
+// to the remaining rows of the block.  N dependent warp-synchronous steps become N / 16 short CTA-level rounds.
+template <int RB>
+__global__ void __launch_bounds__(256)
+k_trsm_tr2_blocked(int N, int nb, const double *__restrict__ U_all, const double *__restrict__ rdiag_all,
+                   const double *__restrict__ Y, const int *__restrict__ active, double *__restrict__ tr2_all)
+{
+    constexpr int ZLD = RB + 1;
+    constexpr int CT = RB / 16;                             // columns per thread in the products
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const double *U = U_all + (size_t)b * N * N;
+    const double *rdiag = rdiag_all + (size_t)b * N;
+    extern __shared__ double sm[];
+    double (*Us)[SLD] = reinterpret_cast<double (*)[SLD]>(sm);                 // one 64 x 64 block of U
+    double *Z = sm + NB * SLD;                                                 // [nb * 64][ZLD]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int c0 = blockIdx.x * RB;
+    for (int e = tid; e < nb * NB * RB; e += 256) {
+        const int c = e / (nb * NB), r = e % (nb * NB);      // consecutive threads read consecutive entries of a row of Y
+        Z[r * ZLD + c] = (r < N && c0 + c < N) ? Y[(size_t)(c0 + c) * N + r] : 0.0;   // right-hand side c = row c0 + c of Y
+    }
+    for (int k = 0; k < nb; k++) {
+        const int r0 = k * NB, nk = min(NB, N - r0);
+        double *Zk = Z + (size_t)r0 * ZLD;
+        // Z_k -= U_ik^T Z_i for the block rows above
+        for (int i = 0; i < k; i++) {
+            __syncthreads();
+            for (int e = tid; e < NB * NB; e += 256) {
+                const int t = e >> 6, rr = e & 63;
+                Us[t][rr] = rr < nk ? U[(size_t)(i * NB + t) * N + r0 + rr] : 0.0;
+            }
+            __syncthreads();
+            const double *Zi = Z + (size_t)i * NB * ZLD;
+            double acc[4][CT] = {};
+#pragma unroll 4
+            for (int t = 0; t < NB; t++) {
+                double ua[4], zb[CT];
+#pragma unroll
+                for (int q = 0; q < 4; q++) ua[q] = Us[t][ty * 4 + q];
+#pragma unroll
+                for (int q = 0; q < CT; q++) zb[q] = Zi[t * ZLD + tx * CT + q];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int w = 0; w < CT; w++) acc[q][w] = fma(ua[q], zb[w], acc[q][w]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int w = 0; w < CT; w++) Zk[(ty * 4 + q) * ZLD + tx * CT + w] -= acc[q][w];
+        }
+        // triangular solve with the diagonal block, 16 rows at a time
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int t = e >> 6, rr = e & 63;
+            Us[t][rr] = (t < nk && rr < nk && rr >= t) ? U[(size_t)(r0 + t) * N + r0 + rr] : 0.0;
+        }
+        __syncthreads();
+        for (int kb = 0; kb < NB; kb += 16) {
+            if (tid < RB) {
+                double x[16];
+#pragma unroll
+                for (int r = 0; r < 16; r++) x[r] = Zk[(kb + r) * ZLD + tid];
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    double acc = x[r];
+#pragma unroll
+                    for (int t = 0; t < r; t++) acc = fma(-Us[kb + t][kb + r], x[t], acc);
+                    x[r] = kb + r < nk ? acc * rdiag[min(r0 + kb + r, N - 1)] : 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < 16; r++) Zk[(kb + r) * ZLD + tid] = x[r];
+            }
+            __syncthreads();
+            const int nt = NB - kb - 16;                    // remaining rows of the block
+            for (int e = tid; e < nt * RB; e += 256) {
+                const int rr = kb + 16 + e / RB, c = e % RB;
+                double acc = Zk[rr * ZLD + c];
+#pragma unroll
+                for (int t = 0; t < 16; t++) acc = fma(-Us[kb + t][rr], Zk[(kb + t) * ZLD + c], acc);
+                Zk[rr * ZLD + c] = acc;
+            }
+            __syncthreads();
+        }
+    }
+    // Tr2_c = sum_r Z[r][c]^2, fixed order
+    if (tid < RB && c0 + tid < N) {
+        double ssq = 0.0;
+        for (int r = 0; r < N; r++) { const double z = Z[r * ZLD + tid]; ssq = fma(z, z, ssq); }
+        tr2_all[(size_t)b * N + c0 + tid] = ssq;
+    }
+}
+
 // ---- mu = U^-1 U^-T j, one CTA (1024 threads) per problem ---------------------------------------------------------
 // Both sweeps walk U in panels of PR rows staged in shared memory (rows of the row-major upper factor are
 // contiguous): the PR x PR triangle is solved by one warp with shuffles, the rest of the panel is a
@@ -588,7 +685,25 @@ static int allow_build_smem(fb_ctx *ctx)
 
 static int launch_tr2(fb_ctx *ctx, int B, const int *d_active)
 {
-    const int N = ctx->N;
+    const int N = ctx->N, nb = (N + NB - 1) / NB;
+    // blocked kernel when the N x RB solution fits in shared memory (N <= 320 with 64 right-hand sides per CTA,
+    // N <= 640 with 32)
+    // (worth it for batches: with a single problem only N / 64 CTAs would run and the warp-per-column kernel is as fast)
+    const size_t lim = B >= 4 ? 200 * 1024 : 0;
+    const size_t need64 = sizeof(double) * ((size_t)NB * SLD + (size_t)nb * NB * 65);
+    const size_t need32 = sizeof(double) * ((size_t)NB * SLD + (size_t)nb * NB * 33);
+    if (need64 <= lim) {
+        FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2_blocked<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need64));
+        k_trsm_tr2_blocked<64><<<dim3((N + 63) / 64, B), 256, need64, ctx->stream>>>(N, nb, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2);
+        FB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (need32 <= lim) {
+        FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2_blocked<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need32));
+        k_trsm_tr2_blocked<32><<<dim3((N + 31) / 32, B), 256, need32, ctx->stream>>>(N, nb, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2);
+        FB_CUDA(cudaGetLastError());
+        return 0;
+    }
     // shared memory: TP staged rows of U + one right-hand side per warp; shrink both for very large N
     int ts = TS, tp = 32;
     while (sizeof(double) * ((size_t)tp + ts) * N > 200 * 1024 && tp > 4) tp /= 2;
@@ -722,7 +837,7 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     FB_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
 
     int n_active = B, it = 0;
-    const int poll = 8;
+    const int poll = 32;      // iterations enqueued between two looks at the active count (gated-off iterations cost ~30 us each)
     while (n_active > 0 && it <= max_iter + 1) {
         for (int sidx = 0; sidx < poll; sidx++, it++) FB_CUDA(cudaGraphLaunch(gexec, ctx->stream));
         FB_CUDA(cudaMemcpyAsync(&n_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
