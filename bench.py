@@ -252,7 +252,28 @@ def main():
     sampler.stop_flag = True             # clocks sampled across the device-resident and the end-to-end timed regions
     sampler.join(timeout=2)
 
-    # ---- whole fit (map + power-spectrum loop) on rank 0, once ------------------------------------------
+    # ---- the HBM-bound uv-binning pass (UVDataBinner) timed alone on rank 0, device-resident arrays ----------
+    binning = None
+    if rank == 0:
+        quv = torch.hypot(u, v).contiguous()
+        bin_width = 1e3                                       # lambda (BASELINE.json configs[4])
+        uv_max = float(quv.max().item())
+        nbins = int(np.ceil(uv_max / bin_width))
+        nbins += int(nbins * bin_width < uv_max)
+        for _ in range(2):
+            ctx.uv_bin_dev(quv, V, w, bin_width, nbins)
+        reps = 5
+        ctx.timer_start()
+        for _ in range(reps):
+            ctx.uv_bin_dev(quv, V, w, bin_width, nbins)
+        bin_ms = ctx.timer_stop() / reps
+        bin_bytes = 72 * n                                    # (32 B read + 4 B index written) x 2 passes
+        binning = {'kernels': ['k_bin_index', 'k_sort_hist x2', 'k_sort_scan x2', 'k_sort_scatter x2', 'k_bin_starts', 'k_bin_reduce'],
+                   'n_vis': n, 'nbins': nbins, 'bin_width_lambda': bin_width, 'ms': bin_ms, 'algorithmic_bytes': bin_bytes,
+                   'achieved_gbs': bin_bytes / (bin_ms * 1e-3) / 1e9, 'Gvis_per_s': n / (bin_ms * 1e-3) / 1e9}
+        del quv
+
+    # ---- whole fit (map + power-spectrum loop) on rank 0 ------------------------------------------------
     fit = None
     if not args.no_fit and rank == 0:
         FF = FrankFitter(RMAX, N, geom, alpha=1.05, weights_smooth=1e-4, verbose=False, device=local_rank,
@@ -264,10 +285,19 @@ def main():
         t0 = time.perf_counter()
         FF.fit_preprocessed(pre)             # warm-up: the first solve of a process pays one-off CUDA start-up costs
         t_first = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        FF.fit_preprocessed(pre)
-        t_loop = time.perf_counter() - t0
-        fit = {'fit_wall_s': t_map + t_loop, 'map_s': t_map, 'solver_loop_s': t_loop, 'solver_loop_first_call_s': t_first,
+        loops, loop_clocks = [], []
+        for _ in range(3):
+            smp = ClockSampler(local_rank)                    # the loop is a chain of small kernels: record the SM clock it ran at
+            smp.start()
+            t0 = time.perf_counter()
+            FF.fit_preprocessed(pre)
+            loops.append(time.perf_counter() - t0)
+            smp.stop_flag = True
+            smp.join(timeout=2)
+            loop_clocks.append(smp.summary()['sm_mhz'])
+        t_loop = float(np.median(loops))
+        fit = {'fit_wall_s': t_map + t_loop, 'map_s': t_map, 'solver_loop_s': t_loop, 'solver_loop_runs_s': loops, 'solver_loop_sm_mhz': loop_clocks,
+               'solver_loop_first_call_s': t_first,
                'iterations': int(FF.iteration_diagnostics['num_iterations']), 'method': 'Normal', 'alpha': 1.05, 'wsmooth': 1e-4,
                'inputs': 'host numpy arrays (pageable)'}
 
@@ -312,6 +342,17 @@ def main():
         peaks = load_peaks()
         if peaks:
             line['measured_peaks'] = {k: peaks.get(k) for k in ('hbm_gbs', 'bf16_tflops')}
+        hbm_peak = float(peaks.get('hbm_gbs') or 6551.7)     # MEASURED_PEAKS.json copy bandwidth of this pool's B200
+        prep_bytes = 72 * n                                   # 40 B read + 32 B record written
+        line['hbm_passes'] = {
+            'peak_gbs': hbm_peak,
+            'prepass_and_sort': {'ms': float(np.mean(prep_ms)), 'algorithmic_bytes': prep_bytes,
+                                 'achieved_gbs': prep_bytes / (float(np.mean(prep_ms)) * 1e-3) / 1e9,
+                                 'frac': prep_bytes / (float(np.mean(prep_ms)) * 1e-3) / 1e9 / hbm_peak,
+                                 'note': 'geometry pre-pass + 2-pass stable radix sort + SoA gather + work-table upload'}}
+        if binning:
+            binning['frac'] = binning['achieved_gbs'] / hbm_peak
+            line['hbm_passes']['uv_binning'] = binning
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

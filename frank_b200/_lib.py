@@ -47,6 +47,7 @@ _SIGNATURES = {
     'fb_predict_visibilities': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
     'fb_uv_max': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_uv_bin': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
+    'fb_uv_bin_dev': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_ln_setup': ([_c_p, _c_p, _c_p, _c_d, _c_d], _c_i),
     'fb_ln_set_spectrum': ([_c_p, _c_p], _c_i),
     'fb_ln_eval': ([_c_p, _c_p, _c_p, _c_p], _c_i),
@@ -274,6 +275,26 @@ class Context(object):
         sums = np.empty((nbins, 4)); err = np.empty((nbins, 2))
         self.check(self._lib.fb_uv_bin(self._h, n, _ptr(uv), _ptr(V), int(is_c), _ptr(w), int(w.size > 1), float(bin_width),
                                        int(nbins), _ptr(idx), _ptr(counts), _ptr(sums), _ptr(err)), 'fb_uv_bin')
+        return idx, counts, sums, err
+
+    def uv_bin_dev(self, uv, V, w, bin_width, nbins):
+        """fb_uv_bin_dev on torch CUDA tensors (uv, w float64 [n] or w [1]; V complex128 or float64 [n]).  Returns
+        device tensors idx (int32 [n]), counts (int64 [nbins]), sums (float64 [nbins, 4]), err (float64 [nbins, 2])."""
+        import torch
+        n = uv.numel()
+        is_c = V.is_complex()
+        Vr = torch.view_as_real(V) if is_c else V
+        for t in (uv, Vr, w):
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float64):
+                raise ValueError("uv_bin_dev: contiguous float64 / complex128 CUDA tensors expected")
+        idx = torch.empty(n, dtype=torch.int32, device=uv.device)
+        counts = torch.empty(nbins, dtype=torch.int64, device=uv.device)
+        sums = torch.empty((nbins, 4), dtype=torch.float64, device=uv.device)
+        err = torch.empty((nbins, 2), dtype=torch.float64, device=uv.device)
+        torch.cuda.current_stream(uv.device).synchronize()       # inputs were produced on torch's stream
+        self.check(self._lib.fb_uv_bin_dev(self._h, n, _ptr(uv), _ptr(Vr), int(is_c), _ptr(w), int(w.numel() > 1),
+                                           float(bin_width), int(nbins), _ptr(idx), _ptr(counts), _ptr(sums), _ptr(err)),
+                   'fb_uv_bin_dev')
         return idx, counts, sums, err
 
     def debug_j0(self, x, far=False):

@@ -1,6 +1,7 @@
 // C ABI of libfrankb200 (see include/frankb200.h): context, DHT setup, map_visibilities entry points.
 #include "fb_common.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -38,7 +39,7 @@ int fb_ctx_destroy(fb_ctx *ctx)
                     (void *)ctx->d_tile_panel, (void *)ctx->d_panel_t0, (void *)ctx->d_panel_nt, (void *)ctx->d_pair_code,
                     (void *)ctx->d_a, (void *)ctx->d_sw, (void *)ctx->d_swV, (void *)ctx->d_kz, (void *)ctx->d_amid, (void *)ctx->d_red,
                     (void *)ctx->d_partial, (void *)ctx->d_H2, (void *)ctx->d_in, (void *)ctx->d_out,
-                    (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist, (void *)ctx->d_work, (void *)ctx->d_work2,
+                    (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist, (void *)ctx->d_binstart, (void *)ctx->d_work, (void *)ctx->d_work2,
                     (void *)ctx->sv_D, (void *)ctx->sv_p, (void *)ctx->sv_mu, (void *)ctx->sv_tr2, (void *)ctx->sv_alpha,
                     (void *)ctx->sv_p0, (void *)ctx->sv_Tinv, (void *)ctx->sv_M, (void *)ctx->sv_j, (void *)ctx->sv_Z,
                     (void *)ctx->sv_flags, (void *)ctx->sv_rdiag, (void *)ctx->ln_S, (void *)ctx->ln_vec})
@@ -168,10 +169,14 @@ int fb_map_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const d
     return 0;
 }
 
-// Host entry point.  From FB_SPLIT_MIN visibilities on, the call runs as two halves so that the host-to-device
-// copy of the second half (on a second stream) overlaps the kernels of the first; the partial blocks of both halves
+// Host entry point.  From FB_SPLIT_MIN visibilities on, the call runs as two parts so that the host-to-device
+// copy of the second part (on a second stream) overlaps the kernels of the first; the partial blocks of both parts
 // are summed in a fixed order, so the result is deterministic (it differs from the one-pass result of the device
 // entry point in the last bits, like any other change of the summation order).
+// The first part is as small as the overlap allows, because its own copy is the exposed one: the copy of the second
+// part (c = 0.75 ns per visibility at ~53 GB/s from pinned memory) has to fit under the first part's kernels
+// (p = 0.16 + 3.85 (N/300)^2 ns per visibility, measured: pre-pass + sort + Gram), i.e. f >= c / (c + p); 25 % margin,
+// at most one half.  N = 300: f = 0.2 (copy exposed: 1.4 ms of a 1e7-visibility call instead of 3.6 ms).
 constexpr int64_t FB_SPLIT_MIN = 4000000;
 
 int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const double *host_v, const double *host_V_reim,
@@ -201,7 +206,15 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
     if (!ctx->stream2) FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     double *du = ctx->d_in, *dv = du + n, *dV = dv + n, *dw = dV + 2 * n;
     const int nparts = n >= FB_SPLIT_MIN ? 2 : 1;
-    const int64_t n0 = nparts == 2 ? (n / 2) / FB_TV * FB_TV : n, n1 = n - n0;
+    int64_t n0 = n;
+    if (nparts == 2) {
+        const double c = 0.75, p = 0.16 + 3.85 * ((double)ctx->N / 300.0) * ((double)ctx->N / 300.0);
+        const double f = std::min(0.5, 1.25 * c / (c + p));
+        n0 = std::max<int64_t>(FB_TV, (int64_t)(f * (double)n) / FB_TV * FB_TV);
+    }
+    const int64_t n1 = n - n0;
+    rc = fb_reserve_prep(ctx, (std::max(n0, n1) + FB_TV - 1) / FB_TV * FB_TV);
+    if (rc) return rc;
     auto copy_part = [&](int64_t off, int64_t cnt, cudaStream_t st) -> int {
         FB_CUDA(cudaMemcpyAsync(du + off, host_u + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
         FB_CUDA(cudaMemcpyAsync(dv + off, host_v + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));

@@ -76,6 +76,8 @@ struct fb_ctx {
     uint32_t *d_perm = nullptr;    // sorted position -> original index
     uint32_t *d_hist = nullptr;
     size_t hist_cap = 0;
+    uint32_t *d_binstart = nullptr;   // uv binner: segment starts of the sorted items [nbins + 1]
+    size_t bin_cap = 0;
     double *d_red = nullptr;     // pre-pass block reductions
     int red_cap = 0;
     double *d_partial = nullptr;
@@ -125,6 +127,8 @@ struct fb_ctx {
 // kernels / launchers implemented in the .cu files
 int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
                    int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax, double *host_H0);
+int fb_reserve_prep(fb_ctx *ctx, int64_t n_pad);
+int fb_reserve_sort(fb_ctx *ctx, int64_t n);
 int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_model);
 int fb_launch_gram_finalize(fb_ctx *ctx, int nparts, double model_scale, double *dev_M, double *dev_j);
 int fb_build_j0_table(fb_ctx *ctx, double x_max);

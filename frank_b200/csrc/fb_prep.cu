@@ -14,6 +14,8 @@
 // np.hypot calls; tests/test_prep_bits.py checks bit equality.
 #include "fb_common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int PREP_THREADS = 256;
@@ -139,10 +141,11 @@ __global__ void __launch_bounds__(1024) k_prep_reduce(int nblocks, const double 
 
 }  // namespace
 
-int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
-                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax, double *host_H0)
+// Grow the per-visibility workspaces (sorted SoA arrays, records, sort items, permutation, tile ranges) to hold
+// n_pad visibilities.  Callers that run a mapping call in parts reserve the largest part up front, so that no
+// buffer is reallocated while an earlier part's kernels are in flight.
+int fb_reserve_prep(fb_ctx *ctx, int64_t n_pad)
 {
-    const int64_t n_pad = ((n + FB_TV - 1) / FB_TV) * FB_TV;
     if (n_pad > ctx->cap) {
         int64_t cap = n_pad + n_pad / 8 + 4096;
         for (double **p : {&ctx->d_a, &ctx->d_sw, &ctx->d_swV, &ctx->d_kz}) {
@@ -162,8 +165,7 @@ int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, con
         ctx->cap = cap;
     }
     const int per_block = PREP_THREADS * PREP_ITEMS;
-    int nblocks = (int)((n_pad + per_block - 1) / per_block);
-    if (nblocks < 1) nblocks = 1;
+    const int nblocks = (int)std::max<int64_t>(1, (n_pad + per_block - 1) / per_block);
     if (nblocks > ctx->red_cap) {
         if (ctx->d_red) FB_CUDA(cudaFree(ctx->d_red));
         ctx->d_red = nullptr;
@@ -171,6 +173,20 @@ int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, con
         FB_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * (3 * (size_t)cap + 8)));
         ctx->red_cap = cap;
     }
+    return fb_reserve_sort(ctx, n_pad);
+}
+
+int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
+                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax, double *host_H0)
+{
+    const int64_t n_pad = ((n + FB_TV - 1) / FB_TV) * FB_TV;
+    {
+        int rc = fb_reserve_prep(ctx, n_pad);
+        if (rc) return rc;
+    }
+    const int per_block = PREP_THREADS * PREP_ITEMS;
+    int nblocks = (int)((n_pad + per_block - 1) / per_block);
+    if (nblocks < 1) nblocks = 1;
     k_prep<<<nblocks, PREP_THREADS, 0, ctx->stream>>>(n, u, v, (const double2 *)V, w, w_stride, *g, ctx->invQmax,
                                                       (double4 *)ctx->d_rec, ctx->d_red);
     FB_CUDA(cudaGetLastError());

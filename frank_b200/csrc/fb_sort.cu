@@ -46,8 +46,24 @@ k_items_from_keys(int64_t n, const int32_t *__restrict__ keys, uint64_t *__restr
     if (i < n) items[i] = ((uint64_t)(uint32_t)keys[i] << 32) | (uint64_t)(uint32_t)i;
 }
 
+// Lanes of the warp (among `active`) whose 8-bit digit equals this lane's: eight ballots, one per digit bit (the
+// MATCH.ANY instruction behind __match_any_sync measured ~4x slower than this on sm_100a: 233 -> see DESIGN.md).
+// Every lane of the warp must call; lanes outside `active` get 0.
+__device__ __forceinline__ unsigned match_digit(int d, unsigned active)
+{
+    unsigned m = active;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return ((active >> (threadIdx.x & 31)) & 1u) ? m : 0u;
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_hist(int64_t n, const uint64_t *__restrict__ items, int shift, uint32_t *__restrict__ hist, int nblocks)
+k_sort_hist(int64_t n, const uint64_t *__restrict__ items, int shift, uint32_t *__restrict__ hist, int nblocks,
+            uint32_t *__restrict__ digit_total)
 {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
@@ -61,18 +77,35 @@ k_sort_hist(int64_t n, const uint64_t *__restrict__ items, int shift, uint32_t *
     }
     __syncthreads();
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+    if (h[threadIdx.x]) atomicAdd(&digit_total[threadIdx.x], h[threadIdx.x]);      // integer: order independent
 }
 
-// exclusive scan of `total` uint32 counters in place: one block of 1024 threads walks the array in coalesced
-// chunks of 4096 (4 per thread), block-scanning each chunk with warp shuffles and carrying the running total
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *__restrict__ data, int64_t total)
+// Exclusive scan of the (digit, block) counters in place, one CTA per digit row: the row's base is the sum of the
+// totals of the smaller digits (accumulated by k_sort_hist), the row itself is scanned in coalesced chunks of 4096
+// (4 per thread) with warp shuffles and a running carry.
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *__restrict__ data, int nblocks, const uint32_t *__restrict__ digit_total)
 {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
+    __shared__ uint32_t carry_s[2];                // double-buffered: read in one chunk, written for the next
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < total; base += 4096) {
+    const int digit = blockIdx.x;
+    {
+        uint32_t b = threadIdx.x < digit ? digit_total[threadIdx.x] : 0u;        // digit < 256 <= blockDim
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) warp_sums[warp] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w2 = 0; w2 < 8; w2++) t += warp_sums[w2];
+            carry_s[0] = t;
+        }
+        __syncthreads();
+    }
+    data += (size_t)digit * nblocks;
+    const int64_t total = nblocks;
+    int cur = 0;
+    for (int64_t base = 0; base < total; base += 4096, cur ^= 1) {
         const int64_t i0 = base + (int64_t)threadIdx.x * 4;
         uint32_t v[4];
 #pragma unroll
@@ -84,9 +117,10 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *__restrict__ data,
             uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
+        __syncthreads();                 // warp_sums of the previous chunk (or of the base) have been read
         if (lane == 31) warp_sums[warp] = inc;
         __syncthreads();
-        const uint32_t carry = carry_s;
+        const uint32_t carry = carry_s[cur];
         if (warp == 0) {
             uint32_t w = warp_sums[lane], winc = w;
 #pragma unroll
@@ -95,7 +129,7 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *__restrict__ data,
                 if (lane >= o) winc += t;
             }
             warp_sums[lane] = winc - w;
-            if (lane == 31) carry_s = carry + winc;
+            if (lane == 31) carry_s[cur ^ 1] = carry + winc;
         }
         __syncthreads();
         uint32_t run = carry + warp_sums[warp] + inc - s;
@@ -104,63 +138,80 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *__restrict__ data,
             if (i0 + k < total) data[i0 + k] = run;
             run += v[k];
         }
-        __syncthreads();
     }
 }
 
+// Stable scatter of one digit pass.  The block's 4096 items are first ordered by digit in shared memory (stable:
+// warps, rounds and lanes in element order), then written out position by position, so that the items of one digit
+// leave as one contiguous run (16 items = 128 B on average) instead of one scattered 8-byte store per item.
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_scatter(int64_t n, const uint64_t *__restrict__ items, int shift, const uint32_t *__restrict__ offs, int nblocks,
                uint64_t *__restrict__ out)
 {
     __shared__ uint32_t cnt[SORT_WARPS][256];
+    __shared__ uint32_t gbase[256];                 // global position of local position 0 of each digit's run
+    __shared__ uint32_t wsum[SORT_WARPS];
+    __shared__ uint64_t staged[SORT_CHUNK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t base = (int64_t)blockIdx.x * SORT_CHUNK;
     for (int w = 0; w < SORT_WARPS; w++) cnt[w][threadIdx.x] = 0;
     __syncthreads();
 
     uint64_t it[SORT_ROUNDS];
+    unsigned peers[SORT_ROUNDS];                    // lanes of the warp holding the same digit in this round
     // walk 1: per-warp digit counts
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
         int64_t i = elem_index(base, warp, r, lane);
         const bool ok = i < n;
         it[r] = ok ? items[i] : ~0ull;
-        const unsigned active = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            const int d = (int)((it[r] >> shift) & 255);
-            const unsigned m = __match_any_sync(active, d);
-            if (lane == __ffs(m) - 1) cnt[warp][d] += __popc(m);
-        }
+        const int d = (int)((it[r] >> shift) & 255);
+        const unsigned m = match_digit(d, __ballot_sync(0xffffffffu, ok));
+        peers[r] = m;
+        if (ok && lane == __ffs(m) - 1) cnt[warp][d] += __popc(m);
         __syncwarp();
     }
     __syncthreads();
-    // per digit: global base + exclusive prefix over the warps of this block
+    // per digit: exclusive prefix over the warps of this block, then over the digits -> local start of every
+    // (warp, digit) group; gbase = global offset of the digit in this block - local start of the digit
     {
         const int d = threadIdx.x;
-        uint32_t run = offs[(size_t)d * nblocks + blockIdx.x];
+        uint32_t c[SORT_WARPS], tot = 0;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-            uint32_t c = cnt[w][d];
-            cnt[w][d] = run;
-            run += c;
+        for (int w = 0; w < SORT_WARPS; w++) { c[w] = cnt[w][d]; tot += c[w]; }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < warp; w++) before += wsum[w];
+        uint32_t run = before + inc - tot;           // local start of digit d
+        gbase[d] = offs[(size_t)d * nblocks + blockIdx.x] - run;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) { cnt[w][d] = run; run += c[w]; }
     }
     __syncthreads();
-    // walk 2: same order, stable ranks
+    // walk 2: same order, stable local ranks
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
-        int64_t i = elem_index(base, warp, r, lane);
-        const bool ok = i < n;
-        const unsigned active = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
+        const unsigned m = peers[r];
+        if (m) {
             const int d = (int)((it[r] >> shift) & 255);
-            const unsigned m = __match_any_sync(active, d);
-            const uint32_t pos = cnt[warp][d] + __popc(m & ((1u << lane) - 1));
-            out[pos] = it[r];
-            __syncwarp(m);
-            if (lane == __ffs(m) - 1) cnt[warp][d] += __popc(m);
+            staged[cnt[warp][d] + __popc(m & ((1u << lane) - 1))] = it[r];
         }
         __syncwarp();
+        if (m && lane == __ffs(m) - 1) cnt[warp][(int)((it[r] >> shift) & 255)] += __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    const int nvalid = (int)(n - base < SORT_CHUNK ? n - base : SORT_CHUNK);
+    for (int k = threadIdx.x; k < nvalid; k += SORT_THREADS) {
+        const uint64_t x = staged[k];
+        out[gbase[(int)((x >> shift) & 255)] + (uint32_t)k] = x;
     }
 }
 
@@ -206,6 +257,20 @@ k_sort_gather(int64_t n, int64_t n_pad, const uint64_t *__restrict__ items, cons
 
 }  // namespace
 
+// Digit-histogram workspace for sorting n items.
+int fb_reserve_sort(fb_ctx *ctx, int64_t n)
+{
+    const size_t hist_need = (size_t)256 * ((n + SORT_CHUNK - 1) / SORT_CHUNK);
+    if (hist_need + 256 > ctx->hist_cap) {                     // + 256 digit totals behind the table
+        if (ctx->d_hist) cudaFree(ctx->d_hist);
+        ctx->d_hist = nullptr;
+        const size_t cap = hist_need + hist_need / 4 + 4096;
+        if (cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * cap) != cudaSuccess) FB_FAIL(-50, "radix sort: out of memory");
+        ctx->hist_cap = cap;
+    }
+    return 0;
+}
+
 // Stable LSD radix sort of n items (key << 32 | index) on `nbits` key bits, 8 bits per pass, ping-ponging between
 // buf0 (input) and buf1.  Returns the buffer holding the sorted items.
 uint64_t *fb_radix_sort_items(fb_ctx *ctx, int64_t n, uint64_t *buf0, uint64_t *buf1, int nbits, int *status)
@@ -213,17 +278,13 @@ uint64_t *fb_radix_sort_items(fb_ctx *ctx, int64_t n, uint64_t *buf0, uint64_t *
     *status = 0;
     const int nblocks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
     const size_t hist_need = (size_t)256 * nblocks;
-    if (hist_need > ctx->hist_cap) {
-        if (ctx->d_hist) cudaFree(ctx->d_hist);
-        ctx->d_hist = nullptr;
-        const size_t cap = hist_need + hist_need / 4 + 4096;       // slack: the second half of a split call is a little larger
-        if (cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * cap) != cudaSuccess) { *status = -50; ctx->err = "radix sort: out of memory"; return nullptr; }
-        ctx->hist_cap = cap;
-    }
+    if (fb_reserve_sort(ctx, n)) { *status = -50; return nullptr; }
     uint64_t *src = buf0, *dst = buf1;
     for (int shift = 32; shift < 32 + nbits; shift += 8) {
-        k_sort_hist<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, src, shift, ctx->d_hist, nblocks);
-        k_sort_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, (int64_t)hist_need);
+        uint32_t *digit_total = ctx->d_hist + hist_need;            // 256 counters behind the (digit, block) table
+        if (cudaMemsetAsync(digit_total, 0, sizeof(uint32_t) * 256, ctx->stream) != cudaSuccess) { *status = -51; ctx->err = "radix sort: memset failed"; return nullptr; }
+        k_sort_hist<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, src, shift, ctx->d_hist, nblocks, digit_total);
+        k_sort_scan<<<256, 1024, 0, ctx->stream>>>(ctx->d_hist, nblocks, digit_total);
         k_sort_scatter<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, src, shift, ctx->d_hist, nblocks, dst);
         uint64_t *t = src; src = dst; dst = t;
     }

@@ -153,11 +153,16 @@ int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, dou
  *   :338-347), counts per bin (int64), sums [nbins*4] = (sum w uv, sum w, sum w Re V, sum w Im V) (:349-361) and
  *   err [nbins*2] = (sum w^2 (Re V - mu)^2, sum w^2 (Im V - mu)^2) with mu the weighted bin mean (:236-247).
  *   V is interleaved complex (v_is_complex != 0) or real.  Visibilities are stably sorted by bin and each bin
- *   is reduced in a fixed order (deterministic). */
+ *   is reduced in a fixed order (deterministic).
+ * fb_uv_bin_dev: the same with every array already resident on the device (idx [n], counts [nbins], sums [nbins*4],
+ *   err [nbins*2] are caller-allocated device buffers); returns after the stream has drained. */
 int fb_uv_max(fb_ctx *ctx, int64_t n, const double *host_uv, double *host_max);
 int fb_uv_bin(fb_ctx *ctx, int64_t n, const double *host_uv, const double *host_V, int v_is_complex, const double *host_w,
               int w_stride, double bin_width, int nbins, int32_t *host_idx, long long *host_counts, double *host_sums,
               double *host_err);
+int fb_uv_bin_dev(fb_ctx *ctx, int64_t n, const double *dev_uv, const double *dev_V, int v_is_complex, const double *dev_w,
+                  int w_stride, double bin_width, int nbins, int32_t *dev_idx, long long *dev_counts, double *dev_sums,
+                  double *dev_err);
 
 /* ---- VisibilityMapping.predict_visibilities (frank/statistical_models.py:279-329) ---------------------------
  * V_i = sum_k H_ik I_k with the same design rows as the mapping; q [n] deprojected baselines, kz [n] (debris model

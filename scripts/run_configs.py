@@ -61,6 +61,21 @@ if '3' in which:
     t0 = time.perf_counter(); sol = FL.fit(u2, v2, V2, w2); t1 = time.perf_counter()
     print(json.dumps({'config': '3b LogNormal N=100, 1e6 vis', 'fit_s': t1 - t0, 'iterations': int(FL.iteration_diagnostics['num_iterations'])}), flush=True)
 
+if '3full' in which:
+    # BASELINE.json configs[2] end to end: method='LogNormal', N=500, 1e7 visibilities (alpha=1.3, wsmooth=1e-2)
+    n, N = 10_000_000, 500
+    dht, (u, v, V, w) = data(n, N)
+    FL = FrankFitter(1.6, N, geom, alpha=1.3, weights_smooth=1e-2, method='LogNormal', verbose=False, store_iteration_diagnostics=True,
+                     convergence_failure='warn')
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    pre = FL.preprocess_visibilities(u, v, V, w)
+    t1 = time.perf_counter()
+    sol = FL.fit_preprocessed(pre)
+    t2 = time.perf_counter()
+    print(json.dumps({'config': '3 (LogNormal MAP fit, N=500, 1e7 visibilities)', 'n_vis': n, 'N': N, 'map_s': t1 - t0, 'solver_s': t2 - t1,
+                      'fit_s': t2 - t0, 'iterations': int(FL.iteration_diagnostics['num_iterations']),
+                      'gram_ms': FL._vis_map.last_timing['gram_ms']}), flush=True)
+
 if '4' in which:
     n, N = 1_000_000, 300
     dht, (u, v, V, w) = data(n, N)

@@ -48,6 +48,58 @@ def test_binner_large_vs_oracle():
     assert np.array_equal(b.V.filled(0), b2.V.filled(0)) and np.array_equal(b.error.filled(0), b2.error.filled(0), equal_nan=True)
 
 
+@pytest.mark.parametrize('case', ['sorted_coarse', 'real_scalar_w', 'medium', 'wide_keys'])
+def test_binner_device_entry_vs_oracle(case):
+    """fb_uv_bin_dev (device-resident arrays) against the oracle on ragged shapes: already sorted baselines with a
+    coarse binning (a block of warps per bin), real visibilities with one scalar weight, a medium binning (2 / 4 warps
+    per bin), and more than 65536 bins (three radix passes); empty bins inside and at the end."""
+    import torch
+    from frank_b200 import _lib
+    rng = np.random.default_rng(31)
+    n, width = 400_003, 1e3
+    uv = 2e6 * np.sqrt(rng.uniform(0, 1, n))
+    V = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    w = rng.uniform(0.5, 2, n)
+    if case == 'sorted_coarse':
+        uv = np.sort(uv); width = 2.5e4                       # 80 bins
+    elif case == 'real_scalar_w':
+        V = V.real.copy(); w = np.array([1.7])
+    elif case == 'medium':
+        width = 1.2e3; uv[uv < 3e5] += 3e5                    # ~1667 bins, the first 250 empty
+    elif case == 'wide_keys':
+        width = 20.0; uv[:1000] = rng.uniform(0, 40.0, 1000)  # 1e5 bins, most of them with 0..8 points
+    uv_max = uv.max()
+    nbins = int(np.ceil(uv_max / width))
+    if nbins * width < uv_max:
+        nbins += 1
+    ref = fo.uv_bin(uv, V, np.ones_like(uv) * w, width)
+    ctx = _lib.get_context(0)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    idx, counts, sums, err = ctx.uv_bin_dev(d(uv), d(V), d(w), width, nbins)
+    idx, counts, sums, err = idx.cpu().numpy(), counts.cpu().numpy(), sums.cpu().numpy(), err.cpu().numpy()
+    assert np.array_equal(idx, ref['idx'])
+    assert np.array_equal(counts, ref['counts'])
+    assert counts.sum() == n
+    ok = counts > 0
+    assert np.allclose(sums[ok, 1], ref['weights'][ok], rtol=1e-13, atol=0)
+    assert np.allclose(sums[ok, 0] / sums[ok, 1], ref['uv'][ok], rtol=1e-13, atol=0)
+    Vb = (sums[ok, 2] + 1j * sums[ok, 3]) / sums[ok, 1]
+    assert np.max(np.abs(Vb - ref['V'][ok])) <= 1e-12 * np.max(np.abs(ref['V'][ok]))
+    assert np.all(sums[~ok] == 0) and np.all(err[~ok] == 0)
+    # the host entry point goes through the same kernels: identical bits
+    idx2, counts2, sums2, err2 = ctx.uv_bin(uv, V, np.ones_like(uv) * w if w.size > 1 else w, width, nbins)
+    assert np.array_equal(idx2, idx) and np.array_equal(counts2, counts)
+    assert np.array_equal(sums2, sums) and np.array_equal(err2, err)
+    # variance sums against a direct evaluation with the device's own means
+    many = counts > 1
+    mu = np.zeros(nbins, dtype=complex); mu[ok] = Vb
+    ww = (np.ones_like(uv) * w) ** 2
+    e_re = np.bincount(idx, weights=ww * (np.real(V) - mu.real[idx]) ** 2, minlength=nbins)
+    e_im = np.bincount(idx, weights=ww * (np.imag(V) - mu.imag[idx]) ** 2, minlength=nbins)
+    assert np.allclose(err[many, 0], e_re[many], rtol=1e-10, atol=0)
+    assert np.allclose(err[many, 1], e_im[many], rtol=1e-10, atol=1e-300)
+
+
 def test_estimate_weights_vs_reference_golden(golden):
     """estimate_weights on top of the GPU binner against the unmodified reference (tests/golden/make_golden.py):
     bin membership is exact, so the weights agree to the round-off of the per-bin variance sums."""
