@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libfrankb200.so')
 
-FB_E_QRANGE, FB_E_NOTPD, FB_E_BADP = 1, 2, 3
+FB_E_QRANGE, FB_E_NOTPD, FB_E_BADP, FB_E_NOCONV = 1, 2, 3, 4
 MODEL_CODE = {'opt_thick': 0, 'opt_thin': 1, 'debris': 2}
 
 
@@ -44,6 +44,7 @@ _SIGNATURES = {
     'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_debug_j0_far': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
+    'fb_gaussian_svd': ([_c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_predict_visibilities': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
     'fb_uv_max': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_uv_bin': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
@@ -190,6 +191,19 @@ class Context(object):
         self.check(rc, 'fb_gaussian_fit')
         return mu, chol, info, rc
 
+    def gaussian_svd(self, M, p=None):
+        """fb_gaussian_svd: U, s, Vt of D^-1 = M (+ Y^T diag(1/p) Y) as scipy.linalg.svd would return them."""
+        N = M.shape[0]
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        pp = None if p is None else np.ascontiguousarray(p, dtype=np.float64).reshape(N)
+        U, s, Vt = np.empty((N, N)), np.empty(N), np.empty((N, N))
+        sweeps = np.zeros(1, dtype=np.int32)
+        rc = self.check(self._lib.fb_gaussian_svd(self._h, _ptr(M), _ptr(pp), int(p is not None), _ptr(U), _ptr(s), _ptr(Vt),
+                                                  _ptr(sweeps)), 'fb_gaussian_svd')
+        if rc == FB_E_NOCONV:
+            raise np.linalg.LinAlgError("SVD did not converge")
+        return U, s, Vt, int(sweeps[0])
+
     def frank_normal_loop(self, M, j, p_init, alpha, p0, Tinv, tol, max_iter, want_chol=True, hist_cap=0):
         """fb_frank_normal_loop for B hyper-parameter points.  Returns a dict."""
         N = M.shape[0]
@@ -203,8 +217,14 @@ class Context(object):
         p = np.empty((B, N)); mu = np.empty((B, N))
         chol = np.empty((B, N, N)) if want_chol else None
         niter = np.zeros(B, dtype=np.int32); conv = np.zeros(B, dtype=np.int32); info = np.zeros(B, dtype=np.int32)
-        hp = np.zeros((B, hist_cap, N)) if hist_cap > 0 else None
-        hm = np.zeros((B, hist_cap, N)) if hist_cap > 0 else None
+        hp = hm = None
+        if hist_cap > 0:
+            # history buffers are kept across calls (callers copy the rows they keep): a fresh multi-megabyte
+            # allocation per fit costs page faults that, on a busy host, showed up as 0.1-0.8 s of jitter
+            if getattr(self, '_hist_shape', None) != (B, hist_cap, N):
+                self._hist = (np.zeros((B, hist_cap, N)), np.zeros((B, hist_cap, N)))
+                self._hist_shape = (B, hist_cap, N)
+            hp, hm = self._hist
         rc = self._lib.fb_frank_normal_loop(self._h, B, _ptr(M), _ptr(j), _ptr(p_init), _ptr(alpha), _ptr(p0), _ptr(Tinv),
                                             float(tol), int(max_iter), _ptr(p), _ptr(mu), _ptr(chol), _ptr(niter),
                                             _ptr(conv), _ptr(info), _ptr(hp), _ptr(hm), int(hist_cap))

@@ -14,6 +14,7 @@
 // einsum('ij,ji->i', Y, cho_solve(Y.T)) up to round-off).
 #include "fb_common.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <string>
 
@@ -789,9 +790,18 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     FB_CUDA(cudaMemcpyAsync(ctx->sv_p0, host_p0, sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
     FB_CUDA(cudaMemcpyAsync(ctx->sv_Tinv, host_Tinv, sizeof(double) * B * N * N, cudaMemcpyHostToDevice, ctx->stream));
     double *d_hist_p = nullptr, *d_hist_mu = nullptr;
-    if (hist_cap > 0 && host_hist_p && host_hist_mu) {
-        FB_CUDA(cudaMalloc(&d_hist_p, sizeof(double) * (size_t)B * hist_cap * N));
-        FB_CUDA(cudaMalloc(&d_hist_mu, sizeof(double) * (size_t)B * hist_cap * N));
+    if (hist_cap > 0 && host_hist_p && host_hist_mu) {         // iteration history: workspace kept across calls
+        const size_t need = (size_t)B * hist_cap * N;
+        if (need > ctx->sv_hist_cap) {
+            if (ctx->sv_hist) FB_CUDA(cudaFree(ctx->sv_hist));
+            ctx->sv_hist = nullptr;
+            ctx->sv_hist_cap = 0;
+            FB_CUDA(cudaMalloc(&ctx->sv_hist, sizeof(double) * 2 * need));
+            ctx->sv_hist_cap = need;
+        }
+        d_hist_p = ctx->sv_hist;
+        d_hist_mu = ctx->sv_hist + need;
+        FB_CUDA(cudaMemsetAsync(ctx->sv_hist, 0, sizeof(double) * 2 * need, ctx->stream));
     }
     const int nb = ((int)N + NB - 1) / NB;
     rc = allow_build_smem(ctx);
@@ -805,16 +815,21 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     if (!ctx->stream2) FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     if (!ctx->fev[0]) { FB_CUDA(cudaEventCreateWithFlags(&ctx->fev[0], cudaEventDisableTiming)); FB_CUDA(cudaEventCreateWithFlags(&ctx->fev[1], cudaEventDisableTiming)); }
 
+    const char *fork_env = getenv("FB_SOLVER_FORK");
+    const bool fork = !(fork_env && fork_env[0] == '0');
     auto enqueue_iteration = [&]() -> int {
-        FB_CUDA(cudaEventRecord(ctx->fev[0], ctx->stream));                    // fork
-        FB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->fev[0], 0));
-        int r = launch_solve(ctx, B, d_active, ctx->stream2);                  // mu of the current factor
+        cudaStream_t side = fork ? ctx->stream2 : ctx->stream;
+        if (fork) {
+            FB_CUDA(cudaEventRecord(ctx->fev[0], ctx->stream));                // fork
+            FB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->fev[0], 0));
+        }
+        int r = launch_solve(ctx, B, d_active, side);                          // mu of the current factor
         if (r) return r;
-        if (d_hist_mu) k_copy_hist_mu<<<B, 256, 0, ctx->stream2>>>((int)N, ctx->sv_mu, d_count, d_active, d_hist_mu, hist_cap);
-        FB_CUDA(cudaEventRecord(ctx->fev[1], ctx->stream2));
+        if (d_hist_mu) k_copy_hist_mu<<<B, 256, 0, side>>>((int)N, ctx->sv_mu, d_count, d_active, d_hist_mu, hist_cap);
+        if (fork) FB_CUDA(cudaEventRecord(ctx->fev[1], ctx->stream2));
         r = launch_tr2(ctx, B, d_active);                                      // Tr2 of the current factor
         if (r) return r;
-        FB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->fev[1], 0));             // join
+        if (fork) FB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->fev[1], 0));   // join
         k_ps_update<<<B, 1024, sizeof(double) * 2 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
                                                                      ctx->sv_p0, ctx->sv_Tinv, tol, max_iter, ctx->sv_p,
                                                                      d_active, d_count, d_conv, d_hist_p, hist_cap);
@@ -835,6 +850,8 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
         if (ce != cudaSuccess) FB_FAIL(-40, std::string("graph capture failed: ") + cudaGetErrorString(ce));
     }
     FB_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+    const bool trace = getenv("FB_SOLVER_TRACE") != nullptr;
+    if (trace) { FB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream)); }
 
     int n_active = B, it = 0;
     const int poll = 32;      // iterations enqueued between two looks at the active count (gated-off iterations cost ~30 us each)
@@ -842,6 +859,13 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
         for (int sidx = 0; sidx < poll; sidx++, it++) FB_CUDA(cudaGraphLaunch(gexec, ctx->stream));
         FB_CUDA(cudaMemcpyAsync(&n_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (trace) {
+        float ms = 0;
+        FB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        FB_CUDA(cudaEventSynchronize(ctx->ev[1]));
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        fprintf(stderr, "[fb_solve trace] fork=%d  %d graph launches  %.3f ms on the device (%.1f us per iteration)\n", (int)fork, it, ms, 1e3 * ms / it);
     }
     cudaGraphExecDestroy(gexec);
     cudaGraphDestroy(graph);
@@ -861,7 +885,6 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
         FB_CUDA(cudaMemcpyAsync(host_hist_mu, d_hist_mu, sizeof(double) * (size_t)B * hist_cap * N, cudaMemcpyDeviceToHost, ctx->stream));
     }
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (d_hist_p) { cudaFree(d_hist_p); cudaFree(d_hist_mu); }
     int worst = 0;
     for (int b = 0; b < B; b++) {
         if (host_converged) host_converged[b] = conv[b];
@@ -870,6 +893,180 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     }
     if (worst) ctx->err = "Cholesky factorisation met a non-positive pivot";
     return worst;
+}
+
+
+// ---- SVD fallback of GaussianModel._fit (frank/statistical_models.py:747-755) --------------------------------------------
+// The reference falls back to scipy.linalg.svd(D^-1) when the Cholesky factorisation fails.  D^-1 is symmetric, so its
+// SVD is its eigen-decomposition with the signs folded into U.  Here: one-sided (Hestenes) Jacobi on the device.  G
+// starts as D^-1 (column j = D^-1 e_j), V as I; plane rotations applied to the columns of both make the columns of
+// G = D^-1 V mutually orthogonal, after which  |lambda_i| = ||g_i||,  u_i = g_i / ||g_i||,  v_i = V[:, i].  One launch
+// per round of a round-robin schedule (N/2 disjoint column pairs, one CTA per pair); a sweep is N-1 rounds.
+namespace {
+
+constexpr int JAC_THREADS = 128;
+
+__global__ void __launch_bounds__(JAC_THREADS)
+k_jacobi_round(int N, int m, int round, double tol, double *__restrict__ G, double *__restrict__ V, int *__restrict__ rotated)
+{
+    // pair `blockIdx.x` of round `round` among m (even) players: circle method, player m-1 fixed
+    int p, q;
+    if (blockIdx.x == 0) { p = m - 1; q = round; }
+    else { p = (round + blockIdx.x) % (m - 1); q = (round - (int)blockIdx.x + (m - 1)) % (m - 1); }
+    if (p >= N || q >= N) return;                      // the padding player of an odd N
+    if (p > q) { int t = p; p = q; q = t; }
+    double *gp = G + (size_t)p * N, *gq = G + (size_t)q * N;      // columns are stored contiguously
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < N; i += JAC_THREADS) {
+        const double x = gp[i], y = gq[i];
+        a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c);
+    }
+    __shared__ double red[3][JAC_THREADS / 32];
+    __shared__ double rot[2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; red[2][threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double A = 0.0, B = 0.0, C = 0.0;
+        for (int w = 0; w < JAC_THREADS / 32; w++) { A += red[0][w]; B += red[1][w]; C += red[2][w]; }
+        double cs = 1.0, sn = 0.0;
+        if (A > 0.0 && B > 0.0 && fabs(C) > tol * sqrt(A) * sqrt(B)) {
+            const double zeta = (B - A) / (2.0 * C);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            cs = 1.0 / sqrt(1.0 + t * t);
+            sn = cs * t;
+            *rotated = 1;
+        }
+        rot[0] = cs; rot[1] = sn;
+    }
+    __syncthreads();
+    const double cs = rot[0], sn = rot[1];
+    if (sn == 0.0) return;
+    double *vp = V + (size_t)p * N, *vq = V + (size_t)q * N;
+    for (int i = threadIdx.x; i < N; i += JAC_THREADS) {
+        const double x = gp[i], y = gq[i];
+        gp[i] = cs * x - sn * y;
+        gq[i] = sn * x + cs * y;
+        const double vx = vp[i], vy = vq[i];
+        vp[i] = cs * vx - sn * vy;
+        vq[i] = sn * vx + cs * vy;
+    }
+}
+
+__global__ void k_set_identity(int N, double *__restrict__ V)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)N * N) V[i] = (i / N == i % N) ? 1.0 : 0.0;
+}
+
+// per column: s_i = ||g_i||, sign_i = sign(v_i . g_i) (= sign of the eigenvalue), u_i = g_i / s_i (v_i * sign when s_i = 0)
+__global__ void __launch_bounds__(JAC_THREADS)
+k_jacobi_finish(int N, double *__restrict__ G, const double *__restrict__ V, double *__restrict__ sval, double *__restrict__ sgn)
+{
+    const int col = blockIdx.x;
+    double *g = G + (size_t)col * N;
+    const double *v = V + (size_t)col * N;
+    double a = 0.0, d = 0.0;
+    for (int i = threadIdx.x; i < N; i += JAC_THREADS) { a = fma(g[i], g[i], a); d = fma(g[i], v[i], d); }
+    __shared__ double red[2][JAC_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); d += __shfl_xor_sync(0xffffffffu, d, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = d; }
+    __syncthreads();
+    a = 0.0; d = 0.0;
+    for (int w = 0; w < JAC_THREADS / 32; w++) { a += red[0][w]; d += red[1][w]; }
+    const double nrm = sqrt(a);
+    if (threadIdx.x == 0) { sval[col] = nrm; sgn[col] = d < 0.0 ? -1.0 : 1.0; }
+    for (int i = threadIdx.x; i < N; i += JAC_THREADS) g[i] = nrm > 0.0 ? g[i] / nrm : v[i];
+}
+
+}  // namespace
+
+extern "C" int fb_gaussian_svd(fb_ctx *ctx, const double *host_M, const double *host_p, int has_prior, double *host_U,
+                               double *host_s, double *host_Vt, int *host_sweeps)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0 || !ctx->d_Y) FB_FAIL(-30, "fb_gaussian_svd: fb_dht_setup (with Ycoef) has not been called");
+    if (!host_M || !host_U || !host_s || !host_Vt) FB_FAIL(-31, "fb_gaussian_svd: bad arguments");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    int rc = ensure_solver_ws(ctx, 1);
+    if (rc) return rc;
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_M, host_M, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
+    const int nb = ((int)N + NB - 1) / NB;
+    rc = allow_build_smem(ctx);
+    if (rc) return rc;
+    if (has_prior) {
+        if (!host_p) FB_FAIL(-32, "fb_gaussian_svd: power spectrum missing");
+        for (size_t i = 0; i < N; i++)
+            if (!(host_p[i] > 0.0)) FB_FAIL(FB_E_BADP, "bad value in power spectrum");
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+        k_build_dinv<<<dim3(nb * (nb + 1) / 2, 1), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, nullptr, ctx->sv_D);
+        FB_CUDA(cudaGetLastError());
+    } else {
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_D, ctx->sv_M, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    // k_build_dinv fills the upper triangle (what the Cholesky kernels read): mirror it on the host side of this
+    // rarely taken path, then run the rotations on the full symmetric matrix
+    std::vector<double> A(N * N);
+    FB_CUDA(cudaMemcpyAsync(A.data(), ctx->sv_D, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < N; i++)
+        for (size_t k = i + 1; k < N; k++) A[k * N + i] = A[i * N + k];
+    double *d_G = nullptr, *d_V = nullptr, *d_s = nullptr;
+    int *d_flag = nullptr;
+    FB_CUDA(cudaMalloc(&d_G, sizeof(double) * N * N));
+    FB_CUDA(cudaMalloc(&d_V, sizeof(double) * N * N));
+    FB_CUDA(cudaMalloc(&d_s, sizeof(double) * 2 * N));
+    FB_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    auto cleanup = [&]() { cudaFree(d_G); cudaFree(d_V); cudaFree(d_s); cudaFree(d_flag); };
+    int status = 0, sweeps = 0;
+    do {
+        if (cudaMemcpyAsync(d_G, A.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { status = -33; break; }
+        k_set_identity<<<(unsigned)((N * N + 255) / 256), 256, 0, ctx->stream>>>((int)N, d_V);
+        const int m = (int)((N + 1) / 2 * 2);
+        const double tol = sqrt((double)N) * 2.220446049250313e-16;            // LAPACK dgesvj's orthogonality threshold
+        const int max_sweeps = 60;
+        int rotated = 1;
+        while (rotated && sweeps < max_sweeps) {
+            cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream);
+            for (int r = 0; r < m - 1; r++)
+                k_jacobi_round<<<m / 2, JAC_THREADS, 0, ctx->stream>>>((int)N, m, r, tol, d_G, d_V, d_flag);
+            if (cudaMemcpyAsync(&rotated, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess) { status = -34; break; }
+            sweeps++;
+        }
+        if (status) break;
+        if (rotated) { status = FB_E_NOCONV; }
+        k_jacobi_finish<<<(unsigned)N, JAC_THREADS, 0, ctx->stream>>>((int)N, d_G, d_V, d_s, d_s + N);
+        std::vector<double> G(N * N), V(N * N), sv(2 * N);
+        if (cudaMemcpyAsync(G.data(), d_G, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(V.data(), d_V, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(sv.data(), d_s, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { status = status ? status : -35; break; }
+        // singular values in descending order, as LAPACK returns them (stable: ties keep the column order)
+        std::vector<int> order(N);
+        for (size_t i = 0; i < N; i++) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sv[x] > sv[y]; });
+        for (size_t i = 0; i < N; i++) {
+            const int c = order[i];
+            host_s[i] = sv[c];
+            for (size_t k = 0; k < N; k++) {
+                host_U[k * N + i] = G[(size_t)c * N + k];                       // U[:, i] = u_c
+                host_Vt[i * N + k] = V[(size_t)c * N + k];                      // Vt[i, :] = v_c
+            }
+        }
+    } while (0);
+    cleanup();
+    if (host_sweeps) *host_sweeps = sweeps;
+    if (status == FB_E_NOCONV) ctx->err = "Jacobi SVD did not converge";
+    else if (status < 0) ctx->err = "fb_gaussian_svd: CUDA error";
+    return status;
 }
 
 

@@ -328,10 +328,16 @@ class GaussianModel(object):
         ctx = _lib.get_context(self._device)
         ctx.dht_setup(self._DHT)
         mu, chol, info, rc = ctx.gaussian_fit(self._M, self._j, None if self._p is None else self._p[0])
+        self._Dsvd = None
         if rc == _lib.FB_E_NOTPD:
-            # the reference falls back to an SVD pseudo-inverse here (statistical_models.py:747-755)
-            raise np.linalg.LinAlgError("D^-1 = M + S^-1 is not positive definite (pivot {}); the SVD "
-                                        "pseudo-inverse fallback of the reference is not provided".format(int(info[0])))
+            # SVD pseudo-inverse fallback (statistical_models.py:747-755): U, s, V of D^-1 from the device (one-sided
+            # Jacobi, fb_gaussian_svd); s1 and mu formed as in the reference
+            U, s, V, _ = ctx.gaussian_svd(self._M, None if self._p is None else self._p[0])
+            s1 = np.where(s > 0, 1. / np.where(s > 0, s, 1.), 0)
+            self._Dsvd = U, s1, V
+            self._U = None
+            self._mu = np.dot(V.T, np.multiply(np.dot(U.T, self._j), s1))
+            return
         self._mu = mu[0]
         self._U = np.triu(chol[0])
 
@@ -346,6 +352,10 @@ class GaussianModel(object):
 
     def Dsolve(self, b):
         r"""D b through the GPU-computed Cholesky factor (post-fit helper, statistical_models.py:762-781)."""
+        if getattr(self, '_Dsvd', None) is not None:                                   # :778-781
+            U, s1, V = self._Dsvd
+            b = np.asarray(b)
+            return np.dot(V.T, (np.dot(U.T, b).T * s1).T)
         import scipy.linalg
         return scipy.linalg.cho_solve((self._U, False), b)
 

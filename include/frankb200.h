@@ -11,6 +11,7 @@
  *   FB_E_NOTPD   Cholesky hit a non-positive pivot (reference: numpy.linalg.LinAlgError -> SVD fallback,
  *                frank/statistical_models.py:747)
  *   FB_E_BADP    non-positive / NaN power spectrum (reference ValueError, statistical_models.py:688-698)
+ *   FB_E_NOCONV  the Jacobi SVD of the fallback path did not converge (scipy.linalg.svd raises LinAlgError)
  * Nothing throws or aborts across the ABI.  A context is bound to one device; calls on one context are
  * serialised on its stream and are complete (host-visible) when the function returns unless stated.
  * "dev" pointers are device memory on the context's device, "host" pointers are host memory.
@@ -25,6 +26,7 @@ extern "C" {
 #define FB_E_QRANGE 1
 #define FB_E_NOTPD 2
 #define FB_E_BADP 3
+#define FB_E_NOCONV 4
 
 #define FB_MODEL_OPT_THICK 0
 #define FB_MODEL_OPT_THIN 1
@@ -111,6 +113,14 @@ int fb_debug_prepped(fb_ctx *ctx, int64_t n, double *host_a, double *host_kz, do
  * FB_E_BADP for a non-positive / NaN spectrum (:688-698). */
 int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p, int has_prior,
                     double *host_mu, double *host_chol, int *host_info);
+
+/* SVD fallback of GaussianModel._fit (frank/statistical_models.py:747-755: scipy.linalg.svd(Dinv) when cho_factor
+ * raises LinAlgError).  D^-1 as above (one power spectrum); outputs U [N*N], s [N] (descending), Vt [N*N] with
+ * D^-1 = U diag(s) Vt, computed by one-sided Jacobi rotations on the device (D^-1 is symmetric: s_i = |lambda_i|,
+ * the sign of lambda_i is folded into U).  The caller forms s1 = where(s > 0, 1/s, 0) and mu = Vt^T (s1 * (U^T j))
+ * exactly as the reference does.  sweeps (optional) receives the number of Jacobi sweeps. */
+int fb_gaussian_svd(fb_ctx *ctx, const double *host_M, const double *host_p, int has_prior, double *host_U,
+                    double *host_s, double *host_Vt, int *host_sweeps);
 
 /* ---- FrankFitter._fit power-spectrum loop, Normal method (frank/radial_fitters.py:765-785) --------
  * Device-resident loop, batched over B hyper-parameter points sharing M and j:

@@ -20,6 +20,8 @@ whatever the reference's public API returns for them:
   uvbin.npz          UVDataBinner bin indices, counts, means, errors (utilities.py:180-400)
   estweights.npz     estimate_weights in its five call forms (utilities.py:515-631)
   geomfit.npz        FitGeometryGaussian / FitGeometryFourierBessel results (geometry.py:404-763)
+  svd_fallback.npz   GaussianModel solutions through the reference's SVD pseudo-inverse branch (indefinite and
+                     rank-deficient systems, statistical_models.py:747-755)
   gauss_kat.npz      the reference's analytic Gaussian Hankel-pair test inputs (tests.py:37-130)
 """
 import os
@@ -126,7 +128,41 @@ def gen_estweights():
     np.savez_compressed(os.path.join(OUT, 'estweights.npz'), u=ue, v=ve, V=Ve, **ew)
 
 
+def gen_svd_fallback():
+    """GaussianModel on systems whose Cholesky factorisation fails, so that the reference takes its SVD
+    pseudo-inverse branch (statistical_models.py:747-755): (a) a well-conditioned symmetric INDEFINITE M (no prior),
+    (b) the same M plus a prior p, still indefinite, (c) a rank-deficient M = H^T W H from fewer visibilities than
+    collocation points (FourierBesselFitter, no prior) -- its solution is round-off dominated along the null space,
+    so only the fitted visibilities H mu are stored for comparison."""
+    from frank.statistical_models import GaussianModel
+    N = 40
+    dht = DiscreteHankelTransform(1.6 / rad_to_arcsec, N)
+    rng = np.random.default_rng(99)
+    Q, _ = np.linalg.qr(rng.standard_normal((N, N)))
+    lam = rng.uniform(1, 10, N) * np.where(rng.uniform(size=N) < 0.3, -1, 1)
+    M = (Q * lam) @ Q.T
+    M = 0.5 * (M + M.T)
+    j = rng.standard_normal(N)
+    ga = GaussianModel(dht, M, j)
+    assert ga._Dsvd is not None
+    p = np.full(N, 1e3) * rng.uniform(0.5, 2, N)
+    gb = GaussianModel(dht, M, j, p=p)
+    assert gb._Dsvd is not None
+    # (c)
+    u, v, V, w, g = synthetic(25, N, seed=5)
+    FB = FourierBesselFitter(1.6, N, g, verbose=False)
+    sol = FB.fit(u, v, V, w)
+    assert sol._fit._Dsvd is not None
+    np.savez_compressed(os.path.join(OUT, 'svd_fallback.npz'), N=N, M=M, j=j, p=p, mu_a=ga.mean, s1_a=ga._Dsvd[1],
+                        Dj_a=ga.Dsolve(j), mu_b=gb.mean, s1_b=gb._Dsvd[1],
+                        u=u, v=v, V=V, w=w, geom=[g.inc, g.PA, g.dRA, g.dDec], Mc=FB._M, jc=FB._j, mu_c=sol.mean,
+                        Vfit_c=sol.predict(u, v), s1_c=sol._fit._Dsvd[1])
+
+
 def main():
+    if sys.argv[1:] == ['svd_fallback']:
+        gen_svd_fallback()
+        return
     if sys.argv[1:] == ['estweights']:           # regenerate this fixture alone
         gen_estweights()
         return

@@ -274,3 +274,48 @@ def test_fit_geometry_fourier_bessel(golden):
     gf2.fit(u, v, V, w)
     assert (gf2.inc, gf2.PA) == (32.0, 47.0)
     assert np.all(np.abs(np.array([gf2.dRA, gf2.dDec]) - g['fb_fixed_incpa'][2:]) <= 2e-7)
+
+
+def test_svd_fallback_vs_reference_golden(fb, golden):
+    """GaussianModel on systems whose Cholesky factorisation fails: the reference takes its SVD pseudo-inverse
+    branch (statistical_models.py:747-755); here the SVD comes from the device (one-sided Jacobi, fb_gaussian_svd).
+    Indefinite, well-conditioned systems (with and without a prior) are compared entry by entry; the rank-deficient
+    M = H^T W H of 25 visibilities at N = 40 is round-off dominated along its null space (the reference itself
+    moves by O(1) when its SVD is swapped for an eigen-decomposition), so there the singular values, the residual
+    and the range-space component of the solution are compared."""
+    g = golden('svd_fallback.npz')
+    N = int(g['N'])
+    dht = fb.DHT(1.6 / fb.r2a, N)
+    M, j, p = g['M'], g['j'], g['p']
+    ctx = fb.lib.get_context(0)
+    ctx.dht_setup(dht)
+    U, s, Vt, sweeps = ctx.gaussian_svd(M)
+    assert 1 <= sweeps < 30
+    assert np.all(np.diff(s) <= 0) and np.all(s > 0)
+    nM = np.linalg.norm(M, 2)
+    assert np.max(np.abs((U * s) @ Vt - M)) <= 1e-13 * nM
+    assert np.max(np.abs(U.T @ U - np.eye(N))) <= 1e-13 and np.max(np.abs(Vt @ Vt.T - np.eye(N))) <= 1e-13
+    assert np.allclose(np.sort(1 / s), np.sort(g['s1_a']), rtol=1e-12, atol=0)
+    for tag, kw in [('a', {}), ('b', {'p': p})]:
+        gm = fb.GaussianModel(dht, M, j, **kw)
+        assert gm._Dsvd is not None
+        ref = g['mu_' + tag]
+        assert np.max(np.abs(gm.mean - ref)) <= 1e-11 * np.max(np.abs(ref)), tag
+        assert np.allclose(np.sort(gm._Dsvd[1]), np.sort(g['s1_' + tag]), rtol=1e-11, atol=0)
+    gm = fb.GaussianModel(dht, M, j)
+    assert np.max(np.abs(gm.Dsolve(j) - g['Dj_a'])) <= 1e-11 * np.max(np.abs(g['Dj_a']))
+    assert np.max(np.abs(gm.covariance @ M - np.eye(N))) <= 1e-11          # Dsolve of a matrix: D^-1's inverse
+    # (c) rank-deficient mapping through the public fitter
+    FB = fb.FourierBesselFitter(1.6, N, geom_of(fb, g), verbose=False)
+    sol = FB.fit(g['u'], g['v'], g['V'], g['w'])
+    assert sol._fit._Dsvd is not None
+    Mc, jc = g['Mc'], g['jc']
+    rank = 25
+    s_ref = np.sort(1 / g['s1_c'])[::-1]
+    s_got = np.sort(1 / sol._fit._Dsvd[1])[::-1]
+    assert np.allclose(s_got[:rank], s_ref[:rank], rtol=1e-9, atol=0)
+    assert np.all(s_got[rank:] <= 1e-13 * s_got[0])
+    assert np.max(np.abs(Mc @ sol.mean - jc)) <= 1e-10 * np.max(np.abs(jc))
+    _, _, Vh = np.linalg.svd(Mc)
+    pr_got, pr_ref = Vh[:rank] @ sol.mean, Vh[:rank] @ g['mu_c']
+    assert np.max(np.abs(pr_got - pr_ref)) <= 1e-7 * np.max(np.abs(pr_ref))
