@@ -46,6 +46,7 @@ _SIGNATURES = {
     'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
     'fb_gaussian_svd': ([_c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_predict_visibilities': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
+    'fb_apply_correction_dev': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_uv_max': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_uv_bin': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_uv_bin_dev': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
@@ -150,6 +151,28 @@ class Context(object):
                 _ptr(M), _ptr(j), _ptr(H0), _ptr(qmm))
         self.check(rc, 'fb_map_visibilities')
         return rc, qmm[0], qmm[1]
+
+    def apply_correction_dev(self, u, v, V, geom, want_q=False):
+        """fb_apply_correction_dev on torch CUDA tensors: returns (up, vp, wp, Vp[, q]) as device tensors (Vp None when V
+        is None)."""
+        import torch
+        for t in (u, v):
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float64):
+                raise ValueError("apply_correction_dev: contiguous float64 CUDA tensors expected")
+        n = u.numel()
+        Vr = Vp = None
+        if V is not None:
+            if not (V.is_cuda and V.is_contiguous() and V.dtype == torch.complex128):
+                raise ValueError("apply_correction_dev: V must be a contiguous complex128 CUDA tensor")
+            Vr = torch.view_as_real(V)
+            Vp = torch.empty_like(V)
+        up, vp, wp = torch.empty_like(u), torch.empty_like(u), torch.empty_like(u)
+        q = torch.empty_like(u) if want_q else None
+        torch.cuda.current_stream(u.device).synchronize()
+        self.check(self._lib.fb_apply_correction_dev(self._h, n, _ptr(u), _ptr(v), _ptr(Vr), ctypes.byref(geom), _ptr(up), _ptr(vp),
+                                                     _ptr(wp), None if Vp is None else _ptr(torch.view_as_real(Vp)), _ptr(q)),
+                   'fb_apply_correction_dev')
+        return (up, vp, wp, Vp, q) if want_q else (up, vp, wp, Vp)
 
     def timer_start(self):
         self.check(self._lib.fb_timer_start(self._h), 'fb_timer_start')

@@ -120,6 +120,48 @@ k_prep(int64_t n, const double *__restrict__ u, const double *__restrict__ v,
     }
 }
 
+// SourceGeometry.apply_correction as a stand-alone pass (geometry.py:202-236) for callers that want the corrected
+// arrays themselves (uv binning, plotting of deprojected visibilities): the same single correctly rounded operations
+// as k_prep, full complex quotient V / (cos phi + i sin phi) by NumPy's Smith division, optional q = hypot(u', v')
+// with the glibc kernel (bit-equal to np.hypot).  32 B read, up to 48 B written per visibility, coalesced.
+__global__ void __launch_bounds__(256)
+k_apply_correction(int64_t n, const double *__restrict__ u, const double *__restrict__ v, const double2 *__restrict__ V,
+                   fb_geometry g, double *__restrict__ up_out, double *__restrict__ vp_out, double *__restrict__ wp_out,
+                   double2 *__restrict__ Vp_out, double *__restrict__ q_out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ui = u[i], vi = v[i];
+        if (V && Vp_out) {
+            const double2 Vi = V[i];
+            const double phi = __dadd_rn(__dmul_rn(ui, g.a_ra), __dmul_rn(vi, g.a_dec));       // geometry.py:72
+            double s, c;
+            sincos(phi, &s, &c);
+            double re, im;
+            if (fabs(c) >= fabs(s)) {
+                const double rat = __ddiv_rn(s, c);
+                const double scl = __ddiv_rn(1.0, __dadd_rn(c, __dmul_rn(s, rat)));
+                re = __dmul_rn(__dadd_rn(Vi.x, __dmul_rn(Vi.y, rat)), scl);
+                im = __dmul_rn(__dsub_rn(Vi.y, __dmul_rn(Vi.x, rat)), scl);
+            } else {
+                const double rat = __ddiv_rn(c, s);
+                const double scl = __ddiv_rn(1.0, __dadd_rn(s, __dmul_rn(c, rat)));
+                re = __dmul_rn(__dadd_rn(__dmul_rn(Vi.x, rat), Vi.y), scl);
+                im = __dmul_rn(__dsub_rn(__dmul_rn(Vi.y, rat), Vi.x), scl);
+            }
+            Vp_out[i] = make_double2(re, im);
+        }
+        double up = __dsub_rn(__dmul_rn(ui, g.cos_pa), __dmul_rn(vi, g.sin_pa));               // geometry.py:122-131
+        const double vp = __dadd_rn(__dmul_rn(ui, g.sin_pa), __dmul_rn(vi, g.cos_pa));
+        const double wp = __dmul_rn(up, g.sin_inc);
+        up = __dmul_rn(up, g.cos_inc);
+        if (up_out) up_out[i] = up;
+        if (vp_out) vp_out[i] = vp;
+        if (wp_out) wp_out[i] = wp;
+        if (q_out) q_out[i] = hypot_glibc(up, vp);
+    }
+}
+
 // single block: fixed-order reduction of the per-block partials; out = {0.5*sum, qmin, qmax}
 __global__ void __launch_bounds__(1024) k_prep_reduce(int nblocks, const double *__restrict__ red, double *__restrict__ out)
 {
@@ -174,6 +216,22 @@ int fb_reserve_prep(fb_ctx *ctx, int64_t n_pad)
         ctx->red_cap = cap;
     }
     return fb_reserve_sort(ctx, n_pad);
+}
+
+extern "C" int fb_apply_correction_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v, const double *dev_V_reim,
+                                       const fb_geometry *geom, double *dev_up, double *dev_vp, double *dev_wp, double *dev_Vp_reim,
+                                       double *dev_q)
+{
+    if (!ctx) return -1;
+    if (n < 0 || !dev_u || !dev_v || !geom) FB_FAIL(-12, "fb_apply_correction_dev: bad arguments");
+    if (n == 0) return 0;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 32);
+    k_apply_correction<<<grid, 256, 0, ctx->stream>>>(n, dev_u, dev_v, (const double2 *)dev_V_reim, *geom, dev_up, dev_vp, dev_wp,
+                                                      (double2 *)dev_Vp_reim, dev_q);
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,

@@ -17,6 +17,10 @@ __all__ = ['apply_phase_shift', 'deproject', 'rescale_total_flux', 'SourceGeomet
            'FitGeometryGaussian', 'FitGeometryFourierBessel']
 
 
+def _is_cuda_tensor(x):
+    return type(x).__module__.startswith('torch') and getattr(x, 'is_cuda', False)
+
+
 def _fix_inc_and_PA_ranges(inc, PA):
     """Make sure the inclination and PA are in the ranges [0,90] and [0-180] (frank/geometry.py:33-39)."""
     inc = inc % 180
@@ -61,6 +65,10 @@ class SourceGeometry(object):
         self._inc, self._PA, self._dRA, self._dDec = inc, PA, dRA, dDec
 
     def apply_correction(self, u, v, V, use3D=False):
+        if _is_cuda_tensor(u):                      # device-resident arrays: one fused pass (fb_prep.cu, k_apply_correction)
+            from frank_b200 import _lib
+            up, vp, wp, Vp = _lib.get_context(u.device.index).apply_correction_dev(u, v, V, self.device_scalars())
+            return (up, vp, wp, Vp) if use3D else (up, vp, Vp)
         Vp = apply_phase_shift(u, v, V, self._dRA, self._dDec, inverse=True)
         up, vp, wp = deproject(u, v, self._inc, self._PA)
         return (up, vp, wp, Vp) if use3D else (up, vp, Vp)
@@ -70,6 +78,10 @@ class SourceGeometry(object):
         return up, vp, apply_phase_shift(up, vp, V, self._dRA, self._dDec, inverse=False)
 
     def deproject(self, u, v, use3D=False):
+        if _is_cuda_tensor(u):
+            from frank_b200 import _lib
+            up, vp, wp, _ = _lib.get_context(u.device.index).apply_correction_dev(u, v, None, self.device_scalars())
+            return (up, vp, wp) if use3D else (up, vp)
         out = deproject(u, v, self._inc, self._PA)
         return out if use3D else out[:2]
 

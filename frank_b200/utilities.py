@@ -20,9 +20,18 @@ class UVDataBinner(object):
     (lambda) -- as frank/utilities.py:204.  `device` selects the GPU."""
 
     def __init__(self, uv, V, weights, bin_width, device=None):
-        ctx = _lib.get_context(device)
-        uv = np.ascontiguousarray(uv, dtype=np.float64)
-        uv_max = ctx.uv_max(uv)
+        on_device = type(uv).__module__.startswith('torch') and getattr(uv, 'is_cuda', False)
+        if on_device:
+            # device-resident arrays (torch CUDA tensors): nothing but the O(nbins) results crosses to the host; the
+            # per-visibility bin index stays on the device (`_idx` is an int32 CUDA tensor)
+            import torch
+            ctx = _lib.get_context(uv.device.index if device is None else device)
+            uv = uv.contiguous()
+            uv_max = float(uv.max().item())
+        else:
+            ctx = _lib.get_context(device)
+            uv = np.ascontiguousarray(uv, dtype=np.float64)
+            uv_max = ctx.uv_max(uv)
         nbins = np.ceil(uv_max / bin_width).astype('int')                  # utilities.py:205-208
         if nbins * bin_width < uv_max:
             nbins += 1
@@ -30,9 +39,20 @@ class UVDataBinner(object):
         bins = np.arange(nbins + 1, dtype='float64') * bin_width
         self._bins, self._nbins, self._norm = bins, nbins, 1 / bin_width
         self._ctx = ctx
-        is_c = np.iscomplexobj(V)
-        w = np.ones_like(uv) * weights
-        idx, counts, sums, err = ctx.uv_bin(uv, V, w, bin_width, nbins)
+        if on_device:
+            is_c = V.is_complex()
+            V = V.contiguous()
+            if type(weights).__module__.startswith('torch'):
+                w = weights.to(dtype=torch.float64, device=uv.device).reshape(-1).contiguous()
+            else:
+                w = torch.as_tensor(np.atleast_1d(np.asarray(weights, dtype=np.float64)), device=uv.device).contiguous()
+            idx, counts, sums, err = ctx.uv_bin_dev(uv, V, w, bin_width, nbins)
+            counts, sums, err = counts.cpu().numpy(), sums.cpu().numpy(), err.cpu().numpy()
+            V = np.zeros(0, dtype=np.complex128 if is_c else np.float64)      # dtype carrier for the error array below
+        else:
+            is_c = np.iscomplexobj(V)
+            w = np.ones_like(uv) * weights
+            idx, counts, sums, err = ctx.uv_bin(uv, V, w, bin_width, nbins)
         self._idx = idx
         bin_uv, bin_wgt = sums[:, 0].copy(), sums[:, 1].copy()
         bin_vis = (sums[:, 2] + 1j * sums[:, 3]) if is_c else sums[:, 2].copy()

@@ -100,6 +100,15 @@ int fb_last_map_timing(fb_ctx *ctx, double *out4);
 int fb_timer_start(fb_ctx *ctx);
 int fb_timer_stop(fb_ctx *ctx, double *elapsed_ms);
 
+/* SourceGeometry.apply_correction (frank/geometry.py:202-236 = apply_phase_shift(inverse=True) :41-79 + deproject
+ * :82-131) as a stand-alone pass over device-resident arrays, for callers that need the corrected arrays themselves
+ * (uv binning of deprojected baselines).  Outputs (each optional, device): up, vp, wp [n]; Vp interleaved complex [2n]
+ * (needs V); q = hypot(up, vp) [n], bit-equal to np.hypot.  Same correctly rounded operation order as the mapping's
+ * pre-pass.  Returns after the stream has drained. */
+int fb_apply_correction_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v, const double *dev_V_reim,
+                            const fb_geometry *geom, double *dev_up, double *dev_vp, double *dev_wp, double *dev_Vp_reim,
+                            double *dev_q);
+
 /* Pre-passed visibilities of the most recent map call in the (baseline-sorted) order the Gram kernel reads
  * them, for parity tests of the geometry pre-pass (geometry.py:202-236): a = q * (1/Qmax) [n], kz [n],
  * Re V' [n] and perm [n] (sorted position -> index into the caller's arrays), device -> host. */

@@ -115,3 +115,43 @@ def test_estimate_weights_vs_reference_golden(golden):
     assert np.allclose(got, g['uV'], rtol=1e-11, atol=0)
     with pytest.raises(ValueError):
         estimate_weights(u)
+
+
+def test_device_pipeline_correction_then_binning():
+    """Device-resident pipeline of BASELINE.json configs[4]: SourceGeometry.apply_correction on CUDA tensors (phase
+    shift + deprojection, geometry.py:202-236), q = hypot(u', v'), UVDataBinner on the deprojected baselines -- against
+    the oracle's NumPy chain.  up, vp, wp and q are bit-equal to NumPy's; V' to a few ulp (sin / cos differ by an ulp);
+    bin indices and counts exact."""
+    import torch
+    from frank_b200 import _lib
+    from frank_b200.geometry import FixedGeometry
+    from frank_b200.utilities import UVDataBinner
+    n = 1_000_003
+    u, v, V, w, dht = fo.synthetic_disc(n, 100, analytic=True)
+    geom = FixedGeometry(30., 40., 1e-3, -2e-3)
+    up, vp, wp, Vp = fo.apply_correction(u, v, V, 30., 40., 1e-3, -2e-3)
+    q = np.hypot(up, vp)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    du, dv, dV, dw = d(u), d(v), d(V), d(w)
+    gup, gvp, gwp, gVp = geom.apply_correction(du, dv, dV, use3D=True)
+    assert np.array_equal(gup.cpu().numpy(), up) and np.array_equal(gvp.cpu().numpy(), vp) and np.array_equal(gwp.cpu().numpy(), wp)
+    assert np.max(np.abs(gVp.cpu().numpy() - Vp)) <= 4 * np.finfo(float).eps * np.max(np.abs(Vp))
+    g2 = geom.deproject(du, dv)
+    assert len(g2) == 2 and np.array_equal(g2[0].cpu().numpy(), up)
+    ctx = _lib.get_context(0)
+    *_, gq = ctx.apply_correction_dev(du, dv, None, geom.device_scalars(), want_q=True)
+    assert np.array_equal(gq.cpu().numpy(), q)                                   # glibc-exact hypot
+    ref = fo.uv_bin(q, Vp, w, 1e3)
+    b = UVDataBinner(gq, gVp, dw, 1e3)
+    assert b._idx.is_cuda and np.array_equal(b._idx.cpu().numpy(), ref['idx'])
+    assert np.array_equal(b.bin_counts.filled(0), ref['counts'])
+    ok = ~ref['mask']
+    assert np.max(np.abs(b.V.filled(0)[ok] - ref['V'][ok])) <= 1e-12 * np.max(np.abs(ref['V'][ok]))
+    assert np.max(np.abs(b.uv.filled(0)[ok] - ref['uv'][ok])) <= 1e-13 * np.max(ref['uv'][ok])
+    fin = ~np.isnan(ref['error'].real) & ok
+    e = b.error.filled(np.nan)
+    assert np.array_equal(np.isnan(e.real[ok]), np.isnan(ref['error'].real[ok]))
+    assert np.max(np.abs(e[fin] - ref['error'][fin])) <= 1e-9 * np.max(np.abs(ref['error'][fin]))
+    # host-array and device-tensor constructors run the same kernels on the same values
+    bh = UVDataBinner(q, gVp.cpu().numpy(), w, 1e3)
+    assert np.array_equal(bh.V.filled(0), b.V.filled(0)) and np.array_equal(bh.error.filled(0), b.error.filled(0), equal_nan=True)
