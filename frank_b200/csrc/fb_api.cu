@@ -42,7 +42,7 @@ int fb_ctx_destroy(fb_ctx *ctx)
                     (void *)ctx->d_rec, (void *)ctx->d_items, (void *)ctx->d_perm, (void *)ctx->d_hist, (void *)ctx->d_binstart, (void *)ctx->d_work, (void *)ctx->d_work2,
                     (void *)ctx->sv_D, (void *)ctx->sv_p, (void *)ctx->sv_mu, (void *)ctx->sv_tr2, (void *)ctx->sv_alpha,
                     (void *)ctx->sv_p0, (void *)ctx->sv_Tinv, (void *)ctx->sv_M, (void *)ctx->sv_j, (void *)ctx->sv_Z,
-                    (void *)ctx->sv_flags, (void *)ctx->sv_hist, (void *)ctx->sv_rdiag, (void *)ctx->ln_S, (void *)ctx->ln_vec})
+                    (void *)ctx->sv_flags, (void *)ctx->sv_hist, (void *)ctx->sv_rhs, (void *)ctx->sv_notconv, (void *)ctx->sv_rdiag, (void *)ctx->ln_S, (void *)ctx->ln_vec})
         if (p) cudaFree(p);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);

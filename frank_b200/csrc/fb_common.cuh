@@ -93,6 +93,8 @@ struct fb_ctx {
     double *sv_D = nullptr, *sv_p = nullptr, *sv_mu = nullptr, *sv_tr2 = nullptr, *sv_alpha = nullptr, *sv_p0 = nullptr;
     double *sv_Tinv = nullptr, *sv_M = nullptr, *sv_j = nullptr, *sv_Z = nullptr, *sv_rdiag = nullptr;
     int *sv_flags = nullptr;
+    double *sv_rhs = nullptr;          // power-spectrum update: right-hand side beta + log p
+    int *sv_notconv = nullptr;         // ... and its per-problem 'some entry moved by more than tol' flag
     double *sv_hist = nullptr;         // iteration history (p, mu) of fb_frank_normal_loop
     size_t sv_hist_cap = 0;
     // LogNormal model state

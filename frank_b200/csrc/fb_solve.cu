@@ -29,6 +29,7 @@ struct SolveDims {
 
 // ---- D^-1 = M + Y^T diag(1/p) Y  (upper blocks computed, mirrored) ------------------------------------------------
 // grid (nb*(nb+1)/2, B), 256 threads, 4x4 outputs per thread.
+template <bool MMA>
 __global__ void __launch_bounds__(256)
 k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restrict__ Y, const double *__restrict__ p_all,
              const int *__restrict__ active, double *__restrict__ Dinv_all)
@@ -41,10 +42,57 @@ k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restri
     const double *p = p_all + (size_t)b * N;
     double *Dinv = Dinv_all + (size_t)b * N * N;
     constexpr int KS = 32;
-    __shared__ double Ya[KS][NB + 4], Yb[KS][NB + 4];     // [k][i] slices of Y scaled / unscaled
+    __shared__ __align__(16) double Ya[KS][NB + 4], Yb[KS][NB + 4];     // [k][i] slices of Y scaled / unscaled
     extern __shared__ double ip_s[];                      // [N] 1 / p
     for (int i = threadIdx.x; i < N; i += 256) ip_s[i] = 1.0 / p[i];
     __syncthreads();
+    if (MMA) {
+        // FP64 tensor-core variant: warp w owns rows (w >> 1) * 16 and columns (w & 1) * 32 of the 64 x 64 block = 2 x 4
+        // m8n8 accumulator tiles; the [k][i] slices with leading dimension 68 (= 4 mod 16 doubles) serve both fragment
+        // patterns without bank conflicts.  Six 8-byte loads per eight DMMAs instead of one load per four DFMAs.
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int rb = (warp >> 1) * 16, cb = (warp & 1) * 32;
+        const int fk = lane & 3, fm = lane >> 2;
+        double acc[2][4][2] = {};
+        for (int k0 = 0; k0 < N; k0 += KS) {
+            for (int e = threadIdx.x; e < KS * NB; e += 256) {
+                const int kk = e >> 6, c = e & 63, k = k0 + kk;
+                const int ia = bi * NB + c, ib = bj * NB + c;
+                Ya[kk][c] = (k < N && ia < N) ? Y[(size_t)k * N + ia] * ip_s[k] : 0.0;
+                Yb[kk][c] = (k < N && ib < N) ? Y[(size_t)k * N + ib] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int ks = 0; ks < KS; ks += 4) {
+                double af[2], bf[4];
+#pragma unroll
+                for (int r = 0; r < 2; r++) af[r] = Ya[ks + fk][rb + r * 8 + fm];
+#pragma unroll
+                for (int c = 0; c < 4; c++) bf[c] = Yb[ks + fk][cb + c * 8 + fm];
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                     : "+d"(acc[r][c][0]), "+d"(acc[r][c][1])
+                                     : "d"(af[r]), "d"(bf[c]));
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = bi * NB + rb + r * 8 + fm, j = bj * NB + cb + c * 8 + 2 * fk + h;
+                    if (i < N && j < N) {
+                        Dinv[(size_t)i * N + j] = (M ? M[(size_t)i * N + j] : 0.0) + acc[r][c][h];
+                        if (bi != bj) Dinv[(size_t)j * N + i] = (M ? M[(size_t)j * N + i] : 0.0) + acc[r][c][h];
+                    }
+                }
+        return;
+    }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double acc[4][4] = {};
     for (int k0 = 0; k0 < N; k0 += KS) {
@@ -57,9 +105,13 @@ k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restri
         __syncthreads();
 #pragma unroll 8
         for (int kk = 0; kk < KS; kk++) {
-            double a[4], bb[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) { a[r] = Ya[kk][ty * 4 + r]; bb[r] = Yb[kk][tx * 4 + r]; }
+            double a[4], bb[4];                  // 16-byte loads: the loop is bound by shared-memory instructions
+            {
+                const double2 a01 = *reinterpret_cast<const double2 *>(&Ya[kk][ty * 4]), a23 = *reinterpret_cast<const double2 *>(&Ya[kk][ty * 4 + 2]);
+                const double2 b01 = *reinterpret_cast<const double2 *>(&Yb[kk][tx * 4]), b23 = *reinterpret_cast<const double2 *>(&Yb[kk][tx * 4 + 2]);
+                a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
+                bb[0] = b01.x; bb[1] = b01.y; bb[2] = b23.x; bb[3] = b23.y;
+            }
 #pragma unroll
             for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -465,70 +517,74 @@ k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__rest
 // Tr1 = (Y mu)^2 ; beta = (p0 + 0.5 (Tr1 + Tr2)) / p - (alpha - 1 + 0.5) ; tau = (T + I)^-1 (beta + log p) ; p_new = exp(tau).
 // (T + I) is a fixed SPD pentadiagonal matrix per filter (condition number <= ~1e6); its dense inverse is formed once
 // on the host, so the solve is a matrix-vector product instead of 3 N dependent steps.
-__global__ void __launch_bounds__(1024)
-k_ps_update(int N, const double *__restrict__ Y, const double *__restrict__ mu_all, const double *__restrict__ tr2_all,
-            const double *__restrict__ alpha_all, const double *__restrict__ p0_all, const double *__restrict__ Tinv_all,
-            double tol, int max_iter, double *__restrict__ p_all, int *__restrict__ active,
-            int *__restrict__ count, int *__restrict__ converged, double *__restrict__ hist_p, int hist_cap)
+// Two kernels, one warp per row, (N / 8, B) CTAs each: a single CTA per problem had to pull Y and (T + I)^-1 (1.4 MB at
+// N = 300) through one SM and took ~45 us of the ~480 us iteration.  The row sums keep their order (lane-strided FMA
+// chain, fixed shuffle tree), so the results are bit-identical to the one-CTA version.
+__global__ void __launch_bounds__(256)
+k_ps_rhs(int N, const double *__restrict__ Y, const double *__restrict__ mu_all, const double *__restrict__ tr2_all,
+         const double *__restrict__ alpha_all, const double *__restrict__ p0_all, const double *__restrict__ p_all,
+         const int *__restrict__ active, double *__restrict__ rhs_all, int *__restrict__ notconv)
 {
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     if (active && !active[b]) return;
-    extern __shared__ double sh[];         // mu[N], rhs[N]
-    double *mu = sh, *rhs = sh + N;
-    __shared__ int not_conv;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const double *p = p_all + (size_t)b * N;
-    const double *Tinv = Tinv_all + (size_t)b * N * N;
-    for (int i = tid; i < N; i += blockDim.x) mu[i] = mu_all[(size_t)b * N + i];
-    if (tid == 0) not_conv = 0;
+    extern __shared__ double sh[];         // mu[N]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N; i += blockDim.x) sh[i] = mu_all[(size_t)b * N + i];
+    if (blockIdx.x == 0 && tid == 0) notconv[b] = 0;          // k_ps_tau (next kernel) raises it
     __syncthreads();
-    const double alpha = alpha_all[b], p0 = p0_all[b];
-    for (int i = warp; i < N; i += nw) {
-        double s = 0.0;
-        const double *Yi = Y + (size_t)i * N;
-        for (int c = lane; c < N; c += 32) s = fma(Yi[c], mu[c], s);
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= N) return;
+    double s = 0.0;
+    const double *Yi = Y + (size_t)i * N;
+    for (int c = lane; c < N; c += 32) s = fma(Yi[c], sh[c], s);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-            const double tr1 = s * s, tr2 = tr2_all[(size_t)b * N + i], pi = p[i];
-            const double beta = (p0 + 0.5 * (tr1 + tr2)) / pi - (alpha - 1.0 + 0.5 * 1.0);
-            rhs[i] = beta + log(pi);
-        }
-    }
-    __syncthreads();
-    int bad = 0;
-    const int cnt0 = count[b];
-    for (int i = warp; i < N; i += nw) {
-        double s = 0.0;
-        const double *Ti = Tinv + (size_t)i * N;
-        for (int c = lane; c < N; c += 32) s = fma(Ti[c], rhs[c], s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-            const double pn = exp(s), po = p[i];
-            if (!(fabs(pn - po) <= tol * pn)) bad = 1;
-            mu[i] = pn;                      // staged: p is still being read by other warps
-            if (hist_p && cnt0 < hist_cap) hist_p[((size_t)b * hist_cap + cnt0) * N + i] = pn;
-        }
-    }
-    if (bad) atomicOr(&not_conv, 1);
-    __syncthreads();
-    for (int i = tid; i < N; i += blockDim.x) p_all[(size_t)b * N + i] = mu[i];
-    if (tid == 0) {
-        count[b] = cnt0 + 1;
-        converged[b] = not_conv ? 0 : 1;
-        // while (not converged and count <= max_iter)          radial_fitters.py:769-770
-        // (the solve of the new p still runs in this iteration; `active` is cleared afterwards by k_loop_gate)
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const double alpha = alpha_all[b], p0 = p0_all[b];
+        const double tr1 = s * s, tr2 = tr2_all[(size_t)b * N + i], pi = p_all[(size_t)b * N + i];
+        const double beta = (p0 + 0.5 * (tr1 + tr2)) / pi - (alpha - 1.0 + 0.5 * 1.0);
+        rhs_all[(size_t)b * N + i] = beta + log(pi);
     }
 }
 
-// clears `active` once the fit of the last power spectrum has been computed
-__global__ void k_loop_gate(int B, int max_iter, const int *__restrict__ count, const int *__restrict__ converged,
+__global__ void __launch_bounds__(256)
+k_ps_tau(int N, const double *__restrict__ rhs_all, const double *__restrict__ Tinv_all, double tol, double *__restrict__ p_all,
+         const int *__restrict__ active, const int *__restrict__ count, int *__restrict__ notconv, double *__restrict__ hist_p,
+         int hist_cap)
+{
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    extern __shared__ double sh[];         // rhs[N]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N; i += blockDim.x) sh[i] = rhs_all[(size_t)b * N + i];
+    __syncthreads();
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= N) return;
+    double s = 0.0;
+    const double *Ti = Tinv_all + (size_t)b * N * N + (size_t)i * N;
+    for (int c = lane; c < N; c += 32) s = fma(Ti[c], sh[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const double pn = exp(s), po = p_all[(size_t)b * N + i];   // p[i] is read by this warp only: updated in place
+        if (!(fabs(pn - po) <= tol * pn)) atomicOr(&notconv[b], 1);
+        p_all[(size_t)b * N + i] = pn;
+        const int cnt0 = count[b];
+        if (hist_p && cnt0 < hist_cap) hist_p[((size_t)b * hist_cap + cnt0) * N + i] = pn;
+    }
+}
+
+// end of an iteration: count it, record convergence (radial_fitters.py:769-770: while not converged and count <=
+// max_iter) and clear `active` once the fit of the last power spectrum has been computed
+__global__ void k_loop_gate(int B, int max_iter, int *__restrict__ count, int *__restrict__ converged, const int *__restrict__ notconv,
                             int *__restrict__ active, int *__restrict__ n_active)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B && active[b]) {
-        if (converged[b] || count[b] > max_iter) {
+        const int c = count[b] + 1, conv = notconv[b] ? 0 : 1;
+        count[b] = c;
+        converged[b] = conv;
+        if (conv || c > max_iter) {
             active[b] = 0;
             atomicSub(n_active, 1);
         }
@@ -623,7 +679,7 @@ static int ensure_solver_ws(fb_ctx *ctx, int B)
     if (B <= ctx->sv_B && ctx->sv_N == (int)N) return 0;
     for (void **p : {(void **)&ctx->sv_D, (void **)&ctx->sv_p, (void **)&ctx->sv_mu, (void **)&ctx->sv_tr2, (void **)&ctx->sv_alpha,
                      (void **)&ctx->sv_p0, (void **)&ctx->sv_Tinv, (void **)&ctx->sv_flags, (void **)&ctx->sv_M, (void **)&ctx->sv_j,
-                     (void **)&ctx->sv_Z, (void **)&ctx->sv_rdiag}) {
+                     (void **)&ctx->sv_Z, (void **)&ctx->sv_rdiag, (void **)&ctx->sv_rhs, (void **)&ctx->sv_notconv}) {
         if (*p) FB_CUDA(cudaFree(*p));
         *p = nullptr;
     }
@@ -632,6 +688,8 @@ static int ensure_solver_ws(fb_ctx *ctx, int B)
     FB_CUDA(cudaMalloc(&ctx->sv_mu, sizeof(double) * B * N));
     FB_CUDA(cudaMalloc(&ctx->sv_tr2, sizeof(double) * B * N));
     FB_CUDA(cudaMalloc(&ctx->sv_rdiag, sizeof(double) * B * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_rhs, sizeof(double) * B * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_notconv, sizeof(int) * B));
     FB_CUDA(cudaMalloc(&ctx->sv_alpha, sizeof(double) * B));
     FB_CUDA(cudaMalloc(&ctx->sv_p0, sizeof(double) * B));
     FB_CUDA(cudaMalloc(&ctx->sv_Tinv, sizeof(double) * B * N * N));
@@ -678,10 +736,26 @@ static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_i
     return launch_solve(ctx, B, d_active, ctx->stream);
 }
 
+// FB_BUILD_DINV=fma selects the DFMA variant (sequential k order per entry); default: FP64 tensor cores
+static bool build_dinv_mma()
+{
+    static const bool mma = [] { const char *e = getenv("FB_BUILD_DINV"); return !(e && e[0] == 'f'); }();
+    return mma;
+}
+
 static int allow_build_smem(fb_ctx *ctx)
 {
-    FB_CUDA(cudaFuncSetAttribute(k_build_dinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ctx->N)));
+    FB_CUDA(cudaFuncSetAttribute(k_build_dinv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ctx->N)));
+    FB_CUDA(cudaFuncSetAttribute(k_build_dinv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ctx->N)));
     return 0;
+}
+
+static void launch_build_dinv(fb_ctx *ctx, int N, int nb, int B, const double *M, const double *Y, const double *p,
+                              const int *active, double *out)
+{
+    const dim3 grid(nb * (nb + 1) / 2, B);
+    if (build_dinv_mma()) k_build_dinv<true><<<grid, 256, sizeof(double) * N, ctx->stream>>>(N, nb, M, Y, p, active, out);
+    else k_build_dinv<false><<<grid, 256, sizeof(double) * N, ctx->stream>>>(N, nb, M, Y, p, active, out);
 }
 
 static int launch_tr2(fb_ctx *ctx, int B, const int *d_active)
@@ -742,7 +816,7 @@ int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host
         for (size_t i = 0; i < (size_t)B * N; i++)
             if (!(host_p[i] > 0.0)) FB_FAIL(FB_E_BADP, "bad value in power spectrum");        // statistical_models.py:688
         FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p, sizeof(double) * B * N, cudaMemcpyHostToDevice, ctx->stream));
-        k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, nullptr, ctx->sv_D);
+        launch_build_dinv(ctx, (int)N, nb, B, ctx->sv_M, ctx->d_Y, ctx->sv_p, nullptr, ctx->sv_D);
     } else {
         for (int b = 0; b < B; b++)
             FB_CUDA(cudaMemcpyAsync(ctx->sv_D + (size_t)b * N * N, ctx->sv_M, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -809,7 +883,7 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
     // Factor for the initial spectrum (the reference enters the loop with `fit` of p_init, radial_fitters.py:752-763).
     // The posterior mean of a factor is computed at the START of the next iteration, concurrently with the Tr2
     // triangular solves (both only read U): fork / join inside the captured graph.
-    k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
+    launch_build_dinv(ctx, (int)N, nb, B, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
     rc = launch_factor(ctx, B, d_active, d_info);
     if (rc) return rc;
     if (!ctx->stream2) FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
@@ -830,13 +904,14 @@ int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double 
         r = launch_tr2(ctx, B, d_active);                                      // Tr2 of the current factor
         if (r) return r;
         if (fork) FB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->fev[1], 0));   // join
-        k_ps_update<<<B, 1024, sizeof(double) * 2 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
-                                                                     ctx->sv_p0, ctx->sv_Tinv, tol, max_iter, ctx->sv_p,
-                                                                     d_active, d_count, d_conv, d_hist_p, hist_cap);
-        k_build_dinv<<<dim3(nb * (nb + 1) / 2, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
+        k_ps_rhs<<<dim3(((int)N + 7) / 8, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
+                                                                                   ctx->sv_p0, ctx->sv_p, d_active, ctx->sv_rhs, ctx->sv_notconv);
+        k_ps_tau<<<dim3(((int)N + 7) / 8, B), 256, sizeof(double) * N, ctx->stream>>>((int)N, ctx->sv_rhs, ctx->sv_Tinv, tol, ctx->sv_p, d_active,
+                                                                                   d_count, ctx->sv_notconv, d_hist_p, hist_cap);
+        launch_build_dinv(ctx, (int)N, nb, B, ctx->sv_M, ctx->d_Y, ctx->sv_p, d_active, ctx->sv_D);
         r = launch_factor(ctx, B, d_active, d_info);
         if (r) return r;
-        k_loop_gate<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, max_iter, d_count, d_conv, d_active, d_nact);
+        k_loop_gate<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, max_iter, d_count, d_conv, ctx->sv_notconv, d_active, d_nact);
         return 0;
     };
     cudaGraph_t graph = nullptr;
@@ -1006,7 +1081,7 @@ extern "C" int fb_gaussian_svd(fb_ctx *ctx, const double *host_M, const double *
         for (size_t i = 0; i < N; i++)
             if (!(host_p[i] > 0.0)) FB_FAIL(FB_E_BADP, "bad value in power spectrum");
         FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-        k_build_dinv<<<dim3(nb * (nb + 1) / 2, 1), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, ctx->sv_M, ctx->d_Y, ctx->sv_p, nullptr, ctx->sv_D);
+        launch_build_dinv(ctx, (int)N, nb, 1, ctx->sv_M, ctx->d_Y, ctx->sv_p, nullptr, ctx->sv_D);
         FB_CUDA(cudaGetLastError());
     } else {
         FB_CUDA(cudaMemcpyAsync(ctx->sv_D, ctx->sv_M, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1114,7 +1189,7 @@ int fb_ln_set_spectrum(fb_ctx *ctx, const double *host_p)
     int rc = allow_build_smem(ctx);
     if (rc) return rc;
     FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-    k_build_dinv<<<dim3(nb * (nb + 1) / 2, 1), 256, sizeof(double) * N, ctx->stream>>>((int)N, nb, nullptr, ctx->d_Y, ctx->sv_p, nullptr, ctx->ln_S);
+    launch_build_dinv(ctx, (int)N, nb, 1, nullptr, ctx->d_Y, ctx->sv_p, nullptr, ctx->ln_S);
     FB_CUDA(cudaGetLastError());
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1212,9 +1287,10 @@ int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, dou
         FB_CUDA(cudaMemcpyAsync(ctx->sv_Tinv, host_Tinv, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
         rc = launch_tr2(ctx, 1, nullptr);
         if (rc) return rc;
-        k_ps_update<<<1, 1024, sizeof(double) * 2 * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha, ctx->sv_p0,
-                                                                     ctx->sv_Tinv, 1e-3, 0, ctx->sv_p, nullptr, d_flags, d_flags + 1,
-                                                                     nullptr, 0);
+        k_ps_rhs<<<dim3(((int)N + 7) / 8, 1), 256, sizeof(double) * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
+                                                                                   ctx->sv_p0, ctx->sv_p, nullptr, ctx->sv_rhs, ctx->sv_notconv);
+        k_ps_tau<<<dim3(((int)N + 7) / 8, 1), 256, sizeof(double) * N, ctx->stream>>>((int)N, ctx->sv_rhs, ctx->sv_Tinv, 1e-3, ctx->sv_p, nullptr,
+                                                                                   d_flags, ctx->sv_notconv, nullptr, 0);
         FB_CUDA(cudaGetLastError());
         FB_CUDA(cudaMemcpyAsync(host_p_new, ctx->sv_p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
     }
