@@ -257,6 +257,9 @@ k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__rest
 }
 
 // ---- trailing update A_ij -= U_ki^T U_kj, k < i <= j -----------------------------------------------------------------
+constexpr int ULD = NB + 4;            // leading dimension of the update's blocks: 4 mod 16 doubles -> conflict-free m8n8k4 fragments
+
+template <bool MMA>
 __global__ void __launch_bounds__(256)
 k_chol_update(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active)
 {
@@ -267,9 +270,9 @@ k_chol_update(int N, int nb, int k, double *__restrict__ A_all, const int *__res
     int rem = blockIdx.x, ii = 0;
     while (rem >= nt - ii) { rem -= nt - ii; ii++; }
     const int bi = k + 1 + ii, bj = bi + rem;
-    extern __shared__ double dyn_sm[];
-    double (*Ui)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm);
-    double (*Uj)[SLD] = reinterpret_cast<double (*)[SLD]>(dyn_sm + NB * SLD);
+    extern __shared__ __align__(16) double dyn_sm[];
+    double (*Ui)[ULD] = reinterpret_cast<double (*)[ULD]>(dyn_sm);
+    double (*Uj)[ULD] = reinterpret_cast<double (*)[ULD]>(dyn_sm + NB * ULD);
     const int r0 = k * NB, nk = min(NB, N - r0);
     for (int e = threadIdx.x; e < NB * NB; e += 256) {
         const int r = e / NB, c = e % NB;
@@ -278,13 +281,48 @@ k_chol_update(int N, int nb, int k, double *__restrict__ A_all, const int *__res
         Uj[r][c] = (r < nk && cj < N) ? A[(size_t)(r0 + r) * N + cj] : 0.0;
     }
     __syncthreads();
+    if (MMA) {
+        // FP64 tensor cores: warp w owns rows (w >> 1) * 16, columns (w & 1) * 32 of the 64 x 64 block (2 x 4 m8n8 tiles)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int rb = (warp >> 1) * 16, cb = (warp & 1) * 32, fk = lane & 3, fm = lane >> 2;
+        double acc[2][4][2] = {};
+#pragma unroll 4
+        for (int ks = 0; ks < NB; ks += 4) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int r = 0; r < 2; r++) af[r] = Ui[ks + fk][rb + r * 8 + fm];
+#pragma unroll
+            for (int c = 0; c < 4; c++) bf[c] = Uj[ks + fk][cb + c * 8 + fm];
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc[r][c][0]), "+d"(acc[r][c][1])
+                                 : "d"(af[r]), "d"(bf[c]));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int i = bi * NB + rb + r * 8 + fm, j = bj * NB + cb + c * 8 + 2 * fk;
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    if (i < N && j + h < N && j + h >= i) A[(size_t)i * N + j + h] -= acc[r][c][h];
+            }
+        return;
+    }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double acc[4][4] = {};
 #pragma unroll 4
     for (int kk = 0; kk < NB; kk++) {
         double a[4], bb[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) { a[r] = Ui[kk][ty * 4 + r]; bb[r] = Uj[kk][tx * 4 + r]; }
+        {
+            const double2 a01 = *reinterpret_cast<const double2 *>(&Ui[kk][ty * 4]), a23 = *reinterpret_cast<const double2 *>(&Ui[kk][ty * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2 *>(&Uj[kk][tx * 4]), b23 = *reinterpret_cast<const double2 *>(&Uj[kk][tx * 4 + 2]);
+            a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
+            bb[0] = b01.x; bb[1] = b01.y; bb[2] = b23.x; bb[3] = b23.y;
+        }
 #pragma unroll
         for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -335,6 +373,55 @@ k_trsm_tr2(int N, int TP, const double *__restrict__ U_all, const double *__rest
             __syncwarp();
             for (int rr = r1 + r + 1 + lane; rr < N; rr += 32) Z[rr] = fma(-Ur[rr], z, Z[rr]);
             __syncwarp();
+        }
+    }
+    if (lane == 0 && c < N) tr2_all[(size_t)b * N + c] = ssq;
+}
+
+// ---- Tr2 with the solution in registers (N <= 512): the same forward substitution, one warp per right-hand side, but lane l
+// keeps Z[l + 32 m] (m < M) in registers instead of shared memory.  Step g broadcasts z_g with one shuffle and updates
+// the lane's remaining entries with independent FMAs, so the dependent chain of a step is shuffle -> multiply -> FMA
+// (~70 clocks) instead of a serial loop over up to N / 32 shared-memory read-modify-writes (~700 clocks): 154 -> ?? us at
+// N = 300.  Same operations in the same order per entry -> bit-identical to k_trsm_tr2.  Panels of 32 rows of U (zero
+// padded to 32 M columns) are staged in shared memory by all warps of the CTA.
+template <int M>
+__global__ void __launch_bounds__(256)
+k_trsm_tr2_reg(int N, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ Y,
+               const int *__restrict__ active, double *__restrict__ tr2_all)
+{
+    constexpr int NP = 32 * M;
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const double *U = U_all + (size_t)b * N * N;
+    extern __shared__ double sm[];
+    double *Up = sm;                                        // [32][NP] panel of U rows
+    double *rd = sm + 32 * NP;                              // [NP] reciprocal diagonal
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x * 8 + warp;                    // right-hand side = row c of Y
+    for (int i = tid; i < NP; i += 256) rd[i] = i < N ? rdiag_all[(size_t)b * N + i] : 0.0;
+    double Z[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) Z[m] = (c < N && lane + 32 * m < N) ? Y[(size_t)c * N + lane + 32 * m] : 0.0;
+    double ssq = 0.0;
+#pragma unroll
+    for (int m0 = 0; m0 < M; m0++) {
+        const int r1 = 32 * m0;
+        if (r1 < N) {                                       // uniform over the CTA
+            __syncthreads();
+            for (int e = tid; e < 32 * (NP - r1); e += 256) {
+                const int r = e / (NP - r1), cc = r1 + e % (NP - r1);
+                Up[r * NP + cc] = (r1 + r < N && cc < N) ? U[(size_t)(r1 + r) * N + cc] : 0.0;
+            }
+            __syncthreads();
+            const int nk = min(32, N - r1);
+            for (int l = 0; l < nk; l++) {
+                const double z = __shfl_sync(0xffffffffu, Z[m0], l) * rd[r1 + l];
+                ssq = fma(z, z, ssq);
+                const double *Ur = Up + l * NP + lane;
+                if (lane > l) Z[m0] = fma(-Ur[r1], z, Z[m0]);
+#pragma unroll
+                for (int m = m0 + 1; m < M; m++) Z[m] = fma(-Ur[32 * m], z, Z[m]);
+            }
         }
     }
     if (lane == 0 && c < N) tr2_all[(size_t)b * N + c] = ssq;
@@ -707,11 +794,17 @@ static int launch_factor(fb_ctx *ctx, int B, const int *d_active, int *d_info)
     const int N = ctx->N, nb = (N + NB - 1) / NB;
     const size_t blk2 = sizeof(double) * 2 * NB * SLD;
     FB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
-    FB_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
+    const size_t blku = sizeof(double) * 2 * NB * ULD;
+    static const bool upd_mma = [] { const char *e = getenv("FB_CHOL_UPDATE"); return !(e && e[0] == 'f'); }();   // =fma: DFMA variant
+    FB_CUDA(cudaFuncSetAttribute(k_chol_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blku));
+    FB_CUDA(cudaFuncSetAttribute(k_chol_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blku));
     for (int k = 0; k < nb; k++) {
         k_chol_panel<<<dim3(nb - k, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag);
         const int nt = nb - k - 1;
-        if (nt > 0) k_chol_update<<<dim3(nt * (nt + 1) / 2, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active);
+        if (nt > 0) {
+            if (upd_mma) k_chol_update<true><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active);
+            else k_chol_update<false><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active);
+        }
     }
     FB_CUDA(cudaGetLastError());
     return 0;
@@ -776,6 +869,25 @@ static int launch_tr2(fb_ctx *ctx, int B, const int *d_active)
     if (need32 <= lim) {
         FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2_blocked<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need32));
         k_trsm_tr2_blocked<32><<<dim3((N + 31) / 32, B), 256, need32, ctx->stream>>>(N, nb, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2);
+        FB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (N <= 512) {                                                            // solution in registers
+        const int M = (N + 31) / 32;
+        const dim3 grid((N + 7) / 8, B);
+#define FB_TR2_REG(MM)                                                                                                         \
+    {                                                                                                                          \
+        const size_t smem = sizeof(double) * 33 * 32 * MM;                                                                     \
+        FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2_reg<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        k_trsm_tr2_reg<MM><<<grid, 256, smem, ctx->stream>>>(N, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2);    \
+    }
+        if (M <= 2) FB_TR2_REG(2)
+        else if (M <= 4) FB_TR2_REG(4)
+        else if (M <= 7) FB_TR2_REG(7)
+        else if (M <= 10) FB_TR2_REG(10)
+        else if (M <= 13) FB_TR2_REG(13)
+        else FB_TR2_REG(16)
+#undef FB_TR2_REG
         FB_CUDA(cudaGetLastError());
         return 0;
     }
@@ -1236,15 +1348,8 @@ int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, doub
     if (refactor) {
         FB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
         k_ln_hess<<<dim3(((int)N + 31) / 32, ((int)N + 7) / 8), 256, 0, ctx->stream>>>((int)N, ctx->sv_M, ctx->ln_S, d_I, d_r, ctx->ln_full_hess, ctx->sv_D);
-        const int nb = ((int)N + NB - 1) / NB;
-        const size_t blk2 = sizeof(double) * 2 * NB * SLD;
-        FB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
-        FB_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
-        for (int k = 0; k < nb; k++) {
-            k_chol_panel<<<dim3(nb - k, 1), 256, blk2, ctx->stream>>>((int)N, nb, k, ctx->sv_D, nullptr, d_info, ctx->sv_rdiag);
-            const int nt = nb - k - 1;
-            if (nt > 0) k_chol_update<<<dim3(nt * (nt + 1) / 2, 1), 256, blk2, ctx->stream>>>((int)N, nb, k, ctx->sv_D, nullptr);
-        }
+        rc = launch_factor(ctx, 1, nullptr, d_info);          // same blocked factorisation as the Normal path
+        if (rc) return rc;
     }
     k_negate<<<((int)N + 255) / 256, 256, 0, ctx->stream>>>((int)N, d_g, d_ng);
     int PR = 32;
