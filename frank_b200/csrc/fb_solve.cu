@@ -132,6 +132,86 @@ k_build_dinv(int N, int nb, const double *__restrict__ M, const double *__restri
         }
 }
 
+// ---- D^-1 build on FP64 tensor cores with the k-slices of Y double-buffered by cp.async -------------------------------
+// Same tiling and fragment pattern as k_build_dinv<true>; the slices are staged raw (the copy of slice s + 1 flies
+// during the DMMAs of slice s) and the 1/p_k scaling is applied when the A fragment is loaded -- the same rounded
+// product Y_ki (1/p_k) as before, so the results are bit-identical.  Dynamic shared memory: 1/p [N padded to 32] |
+// [2 buffers][2 operands][32][68].
+__global__ void __launch_bounds__(256)
+k_build_dinv_pipe(int N, int nb, const double *__restrict__ M, const double *__restrict__ Y, const double *__restrict__ p_all,
+                  const int *__restrict__ active, double *__restrict__ Dinv_all)
+{
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    int rem = blockIdx.x, bi = 0;
+    while (rem >= nb - bi) { rem -= nb - bi; bi++; }
+    const int bj = bi + rem;
+    const double *p = p_all + (size_t)b * N;
+    double *Dinv = Dinv_all + (size_t)b * N * N;
+    constexpr int KS = 32, LD = NB + 4;
+    extern __shared__ __align__(16) double dsm[];
+    const int Npad = (N + KS - 1) / KS * KS;
+    double *ip_s = dsm;                                   // [Npad]
+    double *bufs = dsm + Npad;                            // [2][2][KS][LD]
+    const uint32_t bufs_s = (uint32_t)__cvta_generic_to_shared(bufs);
+    for (int i = threadIdx.x; i < Npad; i += 256) ip_s[i] = i < N ? 1.0 / p[i] : 0.0;
+    auto stage = [&](const int k0, const int buf) {
+#pragma unroll
+        for (int x = 0; x < KS * NB / 256; x++) {
+            const int e = threadIdx.x + 256 * x, kk = e >> 6, c = e & 63, k = k0 + kk;
+            const int ia = bi * NB + c, ib = bj * NB + c;
+            const bool oka = k < N && ia < N, okb = k < N && ib < N;
+            const uint32_t da = bufs_s + (uint32_t)((((buf * 2 + 0) * KS + kk) * LD + c) * 8);
+            const uint32_t db = bufs_s + (uint32_t)((((buf * 2 + 1) * KS + kk) * LD + c) * 8);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(da), "l"(oka ? Y + (size_t)k * N + ia : Y), "r"(oka ? 8 : 0) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(db), "l"(okb ? Y + (size_t)k * N + ib : Y), "r"(okb ? 8 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rb = (warp >> 1) * 16, cb = (warp & 1) * 32, fk = lane & 3, fm = lane >> 2;
+    double acc[2][4][2] = {};
+    const int nchunk = (N + KS - 1) / KS;
+    stage(0, 0);
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunk) { stage((ch + 1) * KS, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const double *Ya = bufs + (size_t)(buf * 2 + 0) * KS * LD, *Yb = bufs + (size_t)(buf * 2 + 1) * KS * LD;
+        const double *ipk = ip_s + ch * KS;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks += 4) {
+            const double sc = ipk[ks + fk];
+            double af[2], bf[4];
+#pragma unroll
+            for (int r = 0; r < 2; r++) af[r] = Ya[(ks + fk) * LD + rb + r * 8 + fm] * sc;      // (Y_ki * (1/p)_k), as the einsum forms it
+#pragma unroll
+            for (int c = 0; c < 4; c++) bf[c] = Yb[(ks + fk) * LD + cb + c * 8 + fm];
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(acc[r][c][0]), "+d"(acc[r][c][1])
+                                 : "d"(af[r]), "d"(bf[c]));
+        }
+        __syncthreads();                                  // this buffer is refilled by the next iteration's stage()
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i = bi * NB + rb + r * 8 + fm, j = bj * NB + cb + c * 8 + 2 * fk + h;
+                if (i < N && j < N) {
+                    Dinv[(size_t)i * N + j] = (M ? M[(size_t)i * N + j] : 0.0) + acc[r][c][h];
+                    if (bi != bj) Dinv[(size_t)j * N + i] = (M ? M[(size_t)j * N + i] : 0.0) + acc[r][c][h];
+                }
+            }
+}
+
 // ---- Cholesky panel: factor A_kk, then U_kj = U_kk^-T A_kj for the block row ----------------------------------------
 // grid (nb - k, B): block x = 0 factors and stores the diagonal block, x > 0 solves block column k + x (and repeats
 // the 64 x 64 factorisation, which is cheaper than waiting for it).  The 64 dependent pivot steps are the critical
@@ -384,7 +464,7 @@ k_trsm_tr2(int N, int TP, const double *__restrict__ U_all, const double *__rest
 // (~70 clocks) instead of a serial loop over up to N / 32 shared-memory read-modify-writes (~700 clocks): 154 -> ?? us at
 // N = 300.  Same operations in the same order per entry -> bit-identical to k_trsm_tr2.  Panels of 32 rows of U (zero
 // padded to 32 M columns) are staged in shared memory by all warps of the CTA.
-template <int M>
+template <int M, int NBUF>
 __global__ void __launch_bounds__(256)
 k_trsm_tr2_reg(int N, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ Y,
                const int *__restrict__ active, double *__restrict__ tr2_all)
@@ -393,36 +473,61 @@ k_trsm_tr2_reg(int N, const double *__restrict__ U_all, const double *__restrict
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     const double *U = U_all + (size_t)b * N * N;
-    extern __shared__ double sm[];
-    double *Up = sm;                                        // [32][NP] panel of U rows
-    double *rd = sm + 32 * NP;                              // [NP] reciprocal diagonal
+    extern __shared__ __align__(16) double sm[];
+    double *rd = sm;                                        // [NP] reciprocal diagonal
+    double *Up0 = sm + NP;                                  // [NBUF][32][NP] panels of U rows
+    const uint32_t up_s = (uint32_t)__cvta_generic_to_shared(Up0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x * 8 + warp;                    // right-hand side = row c of Y
     for (int i = tid; i < NP; i += 256) rd[i] = i < N ? rdiag_all[(size_t)b * N + i] : 0.0;
+    // stage panel m0 (rows 32 m0 .. 32 m0 + 31, columns 32 m0 .. NP - 1, zero beyond N) with cp.async: warp w takes rows
+    // w, w + 8, ...; trip counts are compile-time constants, so all (M - m0) x 4 copies of a thread are in flight at once
+    auto stage = [&](const int m0, const int buf) {
+        const int r1 = 32 * m0;
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+            const int r = warp + 8 * rr;
+#pragma unroll
+            for (int m = 0; m < M; m++) {
+                if (m < m0) continue;
+                const int cc = 32 * m + lane;
+                const bool ok = r1 + r < N && cc < N;
+                const double *src = ok ? U + (size_t)(r1 + r) * N + cc : U;
+                const uint32_t dst = up_s + (uint32_t)(((buf * 32 + r) * NP + cc) * 8);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(ok ? 8 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     double Z[M];
 #pragma unroll
     for (int m = 0; m < M; m++) Z[m] = (c < N && lane + 32 * m < N) ? Y[(size_t)c * N + lane + 32 * m] : 0.0;
     double ssq = 0.0;
+    stage(0, 0);
 #pragma unroll
     for (int m0 = 0; m0 < M; m0++) {
         const int r1 = 32 * m0;
-        if (r1 < N) {                                       // uniform over the CTA
-            __syncthreads();
-            for (int e = tid; e < 32 * (NP - r1); e += 256) {
-                const int r = e / (NP - r1), cc = r1 + e % (NP - r1);
-                Up[r * NP + cc] = (r1 + r < N && cc < N) ? U[(size_t)(r1 + r) * N + cc] : 0.0;
-            }
-            __syncthreads();
-            const int nk = min(32, N - r1);
-            for (int l = 0; l < nk; l++) {
-                const double z = __shfl_sync(0xffffffffu, Z[m0], l) * rd[r1 + l];
-                ssq = fma(z, z, ssq);
-                const double *Ur = Up + l * NP + lane;
-                if (lane > l) Z[m0] = fma(-Ur[r1], z, Z[m0]);
-#pragma unroll
-                for (int m = m0 + 1; m < M; m++) Z[m] = fma(-Ur[32 * m], z, Z[m]);
-            }
+        const int buf = NBUF > 1 ? (m0 & 1) : 0;
+        if (NBUF > 1) {
+            if (m0 + 1 < M) stage(m0 + 1, buf ^ 1);         // flies during this panel's 32 steps
+            if (m0 + 1 < M) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        __syncthreads();                                    // panel m0 visible to every warp
+        const int nk = min(32, N - r1);
+        const double *Up = Up0 + (size_t)buf * 32 * NP;
+        for (int l = 0; l < nk; l++) {
+            const double z = __shfl_sync(0xffffffffu, Z[m0], l) * rd[r1 + l];
+            ssq = fma(z, z, ssq);
+            const double *Ur = Up + l * NP + lane;
+            if (lane > l) Z[m0] = fma(-Ur[r1], z, Z[m0]);
+#pragma unroll
+            for (int m = m0 + 1; m < M; m++) Z[m] = fma(-Ur[32 * m], z, Z[m]);
+        }
+        __syncthreads();                                    // everyone is done with this buffer before it is refilled
+        if (NBUF == 1 && m0 + 1 < M) stage(m0 + 1, 0);
     }
     if (lane == 0 && c < N) tr2_all[(size_t)b * N + c] = ssq;
 }
@@ -836,9 +941,12 @@ static bool build_dinv_mma()
     return mma;
 }
 
+static size_t build_pipe_smem(int N) { return sizeof(double) * ((size_t)(N + 31) / 32 * 32 + 2 * 2 * 32 * (NB + 4)); }
+
 static int allow_build_smem(fb_ctx *ctx)
 {
     FB_CUDA(cudaFuncSetAttribute(k_build_dinv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ctx->N)));
+    FB_CUDA(cudaFuncSetAttribute(k_build_dinv_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_pipe_smem(ctx->N)));
     FB_CUDA(cudaFuncSetAttribute(k_build_dinv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ctx->N)));
     return 0;
 }
@@ -847,7 +955,9 @@ static void launch_build_dinv(fb_ctx *ctx, int N, int nb, int B, const double *M
                               const int *active, double *out)
 {
     const dim3 grid(nb * (nb + 1) / 2, B);
-    if (build_dinv_mma()) k_build_dinv<true><<<grid, 256, sizeof(double) * N, ctx->stream>>>(N, nb, M, Y, p, active, out);
+    static const bool pipe = [] { const char *e = getenv("FB_BUILD_DINV"); return !(e && e[0] == 'm'); }();     // =mma: unpipelined DMMA variant
+    if (build_dinv_mma() && pipe) k_build_dinv_pipe<<<grid, 256, build_pipe_smem(N), ctx->stream>>>(N, nb, M, Y, p, active, out);
+    else if (build_dinv_mma()) k_build_dinv<true><<<grid, 256, sizeof(double) * N, ctx->stream>>>(N, nb, M, Y, p, active, out);
     else k_build_dinv<false><<<grid, 256, sizeof(double) * N, ctx->stream>>>(N, nb, M, Y, p, active, out);
 }
 
@@ -875,18 +985,18 @@ static int launch_tr2(fb_ctx *ctx, int B, const int *d_active)
     if (N <= 512) {                                                            // solution in registers
         const int M = (N + 31) / 32;
         const dim3 grid((N + 7) / 8, B);
-#define FB_TR2_REG(MM)                                                                                                         \
+#define FB_TR2_REG(MM, NBUF)                                                                                                   \
     {                                                                                                                          \
-        const size_t smem = sizeof(double) * 33 * 32 * MM;                                                                     \
-        FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2_reg<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-        k_trsm_tr2_reg<MM><<<grid, 256, smem, ctx->stream>>>(N, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2);    \
+        const size_t smem = sizeof(double) * (32 * MM + (size_t)NBUF * 32 * 32 * MM);                                          \
+        FB_CUDA(cudaFuncSetAttribute(k_trsm_tr2_reg<MM, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        k_trsm_tr2_reg<MM, NBUF><<<grid, 256, smem, ctx->stream>>>(N, ctx->sv_D, ctx->sv_rdiag, ctx->d_Y, d_active, ctx->sv_tr2); \
     }
-        if (M <= 2) FB_TR2_REG(2)
-        else if (M <= 4) FB_TR2_REG(4)
-        else if (M <= 7) FB_TR2_REG(7)
-        else if (M <= 10) FB_TR2_REG(10)
-        else if (M <= 13) FB_TR2_REG(13)
-        else FB_TR2_REG(16)
+        if (M <= 2) FB_TR2_REG(2, 2)
+        else if (M <= 4) FB_TR2_REG(4, 2)
+        else if (M <= 7) FB_TR2_REG(7, 2)
+        else if (M <= 10) FB_TR2_REG(10, 2)
+        else if (M <= 13) FB_TR2_REG(13, 2)
+        else FB_TR2_REG(16, 1)
 #undef FB_TR2_REG
         FB_CUDA(cudaGetLastError());
         return 0;
