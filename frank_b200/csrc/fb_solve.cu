@@ -705,6 +705,111 @@ k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__rest
     for (int i = tid; i < N; i += blockDim.x) mu_all[(size_t)b * N + i] = x[i];
 }
 
+// ---- mu = U^-1 U^-T j with the vector in registers (N <= 512) ---------------------------------------------------------
+// One warp carries the right-hand side / solution (lane l holds x[l + 32 m]); the whole CTA stages U by cp.async one panel
+// ahead.  Forward sweep as in k_trsm_tr2_reg (panels of 32 rows).  Backward sweep right-looking: once mu_g is known,
+// x_i -= U[i][g] mu_g for i < g, from panels of 32 COLUMNS of U staged as [row][33] (conflict-free for lanes over rows).
+// A step is shuffle -> multiply -> independent FMAs; no CTA barrier inside a panel.
+template <int M, int NBUF>
+__global__ void __launch_bounds__(256)
+k_solve_mu_reg(int N, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ jvec,
+               int j_stride, const int *__restrict__ active, double *__restrict__ mu_all)
+{
+    constexpr int NP = 32 * M, BUF = NP * 33;
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    const double *U = U_all + (size_t)b * N * N;
+    extern __shared__ __align__(16) double sm[];
+    double *rd = sm;                                        // [NP]
+    double *P0 = sm + NP;                                   // [NBUF][BUF]
+    const uint32_t p_s = (uint32_t)__cvta_generic_to_shared(P0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < NP; i += 256) rd[i] = i < N ? rdiag_all[(size_t)b * N + i] : 0.0;
+    auto stage_rows = [&](const int m0, const int buf) {    // rows 32 m0 .. +31, columns 32 m0 .. NP-1 -> [r][NP]
+        const int r1 = 32 * m0;
+#pragma unroll 1
+        for (int rr = 0; rr < 5 && warp > 0; rr++) {        // warps 1..7 stage, warp 0 only computes
+            const int r = (warp - 1) + 7 * rr;
+            if (r >= 32) break;
+#pragma unroll 2
+            for (int m = m0; m < M; m++) {
+                const int cc = 32 * m + lane;
+                const bool ok = r1 + r < N && cc < N;
+                const uint32_t dst = p_s + (uint32_t)((buf * BUF + r * NP + cc) * 8);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(ok ? U + (size_t)(r1 + r) * N + cc : U), "r"(ok ? 8 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto stage_cols = [&](const int m0, const int buf) {    // rows 0 .. 32 m0 + 31, columns 32 m0 .. +31 -> [row][33]
+        const int c1 = 32 * m0;
+#pragma unroll 2
+        for (int rr = 0; warp > 0 && (warp - 1) + 7 * rr < 32 * (m0 + 1); rr++) {     // cp.async holds no data registers: a rolled loop is enough
+            const int row = (warp - 1) + 7 * rr;
+            const bool ok = row < N && c1 + lane < N;
+            const uint32_t dst = p_s + (uint32_t)((buf * BUF + row * 33 + lane) * 8);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(ok ? U + (size_t)row * N + c1 + lane : U), "r"(ok ? 8 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double X[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) X[m] = lane + 32 * m < N ? jvec[(size_t)b * j_stride + lane + 32 * m] : 0.0;
+    // ---- forward: U^T z = j
+    stage_rows(0, 0);
+#pragma unroll
+    for (int m0 = 0; m0 < M; m0++) {
+        const int r1 = 32 * m0;
+        const int buf = NBUF > 1 ? (m0 & 1) : 0;
+        if (NBUF > 1 && m0 + 1 < M) { stage_rows(m0 + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            const int nk = min(32, N - r1);
+            const double *Up = P0 + (size_t)buf * BUF;
+            for (int l = 0; l < nk; l++) {
+                const double z = __shfl_sync(0xffffffffu, X[m0], l) * rd[r1 + l];
+                const double *Ur = Up + l * NP + lane;
+                if (lane == l) X[m0] = z;
+                if (lane > l) X[m0] = fma(-Ur[r1], z, X[m0]);
+#pragma unroll
+                for (int m = m0 + 1; m < M; m++) X[m] = fma(-Ur[32 * m], z, X[m]);
+            }
+        }
+        __syncthreads();
+        if (NBUF == 1 && m0 + 1 < M) stage_rows(m0 + 1, 0);
+    }
+    // ---- backward: U mu = z
+    stage_cols(M - 1, 0);
+#pragma unroll
+    for (int q = 0; q < M; q++) {
+        const int m0 = M - 1 - q, c1 = 32 * m0;
+        const int buf = NBUF > 1 ? (q & 1) : 0;
+        if (NBUF > 1 && m0 > 0) { stage_cols(m0 - 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (warp == 0 && c1 < N) {
+            const int nk = min(32, N - c1);
+            const double *Uc = P0 + (size_t)buf * BUF;
+            for (int l = nk - 1; l >= 0; l--) {
+                const double mu = __shfl_sync(0xffffffffu, X[m0], l) * rd[c1 + l];
+                if (lane == l) X[m0] = mu;
+                if (lane < l) X[m0] = fma(-Uc[(c1 + lane) * 33 + l], mu, X[m0]);
+#pragma unroll
+                for (int m = 0; m < M; m++)
+                    if (m < m0) X[m] = fma(-Uc[(32 * m + lane) * 33 + l], mu, X[m]);
+            }
+        }
+        __syncthreads();
+        if (NBUF == 1 && m0 > 0) stage_cols(m0 - 1, 0);
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int m = 0; m < M; m++)
+            if (lane + 32 * m < N) mu_all[(size_t)b * N + lane + 32 * m] = X[m];
+    }
+}
+
 // ---- power-spectrum update, one CTA (1024 threads) per problem ----------------------------------------------------------
 // Tr1 = (Y mu)^2 ; beta = (p0 + 0.5 (Tr1 + Tr2)) / p - (alpha - 1 + 0.5) ; tau = (T + I)^-1 (beta + log p) ; p_new = exp(tau).
 // (T + I) is a fixed SPD pentadiagonal matrix per filter (condition number <= ~1e6); its dense inverse is formed once
@@ -918,6 +1023,25 @@ static int launch_factor(fb_ctx *ctx, int B, const int *d_active, int *d_info)
 static int launch_solve(fb_ctx *ctx, int B, const int *d_active, cudaStream_t stream)
 {
     const int N = ctx->N;
+    static const bool reg = [] { const char *e = getenv("FB_SOLVE_MU"); return !(e && e[0] == 's'); }();   // =smem: the shared-memory variant
+    if (reg && N <= 512) {
+        const int M = (N + 31) / 32;
+#define FB_SOLVE_REG(MM, NBUF)                                                                                                 \
+    {                                                                                                                          \
+        const size_t smem = sizeof(double) * (32 * MM + (size_t)NBUF * 32 * MM * 33);                                          \
+        FB_CUDA(cudaFuncSetAttribute(k_solve_mu_reg<MM, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        k_solve_mu_reg<MM, NBUF><<<B, 256, smem, stream>>>(N, ctx->sv_D, ctx->sv_rdiag, ctx->sv_j, 0, d_active, ctx->sv_mu);  \
+    }
+        if (M <= 2) FB_SOLVE_REG(2, 2)
+        else if (M <= 4) FB_SOLVE_REG(4, 2)
+        else if (M <= 7) FB_SOLVE_REG(7, 2)
+        else if (M <= 10) FB_SOLVE_REG(10, 2)
+        else if (M <= 13) FB_SOLVE_REG(13, 1)
+        else FB_SOLVE_REG(16, 1)
+#undef FB_SOLVE_REG
+        FB_CUDA(cudaGetLastError());
+        return 0;
+    }
     int PR = 32;
     while (PR > 1 && sizeof(double) * ((size_t)N + 32 + (size_t)PR * N) > 200 * 1024) PR /= 2;
     const size_t smem = sizeof(double) * ((size_t)N + 32 + (size_t)PR * N);
