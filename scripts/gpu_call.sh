@@ -1,4 +1,3 @@
 set -x
-FB_SOLVE_MU=smem python scripts/dev_loop_var.py 2>&1 | grep -v WARNING | tail -2
-python scripts/dev_loop_var.py 2>&1 | grep -v WARNING | tail -2
-python -m pytest tests/test_gpu_fit.py -m gpu -x -q -k "gaussian_model or frank_fitter_normal or solver_loop or sweep" 2>&1 | tail -3
+ncu --set full --clock-control none --import-source on -k regex:'k_bin_reduce|k_sort_scatter|k_bin_index|k_sort_hist' -s 12 -c 6 -o gpurun_out/r01_bin_full python scripts/prof_bin.py > /dev/null 2>&1
+ls -la gpurun_out/
