@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *__restrict__ data,
 // Stable scatter of one digit pass.  The block's 4096 items are first ordered by digit in shared memory (stable:
 // warps, rounds and lanes in element order), then written out position by position, so that the items of one digit
 // leave as one contiguous run (16 items = 128 B on average) instead of one scattered 8-byte store per item.
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 3)      // 80 registers: three CTAs per SM (106 registers allowed two)
 k_sort_scatter(int64_t n, const uint64_t *__restrict__ items, int shift, const uint32_t *__restrict__ offs, int nblocks,
                uint64_t *__restrict__ out)
 {
