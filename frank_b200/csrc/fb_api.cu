@@ -46,6 +46,10 @@ int fb_ctx_destroy(fb_ctx *ctx)
         if (p) cudaFree(p);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->cev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -104,6 +104,8 @@ struct fb_ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t tev[2] = {};
     cudaStream_t stream2 = nullptr;     // fork / join branch of the solver graph
+    cudaStream_t stream3 = nullptr;     // side stream of the Cholesky (rest of the trailing updates)
+    std::vector<cudaEvent_t> cev;       // per block column: (panel done, rest of the update done)
     cudaEvent_t fev[2] = {};
     double timing[4] = {0, 0, 0, 0};
     int num_sms = 148;

@@ -222,9 +222,12 @@ k_build_dinv_pipe(int N, int nb, const double *__restrict__ M, const double *__r
 // trailing rows of both blocks.
 constexpr int SB = 16;                 // pivot sub-block
 
+// fuse != 0 (k >= 1): the rank-64 update of block row k by panel k - 1 has NOT been applied by k_chol_update (which then
+// skips that row, see launch_factor); this kernel applies it to its own two blocks first -- the same DMMA product, subtracted
+// from the same values, as k_chol_update<true> would have done -- so that the rest of update k - 1 can run beside it.
 __global__ void __launch_bounds__(256)
 k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active, int *__restrict__ info,
-             double *__restrict__ rdiag_all)
+             double *__restrict__ rdiag_all, int fuse)
 {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
@@ -238,10 +241,55 @@ k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__rest
     const bool off = blockIdx.x > 0;
     const int r0 = k * NB, c0 = j * NB;
     const int nk = min(NB, N - r0), nj = min(NB, N - c0);
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int i = e >> 6, jj = e & 63;
-        S[i][jj] = (i < nk && jj < nk && jj >= i) ? A[(size_t)(r0 + i) * N + r0 + jj] : (i == jj ? 1.0 : 0.0);   // identity padding
-        if (off) X[i][jj] = (i < nk && jj < nj) ? A[(size_t)(r0 + i) * N + c0 + jj] : 0.0;
+    if (fuse) {
+        // pending update: S -= P^T P, X -= P^T Q with P = U[k-1][k], Q = U[k-1][j] (both complete 64-row blocks of the
+        // previous panel).  P and Q are staged behind S and X in dynamic shared memory with leading dimension ULD.
+        double (*P)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_sm + 2 * NB * SLD);
+        double (*Q)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_sm + 2 * NB * SLD + NB * (NB + 4));
+        const int p0 = (k - 1) * NB;
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            P[r][c] = (r0 + c < N) ? A[(size_t)(p0 + r) * N + r0 + c] : 0.0;
+            Q[r][c] = (off && c0 + c < N) ? A[(size_t)(p0 + r) * N + c0 + c] : 0.0;
+        }
+        __syncthreads();
+        const int rb = (warp >> 1) * 16, cb = (warp & 1) * 32, fk = lane & 3, fm = lane >> 2;
+        double accS[2][4][2] = {}, accX[2][4][2] = {};
+#pragma unroll 4
+        for (int ks = 0; ks < NB; ks += 4) {
+            double af[2], bs[4], bx[4];
+#pragma unroll
+            for (int r = 0; r < 2; r++) af[r] = P[ks + fk][rb + r * 8 + fm];
+#pragma unroll
+            for (int c = 0; c < 4; c++) { bs[c] = P[ks + fk][cb + c * 8 + fm]; bx[c] = Q[ks + fk][cb + c * 8 + fm]; }
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(accS[r][c][0]), "+d"(accS[r][c][1]) : "d"(af[r]), "d"(bs[c]));
+                    if (off)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                     : "+d"(accX[r][c][0]), "+d"(accX[r][c][1]) : "d"(af[r]), "d"(bx[c]));
+                }
+        }
+        // S and X start from the un-updated A (the subtraction happens on the loaded value, as k_chol_update does in memory)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = rb + r * 8 + fm, jj = cb + c * 8 + 2 * fk + h;
+                    S[i][jj] = (i < nk && jj < nk && jj >= i) ? A[(size_t)(r0 + i) * N + r0 + jj] - accS[r][c][h] : (i == jj ? 1.0 : 0.0);
+                    if (off) X[i][jj] = (i < nk && jj < nj) ? A[(size_t)(r0 + i) * N + c0 + jj] - accX[r][c][h] : 0.0;
+                }
+    } else {
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int i = e >> 6, jj = e & 63;
+            S[i][jj] = (i < nk && jj < nk && jj >= i) ? A[(size_t)(r0 + i) * N + r0 + jj] : (i == jj ? 1.0 : 0.0);   // identity padding
+            if (off) X[i][jj] = (i < nk && jj < nj) ? A[(size_t)(r0 + i) * N + c0 + jj] : 0.0;
+        }
     }
     __syncthreads();
     for (int kb = 0; kb < NB; kb += SB) {
@@ -341,15 +389,17 @@ constexpr int ULD = NB + 4;            // leading dimension of the update's bloc
 
 template <bool MMA>
 __global__ void __launch_bounds__(256)
-k_chol_update(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active)
+k_chol_update(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active, int skip_first_row)
 {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     double *A = A_all + (size_t)b * N * N;
-    const int nt = nb - k - 1;
+    // blocks (bi, bj), first <= bi <= bj < nb, first = k + 1, or k + 2 when block row k + 1 is left to the next panel kernel
+    const int first = k + 1 + (skip_first_row ? 1 : 0);
+    const int nt = nb - first;
     int rem = blockIdx.x, ii = 0;
     while (rem >= nt - ii) { rem -= nt - ii; ii++; }
-    const int bi = k + 1 + ii, bj = bi + rem;
+    const int bi = first + ii, bj = bi + rem;
     extern __shared__ __align__(16) double dyn_sm[];
     double (*Ui)[ULD] = reinterpret_cast<double (*)[ULD]>(dyn_sm);
     double (*Uj)[ULD] = reinterpret_cast<double (*)[ULD]>(dyn_sm + NB * ULD);
@@ -1003,17 +1053,43 @@ static int launch_factor(fb_ctx *ctx, int B, const int *d_active, int *d_info)
 {
     const int N = ctx->N, nb = (N + NB - 1) / NB;
     const size_t blk2 = sizeof(double) * 2 * NB * SLD;
-    FB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk2));
+    const size_t blk4 = blk2 + sizeof(double) * 2 * NB * ULD;             // + the two blocks of the fused update
     const size_t blku = sizeof(double) * 2 * NB * ULD;
     static const bool upd_mma = [] { const char *e = getenv("FB_CHOL_UPDATE"); return !(e && e[0] == 'f'); }();   // =fma: DFMA variant
+    // FB_CHOL_FUSE=1: panel k + 1 applies update k to its own block row, the rest of update k runs beside it on the side
+    // stream (it touches block rows >= k + 2 only); panel k + 2 waits for it.  Removes the updates from the critical path.
+    static const bool fuse = [] { const char *e = getenv("FB_CHOL_FUSE"); return e && e[0] == '1'; }();
+    FB_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blk4));
     FB_CUDA(cudaFuncSetAttribute(k_chol_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blku));
     FB_CUDA(cudaFuncSetAttribute(k_chol_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blku));
+    if (!(fuse && upd_mma)) {
+        for (int k = 0; k < nb; k++) {
+            k_chol_panel<<<dim3(nb - k, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag, 0);
+            const int nt = nb - k - 1;
+            if (nt > 0) {
+                if (upd_mma) k_chol_update<true><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, 0);
+                else k_chol_update<false><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, 0);
+            }
+        }
+        FB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (!ctx->stream3) FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+    while ((int)ctx->cev.size() < 2 * nb) {
+        cudaEvent_t e;
+        FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->cev.push_back(e);
+    }
     for (int k = 0; k < nb; k++) {
-        k_chol_panel<<<dim3(nb - k, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag);
-        const int nt = nb - k - 1;
+        if (k >= 2 && nb - k >= 1 && (k - 2) + 2 <= nb - 1)                   // rest(k - 2) updated block row k
+            FB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->cev[2 * (k - 2) + 1], 0));
+        k_chol_panel<<<dim3(nb - k, B), 256, k > 0 ? blk4 : blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag, k > 0 ? 1 : 0);
+        const int nt = nb - k - 2;                                            // block rows k + 2 .. nb - 1
         if (nt > 0) {
-            if (upd_mma) k_chol_update<true><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active);
-            else k_chol_update<false><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active);
+            FB_CUDA(cudaEventRecord(ctx->cev[2 * k], ctx->stream));           // panel k done
+            FB_CUDA(cudaStreamWaitEvent(ctx->stream3, ctx->cev[2 * k], 0));   // (rest(k - 1) precedes on the same stream)
+            k_chol_update<true><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream3>>>(N, nb, k, ctx->sv_D, d_active, 1);
+            FB_CUDA(cudaEventRecord(ctx->cev[2 * k + 1], ctx->stream3));      // rest(k) done
         }
     }
     FB_CUDA(cudaGetLastError());
