@@ -196,3 +196,22 @@ def test_estimate_weights(golden):
         assert np.allclose(got, g[tag], rtol=1e-12, atol=0), tag
     got = fo.estimate_weights(np.hypot(u, v), V.real, nbins=100)
     assert np.allclose(got, g['uV'], rtol=1e-12, atol=0)
+
+
+def test_svd_fallback(golden):
+    """GaussianModel's SVD pseudo-inverse branch (statistical_models.py:747-755) on the reference's own outputs:
+    indefinite systems with and without a prior (entry by entry), and the rank-deficient mapping of 25 visibilities
+    at N = 40 (the solution is round-off along the null space, so the residual and the singular values are compared)."""
+    g = golden('svd_fallback.npz')
+    dht = fo.DHTTables(1.6 / fo.RAD_TO_ARCSEC, int(g["N"]))
+    for tag, p in [('a', None), ('b', g['p'])]:
+        fit = fo.GaussianSolve(dht, g['M'], g['j'], p)
+        assert fit.svd is not None and fit.chol is None
+        assert np.max(np.abs(fit.mu - g['mu_' + tag])) <= 1e-12 * np.max(np.abs(g['mu_' + tag]))
+        assert np.allclose(fit.svd[1], g['s1_' + tag], rtol=1e-12, atol=0)
+    fit = fo.GaussianSolve(dht, g['M'], g['j'])
+    assert np.max(np.abs(fit.Dsolve(g['j']) - g['Dj_a'])) <= 1e-12 * np.max(np.abs(g['Dj_a']))
+    fc = fo.GaussianSolve(dht, g['Mc'], g['jc'])
+    assert fc.svd is not None
+    assert np.max(np.abs(g['Mc'] @ fc.mu - g['jc'])) <= 1e-10 * np.max(np.abs(g['jc']))
+    assert np.allclose(np.sort(fc.svd[1])[:25], np.sort(g['s1_c'])[:25], rtol=1e-9, atol=0)
