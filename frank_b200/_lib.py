@@ -44,6 +44,7 @@ _SIGNATURES = {
     'fb_debug_j0': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_debug_j0_far': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_gaussian_fit': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
+    'fb_chol_solve': ([_c_p, _c_p, _c_i, _c_p, _c_p], _c_i),
     'fb_gaussian_svd': ([_c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_predict_visibilities': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
     'fb_apply_correction_dev': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_i),
@@ -213,6 +214,15 @@ class Context(object):
                                        _ptr(info))
         self.check(rc, 'fb_gaussian_fit')
         return mu, chol, info, rc
+
+    def chol_solve(self, U, b):
+        """fb_chol_solve: (U^T U)^-1 b for a vector b [N] or a matrix b [N, k] (columns = right-hand sides)."""
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        b = np.asarray(b, dtype=np.float64)
+        B = np.ascontiguousarray(b.reshape(b.shape[0], -1).T)          # one right-hand side per row
+        X = np.empty_like(B)
+        self.check(self._lib.fb_chol_solve(self._h, _ptr(U), B.shape[0], _ptr(B), _ptr(X)), 'fb_chol_solve')
+        return np.ascontiguousarray(X.T).reshape(b.shape)
 
     def gaussian_svd(self, M, p=None):
         """fb_gaussian_svd: U, s, Vt of D^-1 = M (+ Y^T diag(1/p) Y) as scipy.linalg.svd would return them."""

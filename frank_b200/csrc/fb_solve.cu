@@ -763,18 +763,19 @@ k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__rest
 template <int M, int NBUF>
 __global__ void __launch_bounds__(256)
 k_solve_mu_reg(int N, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ jvec,
-               int j_stride, const int *__restrict__ active, double *__restrict__ mu_all)
+               int j_stride, const int *__restrict__ active, double *__restrict__ mu_all, int shared_factor)
 {
     constexpr int NP = 32 * M, BUF = NP * 33;
     const int b = blockIdx.x;
     if (active && !active[b]) return;
-    const double *U = U_all + (size_t)b * N * N;
+    const size_t ub = shared_factor ? 0 : b;                // shared_factor: every CTA solves with factor 0 (many right-hand sides)
+    const double *U = U_all + ub * N * N;
     extern __shared__ __align__(16) double sm[];
     double *rd = sm;                                        // [NP]
     double *P0 = sm + NP;                                   // [NBUF][BUF]
     const uint32_t p_s = (uint32_t)__cvta_generic_to_shared(P0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < NP; i += 256) rd[i] = i < N ? rdiag_all[(size_t)b * N + i] : 0.0;
+    for (int i = tid; i < NP; i += 256) rd[i] = i < N ? rdiag_all[ub * N + i] : 0.0;
     auto stage_rows = [&](const int m0, const int buf) {    // rows 32 m0 .. +31, columns 32 m0 .. NP-1 -> [r][NP]
         const int r1 = 32 * m0;
 #pragma unroll 1
@@ -1096,17 +1097,20 @@ static int launch_factor(fb_ctx *ctx, int B, const int *d_active, int *d_info)
     return 0;
 }
 
-static int launch_solve(fb_ctx *ctx, int B, const int *d_active, cudaStream_t stream)
+// mu_b = U_b^-1 U_b^-T rhs_b for B problems (shared_factor = 0), or B right-hand sides of one factor (shared_factor = 1;
+// N <= 512 only)
+static int launch_solve_rhs(fb_ctx *ctx, int B, const int *d_active, cudaStream_t stream, const double *rhs, int rhs_stride,
+                            double *out, int shared_factor)
 {
     const int N = ctx->N;
     static const bool reg = [] { const char *e = getenv("FB_SOLVE_MU"); return !(e && e[0] == 's'); }();   // =smem: the shared-memory variant
-    if (reg && N <= 512) {
+    if ((reg || shared_factor) && N <= 512) {
         const int M = (N + 31) / 32;
 #define FB_SOLVE_REG(MM, NBUF)                                                                                                 \
     {                                                                                                                          \
         const size_t smem = sizeof(double) * (32 * MM + (size_t)NBUF * 32 * MM * 33);                                          \
         FB_CUDA(cudaFuncSetAttribute(k_solve_mu_reg<MM, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-        k_solve_mu_reg<MM, NBUF><<<B, 256, smem, stream>>>(N, ctx->sv_D, ctx->sv_rdiag, ctx->sv_j, 0, d_active, ctx->sv_mu);  \
+        k_solve_mu_reg<MM, NBUF><<<B, 256, smem, stream>>>(N, ctx->sv_D, ctx->sv_rdiag, rhs, rhs_stride, d_active, out, shared_factor); \
     }
         if (M <= 2) FB_SOLVE_REG(2, 2)
         else if (M <= 4) FB_SOLVE_REG(4, 2)
@@ -1118,13 +1122,19 @@ static int launch_solve(fb_ctx *ctx, int B, const int *d_active, cudaStream_t st
         FB_CUDA(cudaGetLastError());
         return 0;
     }
+    if (shared_factor) FB_FAIL(-34, "fb_chol_solve: N > 512 is not supported on the device");
     int PR = 32;
     while (PR > 1 && sizeof(double) * ((size_t)N + 32 + (size_t)PR * N) > 200 * 1024) PR /= 2;
     const size_t smem = sizeof(double) * ((size_t)N + 32 + (size_t)PR * N);
     FB_CUDA(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_mu<<<B, 1024, smem, stream>>>(N, PR, ctx->sv_D, ctx->sv_rdiag, ctx->sv_j, 0, d_active, ctx->sv_mu);
+    k_solve_mu<<<B, 1024, smem, stream>>>(N, PR, ctx->sv_D, ctx->sv_rdiag, rhs, rhs_stride, d_active, out);
     FB_CUDA(cudaGetLastError());
     return 0;
+}
+
+static int launch_solve(fb_ctx *ctx, int B, const int *d_active, cudaStream_t stream)
+{
+    return launch_solve_rhs(ctx, B, d_active, stream, ctx->sv_j, 0, ctx->sv_mu, 0);
 }
 
 static int launch_factor_solve(fb_ctx *ctx, int B, const int *d_active, int *d_info)
@@ -1257,6 +1267,42 @@ int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host
     }
     if (worst) ctx->err = "Cholesky factorisation met a non-positive pivot";
     return worst;
+}
+
+int fb_chol_solve(fb_ctx *ctx, const double *host_U, int nrhs, const double *host_B, double *host_X)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0) FB_FAIL(-30, "fb_chol_solve: fb_dht_setup has not been called");
+    if (!host_U || !host_B || !host_X || nrhs < 1) FB_FAIL(-31, "fb_chol_solve: bad arguments");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    if (N > 512) FB_FAIL(-34, "fb_chol_solve: N > 512 is not supported on the device");
+    int rc = ensure_solver_ws(ctx, 1);
+    if (rc) return rc;
+    std::vector<double> rd(N);
+    for (size_t i = 0; i < N; i++) {
+        const double d = host_U[i * N + i];
+        if (!(d > 0.0)) FB_FAIL(FB_E_NOTPD, "fb_chol_solve: non-positive diagonal in the factor");
+        rd[i] = 1.0 / d;
+    }
+    double *d_B = nullptr, *d_X = nullptr;
+    FB_CUDA(cudaMalloc(&d_B, sizeof(double) * (size_t)nrhs * N));
+    if (cudaMalloc(&d_X, sizeof(double) * (size_t)nrhs * N) != cudaSuccess) { cudaFree(d_B); FB_FAIL(-35, "fb_chol_solve: out of memory"); }
+    int status = 0;
+    do {
+        if (cudaMemcpyAsync(ctx->sv_D, host_U, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(ctx->sv_rdiag, rd.data(), sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_B, host_B, sizeof(double) * (size_t)nrhs * N, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { status = -36; break; }
+        status = launch_solve_rhs(ctx, nrhs, nullptr, ctx->stream, d_B, (int)N, d_X, 1);
+        if (status) break;
+        if (cudaMemcpyAsync(host_X, d_X, sizeof(double) * (size_t)nrhs * N, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) status = -37;
+    } while (0);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_B);
+    cudaFree(d_X);
+    if (status < 0 && status != -34) ctx->err = "fb_chol_solve: CUDA error";
+    return status;
 }
 
 int fb_frank_normal_loop(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p_init,

@@ -6,6 +6,7 @@ libfrankb200 (hand-written sm_100a CUDA, reached through ctypes); NumPy only car
 results.  There is no CPU path: constructing these objects without a CUDA device raises.
 """
 import logging
+import os
 
 import numpy as np
 
@@ -13,6 +14,11 @@ from frank_b200 import _lib
 from frank_b200.constants import rad_to_arcsec, deg_to_rad
 
 __all__ = ['VisibilityMapping', 'GaussianModel', 'LogNormalMAPModel']
+
+
+# Dsolve through fb_chol_solve (device; N <= 512) rather than SciPy on the GPU-computed factor; FRANK_B200_DEVICE_DSOLVE=0
+# selects the SciPy helper
+_DEVICE_DSOLVE = os.environ.get('FRANK_B200_DEVICE_DSOLVE', '1') == '1'
 
 
 def _is_cuda_tensor(x):
@@ -356,6 +362,10 @@ class GaussianModel(object):
             U, s1, V = self._Dsvd
             b = np.asarray(b)
             return np.dot(V.T, (np.dot(U.T, b).T * s1).T)
+        if _DEVICE_DSOLVE and self._DHT.size <= 512:
+            ctx = _lib.get_context(self._device)
+            ctx.dht_setup(self._DHT)
+            return ctx.chol_solve(self._U, b)
         import scipy.linalg
         return scipy.linalg.cho_solve((self._U, False), b)
 

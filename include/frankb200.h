@@ -123,6 +123,11 @@ int fb_debug_prepped(fb_ctx *ctx, int64_t n, double *host_a, double *host_kz, do
 int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host_j, const double *host_p, int has_prior,
                     double *host_mu, double *host_chol, int *host_info);
 
+/* GaussianModel.Dsolve (frank/statistical_models.py:762-781, the Cholesky branch): X = (U^T U)^-1 B for nrhs right-hand sides
+ * with the upper factor U [N*N] returned by fb_gaussian_fit / fb_frank_normal_loop.  B and X are [nrhs * N], one right-hand
+ * side per row (host).  N <= 512.  Used for the posterior covariance (Dsolve of the identity) and the Laplace evidence. */
+int fb_chol_solve(fb_ctx *ctx, const double *host_U, int nrhs, const double *host_B, double *host_X);
+
 /* SVD fallback of GaussianModel._fit (frank/statistical_models.py:747-755: scipy.linalg.svd(Dinv) when cho_factor
  * raises LinAlgError).  D^-1 as above (one power spectrum); outputs U [N*N], s [N] (descending), Vt [N*N] with
  * D^-1 = U diag(s) Vt, computed by one-sided Jacobi rotations on the device (D^-1 is symmetric: s_i = |lambda_i|,

@@ -319,3 +319,25 @@ def test_svd_fallback_vs_reference_golden(fb, golden):
     _, _, Vh = np.linalg.svd(Mc)
     pr_got, pr_ref = Vh[:rank] @ sol.mean, Vh[:rank] @ g['mu_c']
     assert np.max(np.abs(pr_got - pr_ref)) <= 1e-7 * np.max(np.abs(pr_ref))
+
+
+@pytest.mark.parametrize('N', [40, 300, 417])
+def test_dsolve_on_device(fb, N):
+    """GaussianModel.Dsolve / covariance (statistical_models.py:762-781, Cholesky branch) through fb_chol_solve against
+    scipy.linalg.cho_solve on the same factor: a vector, a few right-hand sides, and the identity (covariance)."""
+    import scipy.linalg
+    rng = np.random.default_rng(3 + N)
+    dht = fb.DHT(1.6 / fb.r2a, N)
+    ctx = fb.lib.get_context(0)
+    ctx.dht_setup(dht)
+    G = rng.standard_normal((N, N))
+    U = np.triu(scipy.linalg.cho_factor(G @ G.T + N * np.eye(N))[0])
+    for b in (rng.standard_normal(N), rng.standard_normal((N, 7)), np.eye(N)):
+        ref = scipy.linalg.cho_solve((U, False), b)
+        got = ctx.chol_solve(U, b)
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+    # through the model: D^-1 D = I with the GPU factor of a reference mapping
+    gm = fb.GaussianModel(dht, G @ G.T + N * np.eye(N), rng.standard_normal(N))
+    assert gm._Dsvd is None
+    assert np.max(np.abs(gm.covariance @ (G @ G.T + N * np.eye(N)) - np.eye(N))) <= 1e-10
