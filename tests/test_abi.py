@@ -50,3 +50,32 @@ def test_product_does_not_import_oracle():
             if fn.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert 'oracle' not in txt.replace('frank_oracle_unused', ''), os.path.join(dirpath, fn)
+
+
+def test_binding_arity_matches_header():
+    """Every ctypes signature in frank_b200/_lib.py has as many arguments as the prototype in include/frankb200.h,
+    with pointers, 64-bit counts, ints and doubles in the same positions (guards against ABI drift)."""
+    from frank_b200 import _lib
+    src = open(os.path.join(ROOT, 'include', 'frankb200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = dict(re.findall(r'\b(fb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', src))
+    assert set(protos) == set(_lib.exported_symbols())
+
+    def kind(arg):
+        arg = arg.strip()
+        if arg in ('void', ''):
+            return None
+        if '*' in arg:
+            return 'p'
+        if 'int64_t' in arg:
+            return 'l'
+        if arg.startswith('double'):
+            return 'd'
+        return 'i'
+    ckind = {ctypes.c_void_p: 'p', ctypes.c_int64: 'l', ctypes.c_longlong: 'l', ctypes.c_int: 'i', ctypes.c_double: 'd',
+             ctypes.c_char_p: 'p'}
+    for name, args in protos.items():
+        want = [k for k in (kind(a) for a in args.split(',')) if k]
+        argtypes, _ = _lib._SIGNATURES[name]
+        got = [ckind.get(t, 'p') for t in argtypes]          # POINTER(...) types count as pointers
+        assert got == want, f"{name}: header {want} vs binding {got}"
