@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libfrankb200.so')
 
-FB_E_QRANGE, FB_E_NOTPD, FB_E_BADP, FB_E_NOCONV = 1, 2, 3, 4
+FB_E_QRANGE, FB_E_NOTPD, FB_E_BADP, FB_E_NOCONV, FB_E_RETRY, FB_E_SLOPE = 1, 2, 3, 4, 5, 6
 MODEL_CODE = {'opt_thick': 0, 'opt_thin': 1, 'debris': 2}
 
 
@@ -32,11 +32,21 @@ _SIGNATURES = {
     'fb_ctx_create': ([ctypes.POINTER(_c_p), _c_i], _c_i),
     'fb_ctx_destroy': ([_c_p], _c_i),
     'fb_last_error': ([_c_p], ctypes.c_char_p),
+    'fb_set_option': ([_c_p, ctypes.c_char_p, _c_d], _c_i),
     'fb_dht_setup': ([_c_p, _c_i, _c_d, _c_p, _c_p, _c_p, _c_d], _c_i),
     'fb_map_visibilities_dev': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_i, _c_p, _c_i, ctypes.POINTER(FBGeometry),
                                  _c_i, _c_d, _c_p, _c_i, _c_d, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_map_visibilities_host': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_i, _c_p, _c_i, ctypes.POINTER(FBGeometry),
                                   _c_i, _c_d, _c_p, _c_i, _c_d, _c_p, _c_p, _c_p, _c_p], _c_i),
+    'fb_map_visibilities_dev_async': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_i, _c_p, _c_i, ctypes.POINTER(FBGeometry),
+                                       _c_i, _c_d, _c_p, _c_i, _c_d, _c_p, _c_p, _c_p], _c_i),
+    'fb_map_sync': ([_c_p, _c_p], _c_i),
+    'fb_comm_unique_id': ([_c_p], _c_i),
+    'fb_comm_init': ([_c_p, _c_i, _c_i, _c_p], _c_i),
+    'fb_comm_destroy': ([_c_p], _c_i),
+    'fb_comm_info': ([_c_p, _c_p, _c_p], _c_i),
+    'fb_comm_allgather': ([_c_p, _c_p, _c_l, _c_p], _c_i),
+    'fb_comm_allreduce_sum_dev': ([_c_p, _c_p, _c_l], _c_i),
     'fb_last_map_timing': ([_c_p, _c_p], _c_i),
     'fb_timer_start': ([_c_p], _c_i),
     'fb_timer_stop': ([_c_p, _c_p], _c_i),
@@ -56,6 +66,8 @@ _SIGNATURES = {
     'fb_ln_eval': ([_c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_ln_newton_direction': ([_c_p, _c_p, _c_i, _c_p, _c_p, _c_p], _c_i),
     'fb_ln_posterior': ([_c_p, _c_p, _c_p, _c_d, _c_d, _c_p, _c_p, _c_p, _c_p], _c_i),
+    'fb_frank_lognormal_loop': ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_d, _c_d, _c_d, _c_d, _c_p, _c_d, _c_i, _c_d, _c_p, _c_p, _c_p,
+                                 _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i], _c_i),
     'fb_frank_normal_loop': ([_c_p, _c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p,
                               _c_p, _c_p, _c_p, _c_p, _c_i], _c_i),
 }
@@ -123,6 +135,9 @@ class Context(object):
     def error(self):
         return self._lib.fb_last_error(self._h).decode()
 
+    def set_option(self, name, value):
+        self.check(self._lib.fb_set_option(self._h, name.encode(), float(value)), 'fb_set_option')
+
     def check(self, rc, what):
         if rc < 0:
             raise RuntimeError(f"frank_b200: {what} failed ({rc}): {self.error()}")
@@ -130,6 +145,10 @@ class Context(object):
 
     # -- DHT ---------------------------------------------------------------------------------
     def dht_setup(self, dht, x_max=0.0):
+        if dht.order != 0:
+            # the device kernels evaluate J0 only (fb_j0_table.h); an order-nu transform would silently mix J_nu tables
+            # with J0 design rows
+            raise NotImplementedError("frank_b200: the CUDA path implements the order-0 transform only (nu = 0)")
         key = (dht.Rmax, dht.size, dht.order)
         if self._dht_key == key:
             return
@@ -142,16 +161,65 @@ class Context(object):
 
     # -- mapping -----------------------------------------------------------------------------
     def map_visibilities(self, n, u, v, V, w, w_stride, geom, vis_model, model_scale, H2, check_qbounds,
-                         q_last, M, j, H0, host=False):
-        """Thin call into fb_map_visibilities_{dev,host}.  Returns (status, qmin, qmax)."""
+                         q_last, M, j, H0, host=False, chan=None, nchan=1):
+        """Thin call into fb_map_visibilities_{dev,host}.  Returns (status, qmin, qmax).  `chan` (int32 [n], values in
+        [0, nchan)) selects the multi-frequency path: M [nchan, N, N], j [nchan, N]."""
         qmm = np.zeros(2)
         fn = self._lib.fb_map_visibilities_host if host else self._lib.fb_map_visibilities_dev
         H2p = None if H2 is None else np.ascontiguousarray(H2, dtype=np.float64)
-        rc = fn(self._h, int(n), _ptr(u), _ptr(v), _ptr(V), _ptr(w), int(w_stride), None, 1, ctypes.byref(geom),
+        rc = fn(self._h, int(n), _ptr(u), _ptr(v), _ptr(V), _ptr(w), int(w_stride), _ptr(chan), int(nchan), ctypes.byref(geom),
                 int(vis_model), float(model_scale), _ptr(H2p), int(bool(check_qbounds)), float(q_last),
                 _ptr(M), _ptr(j), _ptr(H0), _ptr(qmm))
         self.check(rc, 'fb_map_visibilities')
         return rc, qmm[0], qmm[1]
+
+    def map_visibilities_async(self, n, u, v, V, w, w_stride, geom, vis_model, model_scale, H2, check_qbounds,
+                               q_last, M, j, H0, chan=None, nchan=1):
+        """fb_map_visibilities_dev_async: enqueue only (device tensors); pair with map_sync()."""
+        H2p = None if H2 is None else np.ascontiguousarray(H2, dtype=np.float64)
+        rc = self._lib.fb_map_visibilities_dev_async(self._h, int(n), _ptr(u), _ptr(v), _ptr(V), _ptr(w), int(w_stride), _ptr(chan),
+                                                     int(nchan), ctypes.byref(geom), int(vis_model), float(model_scale), _ptr(H2p),
+                                                     int(bool(check_qbounds)), float(q_last), _ptr(M), _ptr(j), _ptr(H0))
+        return self.check(rc, 'fb_map_visibilities_dev_async')
+
+    def map_sync(self):
+        """fb_map_sync: wait for the asynchronous mapping call; returns (status, qmin, qmax)."""
+        qmm = np.zeros(2)
+        rc = self.check(self._lib.fb_map_sync(self._h, _ptr(qmm)), 'fb_map_sync')
+        return rc, qmm[0], qmm[1]
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    def comm_unique_id(self):
+        buf = np.zeros(128, dtype=np.uint8)
+        rc = self._lib.fb_comm_unique_id(_ptr(buf))
+        if rc != 0:
+            raise RuntimeError(f"frank_b200: fb_comm_unique_id failed ({rc}): is NCCL (libnccl.so.2) available?")
+        return buf
+
+    def comm_init(self, nranks, rank, unique_id):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        self.check(self._lib.fb_comm_init(self._h, int(nranks), int(rank), _ptr(uid)), 'fb_comm_init')
+
+    def comm_destroy(self):
+        self._lib.fb_comm_destroy(self._h)
+
+    def comm_info(self):
+        """(attached, rank, nranks) of the context's communicator."""
+        r, n = ctypes.c_int(0), ctypes.c_int(1)
+        has = self._lib.fb_comm_info(self._h, ctypes.byref(r), ctypes.byref(n))
+        return bool(has), r.value, n.value
+
+    def comm_allgather(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        _, _, n = self.comm_info()
+        out = np.empty((n, x.size))
+        self.check(self._lib.fb_comm_allgather(self._h, _ptr(x), x.size, _ptr(out)), 'fb_comm_allgather')
+        return out
+
+    def comm_allreduce_sum_dev(self, t):
+        """In-place sum of a float64 CUDA tensor over the communicator, asynchronous on the library stream."""
+        self.check(self._lib.fb_comm_allreduce_sum_dev(self._h, _ptr(t), t.numel()), 'fb_comm_allreduce_sum_dev')
 
     def apply_correction_dev(self, u, v, V, geom, want_q=False):
         """fb_apply_correction_dev on torch CUDA tensors: returns (up, vp, wp, Vp[, q]) as device tensors (Vp None when V
@@ -266,6 +334,32 @@ class Context(object):
                 'hist_p': hp, 'hist_mu': hm}
 
     # -- LogNormal model ------------------------------------------------------------------------
+    def frank_lognormal_loop(self, M, j, p_init, guess, s0, alpha=0.0, p0=0.0, Tinv=None, tol=1e-3, max_iter=-1,
+                             full_hessian=1.0, newton_tol=1e-7, want_chol=True, hist_cap=0):
+        """fb_frank_lognormal_loop: the log-normal MAP fit (max_iter < 0) or the whole power-spectrum iteration around
+        it, device resident.  Returns a dict; 'status' is 0, FB_E_BADP, FB_E_NOTPD or FB_E_SLOPE."""
+        N = M.shape[0]
+        M = np.ascontiguousarray(M, dtype=np.float64); j = np.ascontiguousarray(j, dtype=np.float64)
+        p_init = np.ascontiguousarray(p_init, dtype=np.float64).reshape(N)
+        guess = np.ascontiguousarray(guess, dtype=np.float64).reshape(N)
+        Tc = None if Tinv is None else np.ascontiguousarray(Tinv, dtype=np.float64)
+        s, p = np.empty(N), np.empty(N)
+        chol = np.empty((N, N)) if want_chol else None
+        niter, conv, info = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        stats = np.zeros(7, dtype=np.int64)
+        hp = hs = None
+        if hist_cap > 0:
+            hp, hs = np.zeros((hist_cap, N)), np.zeros((hist_cap, N))
+        rc = self._lib.fb_frank_lognormal_loop(self._h, _ptr(M), _ptr(j), _ptr(p_init), _ptr(guess), float(s0), float(full_hessian),
+                                               float(alpha), float(p0), _ptr(Tc), float(tol), int(max_iter), float(newton_tol),
+                                               _ptr(s), _ptr(p), _ptr(chol), _ptr(niter), _ptr(conv), _ptr(info), _ptr(stats),
+                                               _ptr(hp), _ptr(hs), int(hist_cap))
+        self.check(rc, 'fb_frank_lognormal_loop')
+        return {'s': s, 'p': p, 'chol': chol, 'niter': int(niter[0]), 'converged': bool(conv[0]), 'info': int(info[0]),
+                'status': rc, 'hist_p': hp, 'hist_s': hs,
+                'newton': {'steps': int(stats[0]), 'evaluations': int(stats[1]), 'hessians': int(stats[2]),
+                           'status_counts': stats[3:7].tolist()}}
+
     def ln_setup(self, M, j, s0, full_hessian=1.0):
         M = np.ascontiguousarray(M, dtype=np.float64); j = np.ascontiguousarray(j, dtype=np.float64)
         self.check(self._lib.fb_ln_setup(self._h, _ptr(M), _ptr(j), float(s0), float(full_hessian)), 'fb_ln_setup')

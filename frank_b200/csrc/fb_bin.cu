@@ -148,7 +148,7 @@ k_bin_reduce(int nbins, const uint32_t *__restrict__ start, const uint64_t *__re
 // Workspace of the binner beyond the sort buffers: segment starts [nbins + 1].
 static int bin_reserve(fb_ctx *ctx, int64_t n, int nbins)
 {
-    int rc = fb_reserve_prep(ctx, (n + FB_TV - 1) / FB_TV * FB_TV);          // sort items (2 x 8 B per visibility), digit histograms
+    int rc = fb_reserve_lane(ctx, ctx->lane[0], n, 1);          // sort items (2 x 8 B per visibility), records, digit histograms
     if (rc) return rc;
     if ((size_t)nbins + 1 > ctx->bin_cap) {
         if (ctx->d_binstart) FB_CUDA(cudaFree(ctx->d_binstart));
@@ -174,17 +174,18 @@ int fb_uv_bin_dev(fb_ctx *ctx, int64_t n, const double *dev_uv, const double *de
     int rc = bin_reserve(ctx, n, nbins);
     if (rc) return rc;
     const double norm = 1.0 / bin_width;                                        // utilities.py:213
-    uint64_t *buf0 = ctx->d_items, *buf1 = ctx->d_items + ctx->cap;
+    FbLane &ln = ctx->lane[0];
+    uint64_t *buf0 = ln.d_items, *buf1 = ln.d_items + ln.cap;
     const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 32);
     const double2 *Vc = v_is_complex ? (const double2 *)dev_V : nullptr;
     const double *Vr = v_is_complex ? nullptr : dev_V;
-    double4 *rec = (double4 *)ctx->d_rec;
+    double4 *rec = (double4 *)ln.d_rec;
     k_bin_index<<<grid, 256, 0, ctx->stream>>>(n, dev_uv, Vc, Vr, dev_w, w_stride, bin_width, norm, nbins, dev_idx, buf0, rec);
     FB_CUDA(cudaGetLastError());
     int nbits = 8;
     while (nbits < 32 && (1LL << nbits) <= nbins) nbits += 8;                   // keys 0 .. nbins
     int st = 0;
-    const uint64_t *sorted = fb_radix_sort_items(ctx, n, buf0, buf1, nbits, &st);
+    const uint64_t *sorted = fb_radix_sort_items(ctx, ln, n, buf0, buf1, nbits, &st);
     if (st) return st;
     k_bin_starts<<<grid, 256, 0, ctx->stream>>>(n, sorted, nbins, ctx->d_binstart);
     // warps per bin: one while there are enough bins to fill the machine, up to a whole block for coarse binnings

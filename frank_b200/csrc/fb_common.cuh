@@ -38,6 +38,38 @@ struct FbGramType {
     int ld;           // tiles per row of the partial block: b_nt (OFF) | a_nt / 2 + 1 (DIAG)
 };
 
+constexpr int FB_MAX_CHAN = 64;        // channels of one multi-frequency mapping call (np.unique(frequencies))
+constexpr int FB_MAX_CHUNKS = 64;      // chunks of the host entry point's copy / compute pipeline
+
+// status bits a mapping call raises on the device (no host read in the middle of a call)
+constexpr int FB_ST_QRANGE = 1;        // data beyond the last collocation point (check_qbounds)
+constexpr int FB_ST_TABLE = 2;         // the J0 table does not reach a_max * j_{N-1}: the call is redone with a larger table
+
+// One in-flight chunk of a mapping call: a stream and every per-visibility workspace.  The device entry points use
+// lane 0 for the whole call; the host entry point alternates between the two lanes, so that the copy and the kernels of
+// consecutive chunks overlap and the tail of one chunk's Gram kernel is filled by the next chunk's kernels.
+struct FbLane {
+    cudaStream_t stream = nullptr;
+    int64_t cap = 0;                                                   // padded visibilities the workspaces hold
+    double *d_a = nullptr, *d_sw = nullptr, *d_swV = nullptr, *d_kz = nullptr;   // sorted, padded, SoA
+    double *d_amid = nullptr;      // per tile of FB_TV sorted visibilities: (min a, max a)
+    double *d_rec = nullptr;       // unsorted records (a, sqrt w, sqrt w * Re V, kz), 32 B each
+    uint64_t *d_items = nullptr;   // 2 x cap sort buffers of (key << 32 | index)
+    uint32_t *d_perm = nullptr;    // sorted position -> original index
+    uint32_t *d_hist = nullptr;
+    size_t hist_cap = 0;
+    double *d_red = nullptr;       // pre-pass block reductions
+    int red_cap = 0;
+    int *d_seg = nullptr;          // [2 * (FB_MAX_CHAN + 1)]: sorted start | padded start of every channel
+    double *d_partial = nullptr;   // partial blocks of this lane's Gram launches (one set per channel)
+    size_t partial_cap = 0;
+    double *d_in = nullptr;        // device staging of the host entry point: u | v | V | w | chan
+    int64_t in_cap = 0;
+    double *h_pin = nullptr;       // pinned host staging for pageable inputs (same layout as d_in)
+    int64_t pin_cap = 0;
+    cudaEvent_t ev_copied = nullptr, ev_done = nullptr, ev_acc = nullptr, ev_g0 = nullptr, ev_g1 = nullptr, ev_p0 = nullptr;
+};
+
 struct fb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -50,44 +82,43 @@ struct fb_ctx {
     // J0 table
     double2 *d_tab = nullptr;
     int tab_rows = 0;
-    // panel decomposition
+    // panel decomposition and the work table of the Gram kernel (both depend on N only: built by fb_dht_setup)
     int P = 0, ntypes = 0;
     std::vector<FbGramType> h_types;
     FbGramType *d_types = nullptr;
     int *d_tile_panel = nullptr, *d_panel_t0 = nullptr, *d_panel_nt = nullptr;
     int *d_pair_code = nullptr;    // [P * P * 3]: (first OFF type, second OFF type | -1, rows in the first) ; DIAG type on the diagonal
-    // a mapping call may run as two parts (host entry point: the copy of the second half overlaps the first half's
-    // kernels); each part has its own work tables and its own range of partial slots
-    int *d_work2 = nullptr;
-    int work2_cap = 0;
-    long long part_tiles[2] = {0, 0};
-    const int *part_typetab[2] = {nullptr, nullptr};
-    int part_slot0[2] = {0, 0};
-    cudaEvent_t pev[4] = {};
-    int *d_work = nullptr;         // per launch: per-CTA item ranges, items (type, chunk, partial slot), per type (chunks, first slot)
-    int work_cap = 0;
-    // workspaces
-    int64_t cap = 0;
-    double *d_a = nullptr, *d_sw = nullptr, *d_swV = nullptr, *d_kz = nullptr;   // sorted, padded, SoA
-    double *d_amid = nullptr;      // per tile of FB_TV sorted visibilities: (min a, max a)
+    int *d_work = nullptr;         // per-CTA item ranges [grid + 1], items (type, chunk, partial slot) [3 n_items], per type (chunks, first slot)
+    int n_items = 0;
     int sort_bits = 16;            // key bits of the baseline sort (16 or 24)
-    double *d_rec = nullptr;       // unsorted records (a, sqrt w, sqrt w * Re V, kz), 32 B each
-    uint64_t *d_items = nullptr;   // 2 x cap sort buffers of (key << 32 | index)
-    uint32_t *d_perm = nullptr;    // sorted position -> original index
-    uint32_t *d_hist = nullptr;
-    size_t hist_cap = 0;
+    // mapping lanes
+    FbLane lane[2];
+    cudaStream_t stream_copy = nullptr;
+    double *d_S = nullptr;         // [nchan][npairs][64] unscaled Gram accumulated over the chunks of a call
+    size_t S_cap = 0;
+    double *d_chunkred = nullptr;  // [FB_MAX_CHUNKS][4]: H0 sum, min q, max q, (unused) of every chunk
+    double *d_result = nullptr;    // [4]: H0, min q, max q, status
+    int *d_status = nullptr;       // status bits of the call in flight
+    double *h_result = nullptr;    // pinned mirror of d_result
     uint32_t *d_binstart = nullptr;   // uv binner: segment starts of the sorted items [nbins + 1]
     size_t bin_cap = 0;
-    double *d_red = nullptr;     // pre-pass block reductions
-    int red_cap = 0;
-    double *d_partial = nullptr;
-    size_t partial_cap = 0;
     double *d_H2 = nullptr;
-    // staging for the host entry point
-    double *d_in = nullptr;
-    int64_t in_cap = 0;
-    double *d_out = nullptr;
+    double *d_out = nullptr;       // host entry point: M | j | H0 on the device
     size_t out_cap = 0;
+    int map_chunks = 1;            // chunks of the most recent call (timing)
+    std::vector<cudaEvent_t> mev;  // per chunk: (start, sorted, gram done, accumulated); two more for the copy stream
+    std::vector<double> h_H2;      // debris H2 currently on the device
+    int stage_threads = 8;         // host threads gathering pageable inputs into the pinned staging ring
+    int64_t map_chunk = 250000;    // smallest first chunk of the host entry point's pipeline (visibilities)
+    double map_growth = 3.0;       // ratio of consecutive chunk sizes
+    int map_kmax = 4;              // most chunks per call
+    bool force_staging = false;    // treat every host input as pageable (tests)
+    // multi-GPU: NCCL communicator attached by fb_comm_init (library loaded with dlopen)
+    void *nccl_lib = nullptr;
+    void *nccl_comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    double *d_pack = nullptr;      // packed all-reduce buffer
+    size_t pack_cap = 0;
     // solver workspaces (fb_solve.cu)
     int sv_B = 0, sv_N = 0;
     double *sv_D = nullptr, *sv_p = nullptr, *sv_mu = nullptr, *sv_tr2 = nullptr, *sv_alpha = nullptr, *sv_p0 = nullptr;
@@ -100,6 +131,9 @@ struct fb_ctx {
     // LogNormal model state
     int ln_N = 0;
     double *ln_S = nullptr, *ln_vec = nullptr;
+    double *ln_pin = nullptr;          // pinned (mapped) scalars of the device-resident Newton iteration
+    double *ln_ws = nullptr;           // its vectors
+    int ln_ws_N = 0;
     double ln_s0 = 0.0, ln_full_hess = 1.0;
     cudaEvent_t ev[8] = {};
     cudaEvent_t tev[2] = {};
@@ -131,14 +165,24 @@ struct fb_ctx {
     } while (0)
 
 // kernels / launchers implemented in the .cu files
-int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
-                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax, double *host_H0);
-int fb_reserve_prep(fb_ctx *ctx, int64_t n_pad);
-int fb_reserve_sort(fb_ctx *ctx, int64_t n);
-int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_model);
-int fb_launch_gram_finalize(fb_ctx *ctx, int nparts, double model_scale, double *dev_M, double *dev_j);
+struct FbMapJob {              // arguments of one mapping call, shared by its chunks
+    fb_geometry geom;
+    int vis_model = 0;
+    int nchan = 1;
+    int check_qbounds = 0;
+    double q_last = 0.0;
+};
+int fb_reserve_lane(fb_ctx *ctx, FbLane &ln, int64_t n, int nchan);
+int fb_reserve_sort(fb_ctx *ctx, FbLane &ln, int64_t n);
+int fb_enqueue_prep(fb_ctx *ctx, FbLane &ln, int chunk, int64_t n, const double *u, const double *v, const double *V,
+                    const double *w, int w_stride, const int32_t *chan, const FbMapJob &job);
+int fb_enqueue_sort(fb_ctx *ctx, FbLane &ln, int chunk, int64_t n, const int32_t *chan, int nchan);
+int fb_enqueue_gram(fb_ctx *ctx, FbLane &ln, int chan, int vis_model);
+int fb_enqueue_accumulate(fb_ctx *ctx, FbLane &ln, int nchan, int first);
+int fb_enqueue_scale(fb_ctx *ctx, cudaStream_t st, int nchan, double model_scale, double *dev_M, double *dev_j);
+int fb_enqueue_result(fb_ctx *ctx, cudaStream_t st, int nchunks, double *dev_H0);
 int fb_build_j0_table(fb_ctx *ctx, double x_max);
-int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max);
 int fb_build_gram_plan(fb_ctx *ctx);
-uint64_t *fb_radix_sort_items(fb_ctx *ctx, int64_t n, uint64_t *buf0, uint64_t *buf1, int nbits, int *status);
-int fb_items_from_keys(fb_ctx *ctx, int64_t n, const int32_t *dev_keys, uint64_t *items);
+int fb_items_from_keys(fb_ctx *ctx, FbLane &ln, int64_t n, const int32_t *dev_keys, uint64_t *items);
+uint64_t *fb_radix_sort_items(fb_ctx *ctx, FbLane &ln, int64_t n, uint64_t *buf0, uint64_t *buf1, int nbits, int *status);
+int fb_comm_allreduce_map(fb_ctx *ctx, cudaStream_t st, int nchan, double *dev_M, double *dev_j, double *dev_H0);

@@ -34,7 +34,9 @@ namespace {
 struct GramArgs {
     const double *a, *sw, *swV, *kz;
     const double2 *arange;    // per tile: (min a, max a)
-    long long n_tiles;
+    const int *seg;           // channel segments of the lane (fb_sort.cu): start[] | pad[]
+    int chan;                 // channel this launch accumulates
+    const int *status;        // status bits of the call: a flagged call skips the work
     const double *jk;
     const double2 *tab;
     int tab_rows;
@@ -378,12 +380,16 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (*p.status) return;
+    // this channel's run of tiles in the lane's sorted arrays (device-resident: no host planning per call)
+    const int *pad = p.seg + FB_MAX_CHAN + 1;
+    const long long tile0 = pad[p.chan] / FB_TV, n_tiles = (pad[p.chan + 1] - pad[p.chan]) / FB_TV;
     const int k_end = p.cta_off[blockIdx.x + 1];
     for (int k = p.cta_off[blockIdx.x]; k < k_end; ++k) {
         const int type = p.items[3 * k], chunk = p.items[3 * k + 1], slot_out = p.items[3 * k + 2];
         const int Ct = p.type_tab[2 * type];
         const FbGramType ty = p.types[type];
-        const long long q0 = (p.n_tiles * chunk) / Ct, q1 = (p.n_tiles * (chunk + 1)) / Ct;
+        const long long q0 = tile0 + (n_tiles * chunk) / Ct, q1 = tile0 + (n_tiles * (chunk + 1)) / Ct;
         if (q0 >= q1) continue;
         ItemCtx it;
         it.sbase = sbase;
@@ -447,20 +453,22 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
     }
 }
 
-// Sum the chunk partials in a fixed order, scale, mirror.  One 64-thread block per upper tile pair.
+// Sum the partial blocks of one Gram launch in a fixed order into the unscaled Gram S of the call.  One 64-thread block
+// per upper tile pair (blockIdx.x) and channel (blockIdx.y); S[chan][pair][i * 8 + jx].  first != 0: S = sum, else S += sum
+// (the chunks of the host entry point's pipeline arrive in stream order, so the result is deterministic).
 __global__ void __launch_bounds__(64)
-k_gram_finalize(int N, int NT, int P, int nparts, long long n_tiles0, long long n_tiles1, const int *__restrict__ tile_panel,
-                const int *__restrict__ panel_t0, const int *__restrict__ panel_nt, const int *__restrict__ pair_code,
-                const FbGramType *__restrict__ types, const int *__restrict__ type_tab0, const int *__restrict__ type_tab1,
-                int slot0_1, const double *__restrict__ partial, const double *__restrict__ ck, double scale,
-                double *__restrict__ M, double *__restrict__ jvec)
+k_gram_accumulate(int NT, int P, int npairs, int n_items, const int *__restrict__ seg, const int *__restrict__ tile_panel,
+                  const int *__restrict__ panel_t0, const int *__restrict__ panel_nt, const int *__restrict__ pair_code,
+                  const FbGramType *__restrict__ types, const int *__restrict__ type_tab, const double *__restrict__ partial,
+                  double *__restrict__ S, int first, const int *__restrict__ status)
 {
+    if (*status) return;
     // decode the upper-triangular tile pair (tr <= tc) from blockIdx.x
     int rem = blockIdx.x, tr = 0;
     while (rem >= NT - tr) { rem -= NT - tr; tr++; }
     const int tc = tr + rem;
+    const int chan = blockIdx.y;
     const int i = threadIdx.x >> 3, jx = threadIdx.x & 7;
-    const int row = tr * 8 + i, col = tc * 8 + jx;
     if (tr == tc && i > jx) return;
     const int pa = tile_panel[tr], pb = tile_panel[tc];
     const int e_direct = (i * 4 + (jx >> 1)) * 2 + (jx & 1);        // C-fragment slot of element (i, jx)
@@ -481,22 +489,40 @@ k_gram_finalize(int N, int NT, int P, int nparts, long long n_tiles0, long long 
         else   // stored as the transposed tile (row tile lc, offset n - d)
             idx = (lc * D + (n - d)) * 64 + e_transp;
     }
+    const int *pad = seg + FB_MAX_CHAN + 1;
+    const long long n_tiles = (pad[chan + 1] - pad[chan]) / FB_TV;
+    const double *part = partial + (size_t)chan * n_items * FB_PSZ;
     double s = 0.0;
-    for (int part = 0; part < nparts; part++) {               // fixed order: part 0's chunks, then part 1's
-        const int *type_tab = part == 0 ? type_tab0 : type_tab1;
-        const long long n_tiles = part == 0 ? n_tiles0 : n_tiles1;
-        const int Ct = type_tab[2 * type], first = type_tab[2 * type + 1] + (part == 0 ? 0 : slot0_1);
-        for (int c = 0; c < Ct; c++) {
-            const long long q0 = (n_tiles * c) / Ct, q1 = (n_tiles * (c + 1)) / Ct;
-            if (q1 > q0) s += partial[(size_t)(first + c) * FB_PSZ + idx];
-        }
+    const int Ct = type_tab[2 * type], first_slot = type_tab[2 * type + 1];
+    for (int c = 0; c < Ct; c++) {
+        const long long q0 = (n_tiles * c) / Ct, q1 = (n_tiles * (c + 1)) / Ct;
+        if (q1 > q0) s += part[(size_t)(first_slot + c) * FB_PSZ + idx];
     }
+    double *out = S + ((size_t)chan * npairs + blockIdx.x) * 64 + threadIdx.x;
+    *out = first ? s : *out + s;
+}
+
+// M = diag(c) S[:N, :N] diag(c) (mirrored), j = diag(c) S[:N, N].  Grid as k_gram_accumulate.
+__global__ void __launch_bounds__(64)
+k_gram_scale(int N, int NT, int npairs, const double *__restrict__ S, const double *__restrict__ ck, double scale,
+             double *__restrict__ M, double *__restrict__ jvec, const int *__restrict__ status)
+{
+    if (*status) return;
+    int rem = blockIdx.x, tr = 0;
+    while (rem >= NT - tr) { rem -= NT - tr; tr++; }
+    const int tc = tr + rem;
+    const int chan = blockIdx.y;
+    const int i = threadIdx.x >> 3, jx = threadIdx.x & 7;
+    const int row = tr * 8 + i, col = tc * 8 + jx;
+    if (tr == tc && i > jx) return;
+    const double s = S[((size_t)chan * npairs + blockIdx.x) * 64 + threadIdx.x];
+    double *Mc = M + (size_t)chan * N * N;
     if (col < N) {           // row <= col < N
         const double val = ((ck[row] * scale) * (ck[col] * scale)) * s;
-        M[(size_t)row * N + col] = val;
-        M[(size_t)col * N + row] = val;
+        Mc[(size_t)row * N + col] = val;
+        Mc[(size_t)col * N + row] = val;
     } else if (col == N && row < N) {
-        jvec[row] = (ck[row] * scale) * s;
+        jvec[(size_t)chan * N + row] = (ck[row] * scale) * s;
     }
 }
 
@@ -557,7 +583,7 @@ int fb_build_j0_table(fb_ctx *ctx, double x_max)
 {
     std::vector<double> tab;
     fb_j0_build(x_max, tab);
-    FB_CUDA(cudaStreamSynchronize(ctx->stream));          // a kernel of an earlier part may still read the old table
+    FB_CUDA(cudaDeviceSynchronize());                     // a kernel of an earlier call may still read the old table
     if (ctx->d_tab) FB_CUDA(cudaFree(ctx->d_tab));
     ctx->d_tab = nullptr;
     FB_CUDA(cudaMalloc(&ctx->d_tab, tab.size() * sizeof(double)));
@@ -639,6 +665,8 @@ GramPlan make_plan(int NT, int P)
 
 }  // namespace
 
+static int build_work_table(fb_ctx *ctx);
+
 // Choose the panel decomposition of the NT x NT tile grid (cheapest of a few panel counts) and upload it.
 int fb_build_gram_plan(fb_ctx *ctx)
 {
@@ -677,18 +705,17 @@ int fb_build_gram_plan(fb_ctx *ctx)
     FB_CUDA(cudaMemcpy(ctx->d_panel_t0, best.panel_t0.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
     FB_CUDA(cudaMemcpy(ctx->d_panel_nt, best.panel_nt.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
     FB_CUDA(cudaMemcpy(ctx->d_pair_code, best.pair_code.data(), sizeof(int) * P * P * 3, cudaMemcpyHostToDevice));
-
-    return 0;
+    return build_work_table(ctx);
 }
 
-// Plan and launch k_gram over the currently sorted visibilities as part `part` of `nparts` (1 or 2) of a mapping call.
-int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_model)
+// Work items = (type, chunk of the visibilities).  Chunks per type proportional to the type's cost; the items are dealt
+// to the CTAs longest-first (deterministic).  The table depends on the block decomposition and the grid only (the
+// kernel derives a chunk's tile range from the channel's tile count, which it reads from device memory), so it is built
+// once per fb_dht_setup and stays on the device.
+static int build_work_table(fb_ctx *ctx)
 {
-    const long long n_tiles = (n + FB_TV - 1) / FB_TV;
     const int ntypes = ctx->ntypes;
     const int grid = ctx->num_sms;
-    // Work items = (type, chunk of the visibilities).  Chunks per type proportional to the type's cost; the items
-    // are then dealt to the CTAs longest-first (deterministic).
     std::vector<double> cost(ntypes);
     double total = 0.0;
     for (int t = 0; t < ntypes; t++) { cost[t] = block_cost(ctx->h_types[t]); total += cost[t]; }
@@ -711,7 +738,6 @@ int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_mo
             return x.first != y.first ? x.first > y.first : x.second < y.second;
         });
         for (int i = 0; sum < target && i < ntypes; i++, sum++) C[rem[i].second]++;
-        for (int t = 0; t < ntypes; t++) C[t] = (int)std::max<long long>(1, std::min<long long>(C[t], std::max<long long>(1, n_tiles)));
     }
     std::vector<int> type_tab(2 * ntypes);
     int n_items = 0;
@@ -720,10 +746,7 @@ int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_mo
     std::vector<Item> order;
     order.reserve(n_items);
     for (int t = 0; t < ntypes; t++)
-        for (int c = 0; c < C[t]; c++) {
-            const long long q0 = (n_tiles * c) / C[t], q1 = (n_tiles * (c + 1)) / C[t];
-            order.push_back({cost[t] * (double)(q1 - q0), t, c});
-        }
+        for (int c = 0; c < C[t]; c++) order.push_back({cost[t] / (double)C[t], t, c});
     std::stable_sort(order.begin(), order.end(), [](const Item &x, const Item &y) { return x.cost > y.cost; });
     std::vector<std::vector<int>> per_cta(grid);
     {
@@ -753,65 +776,46 @@ int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_mo
         work[grid] = pos;
         std::copy(type_tab.begin(), type_tab.end(), work.begin() + grid + 1 + 3 * (size_t)n_items);
     }
-    int *&d_work = part == 0 ? ctx->d_work : ctx->d_work2;
-    int &work_cap = part == 0 ? ctx->work_cap : ctx->work2_cap;
-    if ((int)work.size() > work_cap) {
-        if (d_work) FB_CUDA(cudaFree(d_work));
-        d_work = nullptr;
-        FB_CUDA(cudaMalloc(&d_work, sizeof(int) * (work.size() + 1024)));
-        work_cap = (int)work.size() + 1024;
-    }
-    // (this synchronisation also orders the table rewrite after the previous part's kernel)
-    FB_CUDA(cudaMemcpyAsync(d_work, work.data(), sizeof(int) * work.size(), cudaMemcpyHostToDevice, ctx->stream));
-    FB_CUDA(cudaStreamSynchronize(ctx->stream));     // `work` is a stack object
-    // partial slots: part 1 follows part 0; room for every part is reserved by part 0 (no reallocation under a
-    // running kernel: the item count does not depend on the part's size unless it is tiny)
-    if (part == 0) {
-        const size_t need = (size_t)n_items * nparts * FB_PSZ + (nparts > 1 ? (size_t)ctx->num_sms * FB_PSZ : 0);
-        if (need > ctx->partial_cap) {
-            if (ctx->d_partial) FB_CUDA(cudaFree(ctx->d_partial));
-            ctx->d_partial = nullptr;
-            FB_CUDA(cudaMalloc(&ctx->d_partial, need * sizeof(double)));
-            ctx->partial_cap = need;
-        }
-        ctx->part_slot0[0] = 0;
-        ctx->part_slot0[1] = n_items;
-    } else if ((size_t)(ctx->part_slot0[1] + n_items) * FB_PSZ > ctx->partial_cap) {
-        FB_FAIL(-18, "fb_map_visibilities: partial buffer too small for the second part");
-    }
-    ctx->part_tiles[part] = n_tiles;
-    ctx->part_typetab[part] = d_work + grid + 1 + 3 * (size_t)n_items;
-    FB_CUDA(cudaEventRecord(part == 0 ? ctx->ev[1] : ctx->pev[1], ctx->stream));
+    if (ctx->d_work) FB_CUDA(cudaFree(ctx->d_work));
+    ctx->d_work = nullptr;
+    FB_CUDA(cudaMalloc(&ctx->d_work, sizeof(int) * work.size()));
+    FB_CUDA(cudaMemcpy(ctx->d_work, work.data(), sizeof(int) * work.size(), cudaMemcpyHostToDevice));
+    ctx->n_items = n_items;
+    return 0;
+}
 
+// Enqueue k_gram for channel `chan` of the lane's sorted visibilities; partial blocks go to the lane's set `chan`.
+int fb_enqueue_gram(fb_ctx *ctx, FbLane &ln, int chan, int vis_model)
+{
+    const int grid = ctx->num_sms;
+    const int n_items = ctx->n_items;
     GramArgs args;
-    args.a = ctx->d_a; args.sw = ctx->d_sw; args.swV = ctx->d_swV; args.kz = ctx->d_kz; args.arange = (const double2 *)ctx->d_amid;
-    args.n_tiles = n_tiles;
+    args.a = ln.d_a; args.sw = ln.d_sw; args.swV = ln.d_swV; args.kz = ln.d_kz; args.arange = (const double2 *)ln.d_amid;
+    args.seg = ln.d_seg; args.chan = chan; args.status = ctx->d_status;
     args.jk = ctx->d_jk; args.tab = ctx->d_tab; args.tab_rows = ctx->tab_rows;
     args.N = ctx->N;
     args.types = ctx->d_types;
-    args.cta_off = d_work; args.items = d_work + grid + 1; args.type_tab = d_work + grid + 1 + 3 * (size_t)n_items;
-    args.H2 = ctx->d_H2; args.partial = ctx->d_partial + (size_t)ctx->part_slot0[part] * FB_PSZ;
-    {
-        args.prof = nullptr;
-        if (getenv("FB_GRAM_PROF")) {
-            FB_CUDA(cudaMalloc(&args.prof, sizeof(long long) * 2 * grid));
-            FB_CUDA(cudaMemsetAsync(args.prof, 0, sizeof(long long) * 2 * grid, ctx->stream));
-        }
+    args.cta_off = ctx->d_work; args.items = ctx->d_work + grid + 1; args.type_tab = ctx->d_work + grid + 1 + 3 * (size_t)n_items;
+    args.H2 = ctx->d_H2; args.partial = ln.d_partial + (size_t)chan * n_items * FB_PSZ;
+    args.prof = nullptr;
+    static const bool prof = getenv("FB_GRAM_PROF") != nullptr;
+    if (prof) {
+        FB_CUDA(cudaMalloc(&args.prof, sizeof(long long) * 2 * grid));
+        FB_CUDA(cudaMemsetAsync(args.prof, 0, sizeof(long long) * 2 * grid, ln.stream));
     }
-    if (n_tiles > 0) {
-        if (vis_model == FB_MODEL_DEBRIS) {
-            FB_CUDA(cudaFuncSetAttribute(k_gram<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-            k_gram<true><<<grid, FB_GRAM_THREADS, GRAM_SMEM_BYTES, ctx->stream>>>(args);
-        } else {
-            FB_CUDA(cudaFuncSetAttribute(k_gram<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES));
-            k_gram<false><<<grid, FB_GRAM_THREADS, GRAM_SMEM_BYTES, ctx->stream>>>(args);
-        }
-        FB_CUDA(cudaGetLastError());
+    if (vis_model == FB_MODEL_DEBRIS) {
+        static bool attr = false;
+        if (!attr) { FB_CUDA(cudaFuncSetAttribute(k_gram<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES)); attr = true; }
+        k_gram<true><<<grid, FB_GRAM_THREADS, GRAM_SMEM_BYTES, ln.stream>>>(args);
+    } else {
+        static bool attr = false;
+        if (!attr) { FB_CUDA(cudaFuncSetAttribute(k_gram<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_BYTES)); attr = true; }
+        k_gram<false><<<grid, FB_GRAM_THREADS, GRAM_SMEM_BYTES, ln.stream>>>(args);
     }
-    FB_CUDA(cudaEventRecord(part == 0 ? ctx->ev[2] : ctx->pev[2], ctx->stream));
+    FB_CUDA(cudaGetLastError());
     if (args.prof) {
         std::vector<long long> h(2 * grid);
-        FB_CUDA(cudaStreamSynchronize(ctx->stream));
+        FB_CUDA(cudaStreamSynchronize(ln.stream));
         FB_CUDA(cudaMemcpy(h.data(), args.prof, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
         long long j0_sum = 0, mma_sum = 0, j0_max = 0, mma_max = 0, tot_max = 0, tot_min = -1;
         for (int b = 0; b < grid; b++) {
@@ -820,21 +824,32 @@ int fb_launch_gram_part(fb_ctx *ctx, int part, int nparts, int64_t n, int vis_mo
             tot_max = std::max(tot_max, h[2 * b] + h[2 * b + 1]);
             tot_min = tot_min < 0 ? h[2 * b] + h[2 * b + 1] : std::min(tot_min, h[2 * b] + h[2 * b + 1]);
         }
-        fprintf(stderr, "[fb_gram prof] tiles=%lld  per-CTA clocks: J0 avg %.0f max %lld | DMMA avg %.0f max %lld | total min %lld max %lld\n",
-                n_tiles, (double)j0_sum / grid, j0_max, (double)mma_sum / grid, mma_max, tot_min, tot_max);
+        fprintf(stderr, "[fb_gram prof] chan=%d  per-CTA clocks: J0 avg %.0f max %lld | DMMA avg %.0f max %lld | total min %lld max %lld\n",
+                chan, (double)j0_sum / grid, j0_max, (double)mma_sum / grid, mma_max, tot_min, tot_max);
         cudaFree(args.prof);
     }
     return 0;
 }
 
-// Sum the partial blocks of all parts in a fixed order -> M, j.
-int fb_launch_gram_finalize(fb_ctx *ctx, int nparts, double model_scale, double *dev_M, double *dev_j)
+// Fold the lane's partial blocks (all channels) into the call's unscaled Gram S.
+int fb_enqueue_accumulate(fb_ctx *ctx, FbLane &ln, int nchan, int first)
 {
     const int npairs = ctx->NT * (ctx->NT + 1) / 2;
-    k_gram_finalize<<<npairs, 64, 0, ctx->stream>>>(ctx->N, ctx->NT, ctx->P, nparts, ctx->part_tiles[0], ctx->part_tiles[1],
-                                                    ctx->d_tile_panel, ctx->d_panel_t0, ctx->d_panel_nt, ctx->d_pair_code,
-                                                    ctx->d_types, ctx->part_typetab[0], ctx->part_typetab[nparts > 1 ? 1 : 0],
-                                                    ctx->part_slot0[1], ctx->d_partial, ctx->d_ck, model_scale, dev_M, dev_j);
+    const int grid = ctx->num_sms;
+    k_gram_accumulate<<<dim3(npairs, nchan), 64, 0, ln.stream>>>(ctx->NT, ctx->P, npairs, ctx->n_items, ln.d_seg, ctx->d_tile_panel,
+                                                              ctx->d_panel_t0, ctx->d_panel_nt, ctx->d_pair_code, ctx->d_types,
+                                                              ctx->d_work + grid + 1 + 3 * (size_t)ctx->n_items, ln.d_partial,
+                                                              ctx->d_S, first, ctx->d_status);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// S -> M, j (scaled, mirrored) for every channel.
+int fb_enqueue_scale(fb_ctx *ctx, cudaStream_t st, int nchan, double model_scale, double *dev_M, double *dev_j)
+{
+    const int npairs = ctx->NT * (ctx->NT + 1) / 2;
+    k_gram_scale<<<dim3(npairs, nchan), 64, 0, st>>>(ctx->N, ctx->NT, npairs, ctx->d_S, ctx->d_ck, model_scale, dev_M, dev_j,
+                                                   ctx->d_status);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

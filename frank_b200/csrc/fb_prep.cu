@@ -162,8 +162,12 @@ k_apply_correction(int64_t n, const double *__restrict__ u, const double *__rest
     }
 }
 
-// single block: fixed-order reduction of the per-block partials; out = {0.5*sum, qmin, qmax}
-__global__ void __launch_bounds__(1024) k_prep_reduce(int nblocks, const double *__restrict__ red, double *__restrict__ out)
+// single block: fixed-order reduction of the per-block partials of one chunk; out = {0.5 * sum, qmin, qmax, 0}.
+// Also raises the call's status bits on the device, so that no host read is needed in the middle of a call
+// (statistical_models.py:526: data beyond the last collocation point; J0 table shorter than a_max * j_{N-1}).
+__global__ void __launch_bounds__(1024)
+k_prep_reduce(int nblocks, const double *__restrict__ red, double *__restrict__ out, int check_qbounds, double q_last,
+              double x_per_q, double x_table, int *__restrict__ status)
 {
     __shared__ double scratch[32];
     double h0 = 0.0, qmin = INFINITY, qmax = -INFINITY;
@@ -178,44 +182,68 @@ __global__ void __launch_bounds__(1024) k_prep_reduce(int nblocks, const double 
     double r0 = block_reduce(h0, scratch, OpAdd(), 0.0);
     double r1 = block_reduce(qmin, scratch, OpMin(), INFINITY);
     double r2 = block_reduce(qmax, scratch, OpMax(), -INFINITY);
-    if (threadIdx.x == 0) { out[0] = 0.5 * r0; out[1] = r1; out[2] = r2; }
+    if (threadIdx.x == 0) {
+        out[0] = 0.5 * r0; out[1] = r1; out[2] = r2; out[3] = 0.0;
+        int st = 0;
+        if (check_qbounds && q_last < r2) st |= FB_ST_QRANGE;
+        else if (r2 * x_per_q > x_table) st |= FB_ST_TABLE;
+        if (st) atomicOr(status, st);
+    }
+}
+
+// End of a call: combine the chunks' reductions in chunk order -> result = {H0, min q, max q, status}.
+__global__ void k_map_result(int nchunks, const double *__restrict__ chunkred, const int *__restrict__ status,
+                             double *__restrict__ result, double *__restrict__ dev_H0)
+{
+    double h0 = 0.0, qmin = INFINITY, qmax = -INFINITY;
+    for (int c = 0; c < nchunks; c++) {
+        h0 += chunkred[4 * c];
+        qmin = fmin(qmin, chunkred[4 * c + 1]);
+        qmax = fmax(qmax, chunkred[4 * c + 2]);
+    }
+    result[0] = h0; result[1] = qmin; result[2] = qmax; result[3] = (double)*status;
+    if (dev_H0 && !(*status)) dev_H0[0] = h0;
 }
 
 }  // namespace
 
-// Grow the per-visibility workspaces (sorted SoA arrays, records, sort items, permutation, tile ranges) to hold
-// n_pad visibilities.  Callers that run a mapping call in parts reserve the largest part up front, so that no
-// buffer is reallocated while an earlier part's kernels are in flight.
-int fb_reserve_prep(fb_ctx *ctx, int64_t n_pad)
+// Grow the per-visibility workspaces of a lane (sorted SoA arrays, records, sort items, permutation, tile ranges) to
+// hold n visibilities of nchan channels (every channel's segment is padded to a whole tile).  Never called while the
+// lane has work in flight that uses the old buffers: the entry points reserve for the largest chunk up front.
+int fb_reserve_lane(fb_ctx *ctx, FbLane &ln, int64_t n, int nchan)
 {
-    if (n_pad > ctx->cap) {
-        int64_t cap = n_pad + n_pad / 8 + 4096;
-        for (double **p : {&ctx->d_a, &ctx->d_sw, &ctx->d_swV, &ctx->d_kz}) {
+    const int64_t n_pad = (n + FB_TV - 1) / FB_TV * FB_TV + (int64_t)FB_TV * nchan;
+    if (n_pad > ln.cap) {
+        FB_CUDA(cudaStreamSynchronize(ln.stream));
+        const int64_t cap = n_pad + n_pad / 8 + 4096;
+        for (double **p : {&ln.d_a, &ln.d_sw, &ln.d_swV, &ln.d_kz}) {
             if (*p) FB_CUDA(cudaFree(*p));
             *p = nullptr;
             FB_CUDA(cudaMalloc(p, sizeof(double) * cap));
         }
-        if (ctx->d_rec) FB_CUDA(cudaFree(ctx->d_rec));
-        if (ctx->d_items) FB_CUDA(cudaFree(ctx->d_items));
-        if (ctx->d_perm) FB_CUDA(cudaFree(ctx->d_perm));
-        if (ctx->d_amid) FB_CUDA(cudaFree(ctx->d_amid));
-        ctx->d_rec = nullptr; ctx->d_items = nullptr; ctx->d_perm = nullptr; ctx->d_amid = nullptr;
-        FB_CUDA(cudaMalloc(&ctx->d_amid, sizeof(double) * 2 * (cap / FB_TV + 1)));
-        FB_CUDA(cudaMalloc(&ctx->d_rec, sizeof(double) * 4 * cap));
-        FB_CUDA(cudaMalloc(&ctx->d_items, sizeof(uint64_t) * 2 * cap));
-        FB_CUDA(cudaMalloc(&ctx->d_perm, sizeof(uint32_t) * cap));
-        ctx->cap = cap;
+        if (ln.d_rec) FB_CUDA(cudaFree(ln.d_rec));
+        if (ln.d_items) FB_CUDA(cudaFree(ln.d_items));
+        if (ln.d_perm) FB_CUDA(cudaFree(ln.d_perm));
+        if (ln.d_amid) FB_CUDA(cudaFree(ln.d_amid));
+        ln.d_rec = nullptr; ln.d_items = nullptr; ln.d_perm = nullptr; ln.d_amid = nullptr;
+        FB_CUDA(cudaMalloc(&ln.d_amid, sizeof(double) * 2 * (cap / FB_TV + 1)));
+        FB_CUDA(cudaMalloc(&ln.d_rec, sizeof(double) * 4 * cap));
+        FB_CUDA(cudaMalloc(&ln.d_items, sizeof(uint64_t) * 2 * cap));
+        FB_CUDA(cudaMalloc(&ln.d_perm, sizeof(uint32_t) * cap));
+        ln.cap = cap;
     }
     const int per_block = PREP_THREADS * PREP_ITEMS;
-    const int nblocks = (int)std::max<int64_t>(1, (n_pad + per_block - 1) / per_block);
-    if (nblocks > ctx->red_cap) {
-        if (ctx->d_red) FB_CUDA(cudaFree(ctx->d_red));
-        ctx->d_red = nullptr;
+    const int nblocks = (int)std::max<int64_t>(1, (n + per_block - 1) / per_block);
+    if (nblocks > ln.red_cap) {
+        FB_CUDA(cudaStreamSynchronize(ln.stream));
+        if (ln.d_red) FB_CUDA(cudaFree(ln.d_red));
+        ln.d_red = nullptr;
         const int cap = nblocks + nblocks / 4 + 16;
-        FB_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * (3 * (size_t)cap + 8)));
-        ctx->red_cap = cap;
+        FB_CUDA(cudaMalloc(&ln.d_red, sizeof(double) * (3 * (size_t)cap + 8)));
+        ln.red_cap = cap;
     }
-    return fb_reserve_sort(ctx, n_pad);
+    if (!ln.d_seg) FB_CUDA(cudaMalloc(&ln.d_seg, sizeof(int) * 2 * (FB_MAX_CHAN + 1)));
+    return fb_reserve_sort(ctx, ln, n);
 }
 
 extern "C" int fb_apply_correction_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v, const double *dev_V_reim,
@@ -234,31 +262,30 @@ extern "C" int fb_apply_correction_dev(fb_ctx *ctx, int64_t n, const double *dev
     return 0;
 }
 
-int fb_launch_prep(fb_ctx *ctx, int64_t n, const double *u, const double *v, const double *V, const double *w,
-                   int w_stride, const fb_geometry *g, double *dev_H0, double *host_qminmax, double *host_H0)
+// Enqueue the geometry pre-pass of one chunk on the lane's stream: records, block partials, the chunk's reduction
+// (H0 sum, min / max q) into ctx->d_chunkred[chunk] and the call's status bits.  Nothing is read back here.
+int fb_enqueue_prep(fb_ctx *ctx, FbLane &ln, int chunk, int64_t n, const double *u, const double *v, const double *V,
+                    const double *w, int w_stride, const int32_t *chan, const FbMapJob &job)
 {
-    const int64_t n_pad = ((n + FB_TV - 1) / FB_TV) * FB_TV;
-    {
-        int rc = fb_reserve_prep(ctx, n_pad);
-        if (rc) return rc;
-    }
+    (void)chan;
     const int per_block = PREP_THREADS * PREP_ITEMS;
-    int nblocks = (int)((n_pad + per_block - 1) / per_block);
+    int nblocks = (int)((n + per_block - 1) / per_block);
     if (nblocks < 1) nblocks = 1;
-    k_prep<<<nblocks, PREP_THREADS, 0, ctx->stream>>>(n, u, v, (const double2 *)V, w, w_stride, *g, ctx->invQmax,
-                                                      (double4 *)ctx->d_rec, ctx->d_red);
+    k_prep<<<nblocks, PREP_THREADS, 0, ln.stream>>>(n, u, v, (const double2 *)V, w, w_stride, job.geom, ctx->invQmax,
+                                                    (double4 *)ln.d_rec, ln.d_red);
     FB_CUDA(cudaGetLastError());
-    double *fin = ctx->d_red + 3 * (size_t)ctx->red_cap;   // 3 doubles after the block partials
-    k_prep_reduce<<<1, 1024, 0, ctx->stream>>>(nblocks, ctx->d_red, fin);
+    // largest J0 argument the table serves: rows reach (tab_rows - 3) / 16 (fb_j0_rows_for)
+    const double x_table = (double)(ctx->tab_rows - 3) * FB_J0_H;
+    k_prep_reduce<<<1, 1024, 0, ln.stream>>>(nblocks, ln.d_red, ctx->d_chunkred + 4 * chunk, job.check_qbounds, job.q_last,
+                                             ctx->invQmax * ctx->h_jk[ctx->N - 1], x_table, ctx->d_status);
     FB_CUDA(cudaGetLastError());
-    double h[3];
-    FB_CUDA(cudaMemcpyAsync(h, fin, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    if (dev_H0) FB_CUDA(cudaMemcpyAsync(dev_H0, fin, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    FB_CUDA(cudaStreamSynchronize(ctx->stream));
-    host_qminmax[0] = h[1];
-    host_qminmax[1] = h[2];
-    if (host_H0) *host_H0 = h[0];
     ctx->last_n = n;
-    // order the visibilities by baseline bin (stable) and lay them out for the Gram kernel
-    return fb_launch_sort(ctx, n, n_pad, n > 0 ? h[2] * ctx->invQmax : 0.0);
+    return 0;
+}
+
+int fb_enqueue_result(fb_ctx *ctx, cudaStream_t st, int nchunks, double *dev_H0)
+{
+    k_map_result<<<1, 1, 0, st>>>(nchunks, ctx->d_chunkred, ctx->d_status, ctx->d_result, dev_H0);
+    FB_CUDA(cudaGetLastError());
+    return 0;
 }

@@ -1016,6 +1016,143 @@ __global__ void k_negate(int N, const double *__restrict__ in, double *__restric
     if (i < N) out[i] = -in[i];
 }
 
+
+// ---- device-resident Newton iteration of the log-normal model (K7) ----------------------------------------------------
+// Objective / gradient at the trial point xt = x + lam * pdir (lam = 0: at x itself), rows over N / 8 CTAs, one warp per
+// row (the one-CTA k_ln_eval pulls M and S^-1 -- 2 x 2 MB at N = 500 -- through a single SM).  Same per-row arithmetic
+// and summation order as k_ln_eval.  Every CTA forms the whole trial vector in shared memory; CTA 0 also stores it.
+__global__ void __launch_bounds__(256)
+k_ln_eval_rows(int N, const double *__restrict__ M, const double *__restrict__ Sinv, const double *__restrict__ jvec,
+               const double *__restrict__ x, const double *__restrict__ pdir, double lam, double s0,
+               double *__restrict__ xt_out, double *__restrict__ I_out, double *__restrict__ r_out, double *__restrict__ g_out,
+               double *__restrict__ fpart, double *__restrict__ gxpart)
+{
+    extern __shared__ double sh[];
+    double *sv = sh, *Iv = sh + N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N; i += blockDim.x) {
+        const double xi = x[i];
+        const double si = pdir ? xi + lam * pdir[i] : xi;             // x_new = x0 + lam * p   (minimizer.py:136)
+        sv[i] = si;
+        const double Ii = exp(si + s0);
+        Iv[i] = Ii;
+        if (blockIdx.x == 0) { xt_out[i] = si; I_out[i] = Ii; }
+    }
+    __syncthreads();
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= N) return;
+    double mi = 0.0, ss = 0.0;
+    const double *Mr = M + (size_t)r * N, *Sr = Sinv + (size_t)r * N;
+    for (int c = lane; c < N; c += 32) {
+        mi = fma(Mr[c], Iv[c], mi);
+        ss = fma(Sr[c], sv[c], ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mi += __shfl_down_sync(0xffffffffu, mi, o);
+        ss += __shfl_down_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+        const double res = mi - jvec[r];                 // (M I - j)_r
+        const double gr = ss + Iv[r] * res;
+        r_out[r] = Iv[r] * res;                          // diagonal term of the Hessian: I o (M I - j)
+        g_out[r] = gr;
+        fpart[r] = 0.5 * sv[r] * ss + 0.5 * Iv[r] * mi - Iv[r] * jvec[r];
+        gxpart[r] = fabs(gr) * fabs(sv[r]);              // convergence test max(|g| |x|)   (minimizer.py:281)
+    }
+}
+
+// scal[0] = f(xt), scal[1] = max_i |g_i| |xt_i|, scal[2] = 1 when xt == x element-wise (minimizer.py:139).  One warp,
+// fixed order.  `scal` may be mapped pinned host memory: the host reads it after synchronising the stream.
+__global__ void __launch_bounds__(32)
+k_ln_eval_reduce(int N, const double *__restrict__ fpart, const double *__restrict__ gxpart, const double *__restrict__ x,
+                 const double *__restrict__ xt, double *__restrict__ scal)
+{
+    const int lane = threadIdx.x;
+    double acc = 0.0, gx = 0.0;
+    int same = 1;
+    for (int i = lane; i < N; i += 32) {
+        acc += fpart[i];
+        gx = fmax(gx, gxpart[i]);
+        if (isnan(gxpart[i])) gx = NAN;
+        same &= (xt[i] == x[i]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_down_sync(0xffffffffu, acc, o);
+        const double og = __shfl_down_sync(0xffffffffu, gx, o);
+        gx = (isnan(og) || isnan(gx)) ? NAN : fmax(gx, og);
+        same &= __shfl_down_sync(0xffffffffu, same, o);
+    }
+    if (lane == 0) { scal[0] = acc; scal[1] = gx; scal[2] = (double)same; }
+}
+
+// Search direction of one line search (minimizer.py:119-127 with LogNormalMAPModel's limit_step, statistical_models.py:
+// 1136-1140): d = sign * dir;  raw = g . d;  alpha = min(1.1 min_i |x_i / d_i|, 1);  p = alpha d;  slope = g . p.
+// scal[4] = raw, scal[5] = slope, scal[6] = alpha, scal[7] = potrf info of the factor that produced the direction.
+__global__ void __launch_bounds__(1024)
+k_ln_step_prep(int N, const double *__restrict__ x, const double *__restrict__ g, const double *__restrict__ dir, double sign,
+               double *__restrict__ p, const int *__restrict__ info, double *__restrict__ scal)
+{
+    __shared__ double red[3][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double raw = 0.0, amin = INFINITY;
+    for (int i = tid; i < N; i += blockDim.x) {
+        const double d = sign * dir[i];
+        raw = fma(g[i], d, raw);
+        amin = fmin(amin, fabs(x[i] / d));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        raw += __shfl_down_sync(0xffffffffu, raw, o);
+        amin = fmin(amin, __shfl_down_sync(0xffffffffu, amin, o));
+    }
+    if (lane == 0) { red[0][warp] = raw; red[1][warp] = amin; }
+    __syncthreads();
+    if (warp == 0) {
+        raw = red[0][lane]; amin = red[1][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            raw += __shfl_down_sync(0xffffffffu, raw, o);
+            amin = fmin(amin, __shfl_down_sync(0xffffffffu, amin, o));
+        }
+        if (lane == 0) { red[0][0] = raw; red[1][0] = fmin(1.1 * amin, 1.0); }
+    }
+    __syncthreads();
+    const double alpha = red[1][0];
+    double slope = 0.0;
+    for (int i = tid; i < N; i += blockDim.x) {
+        const double pi = alpha * (sign * dir[i]);
+        p[i] = pi;
+        slope = fma(g[i], pi, slope);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) slope += __shfl_down_sync(0xffffffffu, slope, o);
+    if (lane == 0) red[2][warp] = slope;
+    __syncthreads();
+    if (warp == 0) {
+        slope = red[2][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) slope += __shfl_down_sync(0xffffffffu, slope, o);
+        if (lane == 0) { scal[4] = red[0][0]; scal[5] = slope; scal[6] = alpha; scal[7] = info ? (double)info[0] : 0.0; }
+    }
+}
+
+// after a power-spectrum update: scal[8] = 'some entry moved by more than tol', scal[9] = bad value in p
+// (statistical_models.py:1053), scal[10] = potrf info of the posterior factor
+__global__ void __launch_bounds__(256)
+k_ln_ps_flags(int N, const double *__restrict__ p, const int *__restrict__ notconv, const int *__restrict__ info,
+              double *__restrict__ scal)
+{
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        if (!(p[i] > 0.0)) atomicOr(&bad, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { scal[8] = notconv ? (double)notconv[0] : 0.0; scal[9] = (double)bad; scal[10] = info ? (double)info[0] : 0.0; }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1760,3 +1897,290 @@ int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, dou
 }
 
 }  // extern "C"
+
+// ---- K7: the whole log-normal fit in one call --------------------------------------------------------------------------
+// MinimizeNewton / LineSearch (frank/minimizer.py:74-283) and the outer power-spectrum iteration of FrankFitter._fit
+// (frank/radial_fitters.py:756-785) with every vector resident on the device.  The host thread only takes the scalar
+// decisions (Armijo test, back-tracking step, re-factorise or not, converged or not) from a handful of doubles that the
+// kernels write to mapped pinned memory: no vector crosses the bus between the first upload and the final download.
+namespace {
+
+struct LnWork {
+    fb_ctx *ctx;
+    int N;
+    double *x, *xt, *g, *gt, *I, *It, *r, *rt, *dxn, *p, *ng, *fpart, *gxpart;
+    volatile double *scal;        // pinned, mapped
+    double *d_scal;               // its device address
+    int *d_info;
+    long nfev = 0, nhess = 0, nsteps = 0;
+    int status_count[4] = {0, 0, 0, 0};
+};
+
+// f, max|g||x|, same-point flag at x + lam * pdir (pdir = null: at x); results land in the trial buffers
+int ln_eval(LnWork &w, const double *pdir, double lam, double *f, double *gx, bool *same)
+{
+    fb_ctx *ctx = w.ctx;
+    const int N = w.N;
+    k_ln_eval_rows<<<(N + 7) / 8, 256, sizeof(double) * 2 * N, ctx->stream>>>(N, ctx->sv_M, ctx->ln_S, ctx->sv_j, w.x, pdir, lam, ctx->ln_s0,
+                                                                            w.xt, w.It, w.rt, w.gt, w.fpart, w.gxpart);
+    k_ln_eval_reduce<<<1, 32, 0, ctx->stream>>>(N, w.fpart, w.gxpart, w.x, w.xt, w.d_scal);
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *f = w.scal[0];
+    if (gx) *gx = w.scal[1];
+    if (same) *same = w.scal[2] != 0.0;
+    w.nfev++;
+    return 0;
+}
+
+void ln_accept(LnWork &w)
+{
+    std::swap(w.x, w.xt); std::swap(w.g, w.gt); std::swap(w.I, w.It); std::swap(w.r, w.rt);
+}
+
+// LineSearch.__call__ (minimizer.py:104-184, root = False) along `dir` * sign from x; on success the trial buffers are
+// accepted.  *failed as the reference's flag; *reduction = the accepted step length.  Returns FB_E_SLOPE for the
+// reference's ValueError("Round off in slope calculation").
+int ln_line_search(LnWork &w, const double *dir, double sign, const int *d_info, double *fx, double *gx, bool *failed,
+                   double *reduction, bool need_raw, double *raw_out, int *info_out)
+{
+    fb_ctx *ctx = w.ctx;
+    const int N = w.N;
+    k_ln_step_prep<<<1, 1024, 0, ctx->stream>>>(N, w.x, w.g, dir, sign, w.p, d_info, w.d_scal);
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double raw = w.scal[4], slope = w.scal[5];
+    if (raw_out) *raw_out = raw;
+    if (info_out) *info_out = (int)w.scal[7];
+    if (need_raw && (!(raw < 0.0) || (int)w.scal[7] != 0)) { *failed = true; return 0; }     // minimizer.py:244: not a descent direction
+    if (slope > 0.0) FB_FAIL(FB_E_SLOPE, "Round off in slope calculation");                   // minimizer.py:130-133
+    const double armijo = 1e-4, l_min = 0.1;
+    const double cost = *fx;
+    double lam = 1.0, lam_prev = 0.0, cost_prev = 0.0;
+    for (;;) {
+        double cost_new, gxn;
+        bool same;
+        int rc = ln_eval(w, w.p, lam, &cost_new, &gxn, &same);
+        if (rc) return rc;
+        if (same) { w.nfev--; *failed = true; return 0; }                                    // minimizer.py:139 (no evaluation counted)
+        if (cost_new <= cost + armijo * lam * slope) {                                       // :146
+            *reduction = lam;
+            *fx = cost_new;
+            *gx = gxn;
+            ln_accept(w);
+            *failed = false;
+            return 0;
+        }
+        double lam_new;
+        if (lam == 1.0) {
+            lam_new = -0.5 * slope / (cost_new - cost - slope);                              // quadratic model, :151-154
+        } else {                                                                             // cubic model, :156-173
+            const double r1 = (cost_new - cost - lam * slope) / (lam * lam);
+            const double r2 = (cost_prev - cost - lam_prev * slope) / (lam_prev * lam_prev);
+            const double a = (r1 - r2) / (lam - lam_prev);
+            const double b = (lam * r2 - lam_prev * r1) / (lam - lam_prev);
+            if (a == 0.0) {
+                lam_new = -0.5 * slope / b;
+            } else {
+                const double disc = b * b - 3.0 * a * slope;
+                if (disc < 0.0) lam_new = 0.5 * lam;
+                else if (b <= 0.0) lam_new = (-b + sqrt(disc)) / (3.0 * a);
+                else lam_new = -1.0 * slope / (b + sqrt(disc));
+                lam_new = std::min(0.5 * lam, lam_new);
+            }
+        }
+        if (std::isnan(lam_new)) lam_new = l_min * lam;                                      // :175-177
+        lam_prev = lam; cost_prev = cost_new;
+        lam = std::max(lam_new, l_min * lam);                                                // :181
+    }
+}
+
+// MinimizeNewton (minimizer.py:228-283) from the point in w.x; tol as LogNormalMAPModel passes it (1e-7).
+// status: 0 success, 1 failed to improve, 2 too many iterations, 3 too many Hessian evaluations.
+int ln_newton(LnWork &w, double tol, int *status)
+{
+    fb_ctx *ctx = w.ctx;
+    const int N = w.N;
+    const int max_step = 100000, max_hev = 1000;
+    bool need_hess = true;
+    long nhess = 0;
+    double fx, gx;
+    int rc = ln_eval(w, nullptr, 0.0, &fx, &gx, nullptr);         // fx = fun(x); also g, I, r at x
+    if (rc) return rc;
+    ln_accept(w);                                                 // the evaluation point IS x
+    for (int nstep = 0; nstep < max_step; nstep++) {
+        w.nsteps++;
+        if (need_hess) {
+            if (nhess == max_hev) { *status = 3; return 0; }
+            FB_CUDA(cudaMemsetAsync(w.d_info, 0, sizeof(int), ctx->stream));
+            k_ln_hess<<<dim3((N + 31) / 32, (N + 7) / 8), 256, 0, ctx->stream>>>(N, ctx->sv_M, ctx->ln_S, w.I, w.r, ctx->ln_full_hess, ctx->sv_D);
+            rc = launch_factor(ctx, 1, nullptr, w.d_info);
+            if (rc) return rc;
+            nhess++; w.nhess++;
+        }
+        // dx = -Hess^-1 g   (the factor is re-used while full steps are accepted, minimizer.py:236-242, 276)
+        k_negate<<<(N + 255) / 256, 256, 0, ctx->stream>>>(N, w.g, w.ng);
+        rc = launch_solve_rhs(ctx, 1, nullptr, ctx->stream, w.ng, 0, w.dxn, 0);
+        if (rc) return rc;
+        bool failed = true;
+        double reduction = 0.0;
+        rc = ln_line_search(w, w.dxn, 1.0, w.d_info, &fx, &gx, &failed, &reduction, true, nullptr, nullptr);
+        if (rc) return rc;
+        if (failed) {                                                                        // gradient descent instead, :250-253
+            bool failed_descent = true;
+            rc = ln_line_search(w, w.g, -1.0, nullptr, &fx, &gx, &failed_descent, &reduction, false, nullptr, nullptr);
+            if (rc) return rc;
+            if (failed_descent) {                                                            // shrinking steps, :255-274
+                // w.p holds reduce_step(-g, x) from the failed search; dx * 2^-4k is exact in binary
+                double lam = 1.0, fn = 0.0, gxn = 0.0;
+                bool found = false;
+                for (int k = 0; k < 10; k++) {
+                    rc = ln_eval(w, w.p, lam, &fn, &gxn, nullptr);
+                    if (rc) return rc;
+                    if (fn < fx) { found = true; break; }
+                    lam *= 0.0625;
+                }
+                if (!found) { *status = 1; return 0; }
+                fx = fn; gx = gxn;
+                ln_accept(w);
+            }
+        }
+        need_hess = failed || (reduction != 1.0);                                            // :276
+        if (gx < tol * std::max(std::fabs(fx), 1.0)) { *status = 0; return 0; }              // :281
+    }
+    *status = 2;
+    return 0;
+}
+
+int ln_workspace(fb_ctx *ctx, LnWork &w)
+{
+    const size_t N = ctx->N;
+    int rc = ensure_solver_ws(ctx, 1);
+    if (rc) return rc;
+    rc = ln_ensure(ctx);
+    if (rc) return rc;
+    if (!ctx->ln_pin) {
+        FB_CUDA(cudaHostAlloc(&ctx->ln_pin, sizeof(double) * 16, cudaHostAllocMapped));
+        for (int i = 0; i < 16; i++) ctx->ln_pin[i] = 0.0;
+    }
+    if (ctx->ln_ws_N != (int)N) {
+        if (ctx->ln_ws) FB_CUDA(cudaFree(ctx->ln_ws));
+        ctx->ln_ws = nullptr;
+        FB_CUDA(cudaMalloc(&ctx->ln_ws, sizeof(double) * (13 * N + 16)));
+        ctx->ln_ws_N = (int)N;
+    }
+    double *b = ctx->ln_ws;
+    w.ctx = ctx; w.N = (int)N;
+    w.x = b; w.xt = b + N; w.g = b + 2 * N; w.gt = b + 3 * N; w.I = b + 4 * N; w.It = b + 5 * N; w.r = b + 6 * N; w.rt = b + 7 * N;
+    w.dxn = b + 8 * N; w.p = b + 9 * N; w.ng = b + 10 * N; w.fpart = b + 11 * N; w.gxpart = b + 12 * N;
+    w.scal = ctx->ln_pin;
+    FB_CUDA(cudaHostGetDevicePointer((void **)&w.d_scal, ctx->ln_pin, 0));
+    w.d_info = ctx->sv_flags;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int fb_frank_lognormal_loop(fb_ctx *ctx, const double *host_M, const double *host_j, const double *host_p_init,
+                                       const double *host_guess, double s0, double full_hessian, double alpha, double p0,
+                                       const double *host_Tinv, double tol, int max_iter, double newton_tol, double *host_s,
+                                       double *host_p, double *host_chol, int *host_niter, int *host_converged, int *host_info,
+                                       long long *host_stats, double *host_hist_p, double *host_hist_s, int hist_cap)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0 || !ctx->d_Y) FB_FAIL(-30, "fb_frank_lognormal_loop: fb_dht_setup (with Ycoef) has not been called");
+    if (!host_M || !host_j || !host_p_init || !host_guess || !host_s || !host_p || (max_iter >= 0 && !host_Tinv))
+        FB_FAIL(-31, "fb_frank_lognormal_loop: bad arguments");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    const int nb = ((int)N + NB - 1) / NB;
+    for (size_t i = 0; i < N; i++)
+        if (!(host_p_init[i] > 0.0)) FB_FAIL(FB_E_BADP, "bad value in power spectrum");            // statistical_models.py:1053
+    LnWork w;
+    int rc = ln_workspace(ctx, w);
+    if (rc) return rc;
+    rc = allow_build_smem(ctx);
+    if (rc) return rc;
+    ctx->ln_s0 = s0;
+    ctx->ln_full_hess = full_hessian;
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_M, host_M, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_j, host_j, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(ctx->sv_p, host_p_init, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(w.x, host_guess, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    if (max_iter >= 0) {
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_Tinv, host_Tinv, sizeof(double) * N * N, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_alpha, &alpha, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_p0, &p0, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));            // alpha / p0 are stack variables
+    int *d_count = ctx->sv_flags + 1;
+    FB_CUDA(cudaMemsetAsync(ctx->sv_flags, 0, sizeof(int) * 8, ctx->stream));
+
+    int count = 0, converged = 0, status = 0, info = 0;
+    const bool trace = getenv("FB_SOLVER_TRACE") != nullptr;
+    if (trace) FB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // one LogNormalMAPModel: S^-1 of the current spectrum, Newton from the current point, factor of the Hessian at the MAP
+    auto fit_current = [&]() -> int {
+        launch_build_dinv(ctx, (int)N, nb, 1, nullptr, ctx->d_Y, ctx->sv_p, nullptr, ctx->ln_S);       // :1064-1065
+        int st = 0;
+        int r = ln_newton(w, newton_tol, &st);
+        if (r) return r;
+        w.status_count[st]++;
+        // Hessian at the MAP point and its upper factor (:1148-1150); I, r of the accepted point are current
+        FB_CUDA(cudaMemsetAsync(w.d_info, 0, sizeof(int), ctx->stream));
+        k_ln_hess<<<dim3(((int)N + 31) / 32, ((int)N + 7) / 8), 256, 0, ctx->stream>>>((int)N, ctx->sv_M, ctx->ln_S, w.I, w.r, ctx->ln_full_hess, ctx->sv_D);
+        return launch_factor(ctx, 1, nullptr, w.d_info);
+    };
+    rc = fit_current();
+    if (rc) return rc;
+    while (max_iter >= 0) {
+        // CriticalFilter.update_power_spectrum with the factor of the current fit (filter.py:154-177); fit.MAP = s
+        FB_CUDA(cudaMemcpyAsync(ctx->sv_mu, w.x, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
+        rc = launch_tr2(ctx, 1, nullptr);
+        if (rc) return rc;
+        k_ps_rhs<<<dim3(((int)N + 7) / 8, 1), 256, sizeof(double) * N, ctx->stream>>>((int)N, ctx->d_Y, ctx->sv_mu, ctx->sv_tr2, ctx->sv_alpha,
+                                                                                   ctx->sv_p0, ctx->sv_p, nullptr, ctx->sv_rhs, ctx->sv_notconv);
+        k_ps_tau<<<dim3(((int)N + 7) / 8, 1), 256, sizeof(double) * N, ctx->stream>>>((int)N, ctx->sv_rhs, ctx->sv_Tinv, tol, ctx->sv_p, nullptr,
+                                                                                   d_count, ctx->sv_notconv, nullptr, 0);
+        k_ln_ps_flags<<<1, 256, 0, ctx->stream>>>((int)N, ctx->sv_p, ctx->sv_notconv, w.d_info, w.d_scal);
+        FB_CUDA(cudaGetLastError());
+        FB_CUDA(cudaStreamSynchronize(ctx->stream));
+        info = (int)w.scal[10];
+        if (info) break;                                       // the factor that fed this update was not positive definite
+        const bool moved = w.scal[8] != 0.0, bad = w.scal[9] != 0.0;
+        if (host_hist_p && count < hist_cap)
+            FB_CUDA(cudaMemcpyAsync(host_hist_p + (size_t)count * N, ctx->sv_p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        if (bad) { status = FB_E_BADP; break; }               // the reference raises from LogNormalMAPModel.__init__
+        rc = fit_current();                                    // fit = _perform_fit(pI, guess=fit.MAP)
+        if (rc) return rc;
+        if (host_hist_s && count < hist_cap)
+            FB_CUDA(cudaMemcpyAsync(host_hist_s + (size_t)count * N, w.x, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        count++;
+        converged = moved ? 0 : 1;
+        if (converged || count > max_iter) break;              // while not converged and count <= max_iter
+    }
+    FB_CUDA(cudaMemcpyAsync(host_s, w.x, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaMemcpyAsync(host_p, ctx->sv_p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_chol) FB_CUDA(cudaMemcpyAsync(host_chol, ctx->sv_D, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream));
+    int last_info = 0;
+    FB_CUDA(cudaMemcpyAsync(&last_info, w.d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (trace) {
+        float ms = 0;
+        FB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        FB_CUDA(cudaEventSynchronize(ctx->ev[1]));
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        fprintf(stderr, "[fb_solve trace] lognormal: %d outer iterations, %ld Newton steps, %ld evaluations, %ld Hessians, %.3f ms\n",
+                count, w.nsteps, w.nfev, w.nhess, ms);
+    }
+    if (host_niter) *host_niter = count;
+    if (host_converged) *host_converged = converged;
+    if (host_info) *host_info = info ? info : last_info;
+    if (host_stats) {
+        host_stats[0] = w.nsteps; host_stats[1] = w.nfev; host_stats[2] = w.nhess;
+        for (int k = 0; k < 4; k++) host_stats[3 + k] = w.status_count[k];
+    }
+    if (status) { ctx->err = "bad value in power spectrum"; return status; }
+    if (info || last_info) FB_FAIL(FB_E_NOTPD, "Hessian at the MAP point is not positive definite");
+    return 0;
+}

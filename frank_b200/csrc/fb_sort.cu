@@ -13,6 +13,8 @@
 // block with __match_any_sync in a fixed element order.
 #include "fb_common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int SORT_THREADS = 256;
@@ -26,15 +28,25 @@ __device__ __forceinline__ int64_t elem_index(int64_t base, int warp, int round,
     return base + (int64_t)warp * (32 * SORT_ROUNDS) + round * 32 + lane;
 }
 
-// key = floor(a * key_scale) clipped to [0, kmax], payload = index
+// key = (channel << nbits) | floor(a * key_scale) clipped to [0, kmax], payload = index.  The scale follows the chunk's
+// largest baseline, read from the chunk's device-resident reduction (red[2] = max q): no host round trip.
 __global__ void __launch_bounds__(256)
-k_items_from_rec(int64_t n, const double4 *__restrict__ rec, double key_scale, int kmax, uint64_t *__restrict__ items)
+k_items_from_rec(int64_t n, const double4 *__restrict__ rec, const double *__restrict__ red, double invQmax, int kmax,
+                 int nbits, const int32_t *__restrict__ chan, int nchan, uint64_t *__restrict__ items)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
+        const double a_max = red[2] * invQmax;
+        const double key_scale = a_max > 0 ? ((double)kmax + 0.5) / a_max : 0.0;
         int k = __double2int_rz(rec[i].x * key_scale);
         k = k < 0 ? 0 : (k > kmax ? kmax : k);
-        items[i] = ((uint64_t)k << 32) | (uint64_t)(uint32_t)i;
+        uint32_t key = (uint32_t)k;
+        if (chan) {
+            int c = chan[i];
+            c = c < 0 ? 0 : (c >= nchan ? nchan - 1 : c);
+            key |= (uint32_t)c << nbits;
+        }
+        items[i] = ((uint64_t)key << 32) | (uint64_t)(uint32_t)i;
     }
 }
 
@@ -215,26 +227,67 @@ k_sort_scatter(int64_t n, const uint64_t *__restrict__ items, int shift, const u
     }
 }
 
-// permute the records into the structure-of-arrays layout the Gram kernel reads; zero padding to n_pad.
-// A block covers 4 tiles of FB_TV = 64 sorted visibilities: it also records each tile's range (min a, max a), from
+// Channel segments of the sorted items (multi-frequency calls: the channel is the high part of the key, so every
+// channel is one contiguous run): start[c] = first sorted position of a channel >= c, c = 0 .. nchan.
+__global__ void __launch_bounds__(256)
+k_chan_starts(int64_t n, const uint64_t *__restrict__ sorted, int nbits, int nchan, int *__restrict__ start)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+        const int c = (int)(sorted[p] >> (32 + nbits));
+        const int prev = p > 0 ? (int)(sorted[p - 1] >> (32 + nbits)) : -1;
+        for (int b = prev + 1; b <= c; b++) start[b] = (int)p;
+        if (p == n - 1)
+            for (int b = c + 1; b <= nchan; b++) start[b] = (int)n;
+    }
+}
+
+// seg = start[0 .. nchan] | pad[0 .. nchan]: every channel's run is laid out from a tile boundary, pad[c] = sum over the
+// channels before c of their counts rounded up to whole tiles.  The Gram kernel reads its tile range from here.
+__global__ void k_seg_finish(int64_t n, int nchan, int *__restrict__ seg)
+{
+    int *start = seg, *pad = seg + FB_MAX_CHAN + 1;
+    if (nchan == 1) { start[0] = 0; start[1] = (int)n; }
+    if (n == 0) for (int c = 0; c <= nchan; c++) start[c] = 0;
+    int acc = 0;
+    for (int c = 0; c < nchan; c++) {
+        pad[c] = acc;
+        acc += (start[c + 1] - start[c] + FB_TV - 1) / FB_TV * FB_TV;
+    }
+    pad[nchan] = acc;
+}
+
+// permute the records into the structure-of-arrays layout the Gram kernel reads; zero padding at the end of every
+// channel's run.  A block covers 4 tiles of FB_TV = 64 slots: it also records each tile's range (min a, max a), from
 // which the Gram kernel picks one J0 table row per (mode, tile).
 __global__ void __launch_bounds__(256)
-k_sort_gather(int64_t n, int64_t n_pad, const uint64_t *__restrict__ items, const double4 *__restrict__ rec,
-              double *__restrict__ a, double *__restrict__ sw, double *__restrict__ swV, double *__restrict__ kz,
-              uint32_t *__restrict__ perm, double *__restrict__ amid)
+k_sort_gather(int64_t n_slots, int nchan, const int *__restrict__ seg, const uint64_t *__restrict__ items,
+              const double4 *__restrict__ rec, double *__restrict__ a, double *__restrict__ sw, double *__restrict__ swV,
+              double *__restrict__ kz, uint32_t *__restrict__ perm, double *__restrict__ amid)
 {
     static_assert(FB_TV == 64, "two warps per tile");
     __shared__ double s_lo[8], s_hi[8];
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_seg[2 * (FB_MAX_CHAN + 1)];
+    for (int k = threadIdx.x; k < 2 * (FB_MAX_CHAN + 1); k += blockDim.x) s_seg[k] = seg[k];
+    __syncthreads();
+    const int *start = s_seg, *pad = s_seg + FB_MAX_CHAN + 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = pad[nchan];
     double lo = INFINITY, hi = -INFINITY;
-    if (i < n) {
-        const uint32_t src = (uint32_t)(items[i] & 0xffffffffull);
-        const double4 r = rec[src];
-        a[i] = r.x; sw[i] = r.y; swV[i] = r.z; kz[i] = r.w;
-        perm[i] = src;
-        lo = hi = r.x;
-    } else if (i < n_pad) {
-        a[i] = 0.0; sw[i] = 0.0; swV[i] = 0.0; kz[i] = 0.0;
+    if (i < total) {
+        int c = 0;
+        while (c + 1 < nchan && i >= pad[c + 1]) c++;
+        const int64_t p = (int64_t)start[c] + (i - pad[c]);
+        if (p < start[c + 1]) {
+            const uint32_t src = (uint32_t)(items[p] & 0xffffffffull);
+            const double4 r = rec[src];
+            a[i] = r.x; sw[i] = r.y; swV[i] = r.z; kz[i] = r.w;
+            perm[i] = src;
+            lo = hi = r.x;
+        } else {
+            a[i] = 0.0; sw[i] = 0.0; swV[i] = 0.0; kz[i] = 0.0;
+            perm[i] = 0xffffffffu;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -246,7 +299,7 @@ k_sort_gather(int64_t n, int64_t n_pad, const uint64_t *__restrict__ items, cons
     __syncthreads();
     if (threadIdx.x < 4) {
         const int64_t tile = (int64_t)blockIdx.x * 4 + threadIdx.x;
-        if (tile * FB_TV < n_pad) {
+        if (tile * FB_TV < total && tile * FB_TV < n_slots) {
             const double l = fmin(s_lo[2 * threadIdx.x], s_lo[2 * threadIdx.x + 1]);
             const double h = fmax(s_hi[2 * threadIdx.x], s_hi[2 * threadIdx.x + 1]);
             amid[2 * tile] = h >= l ? l : 0.0;
@@ -258,62 +311,75 @@ k_sort_gather(int64_t n, int64_t n_pad, const uint64_t *__restrict__ items, cons
 }  // namespace
 
 // Digit-histogram workspace for sorting n items.
-int fb_reserve_sort(fb_ctx *ctx, int64_t n)
+int fb_reserve_sort(fb_ctx *ctx, FbLane &ln, int64_t n)
 {
     const size_t hist_need = (size_t)256 * ((n + SORT_CHUNK - 1) / SORT_CHUNK);
-    if (hist_need + 256 > ctx->hist_cap) {                     // + 256 digit totals behind the table
-        if (ctx->d_hist) cudaFree(ctx->d_hist);
-        ctx->d_hist = nullptr;
+    if (hist_need + 256 > ln.hist_cap) {                     // + 256 digit totals behind the table
+        cudaStreamSynchronize(ln.stream);
+        if (ln.d_hist) cudaFree(ln.d_hist);
+        ln.d_hist = nullptr;
         const size_t cap = hist_need + hist_need / 4 + 4096;
-        if (cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * cap) != cudaSuccess) FB_FAIL(-50, "radix sort: out of memory");
-        ctx->hist_cap = cap;
+        if (cudaMalloc(&ln.d_hist, sizeof(uint32_t) * cap) != cudaSuccess) FB_FAIL(-50, "radix sort: out of memory");
+        ln.hist_cap = cap;
     }
     return 0;
 }
 
 // Stable LSD radix sort of n items (key << 32 | index) on `nbits` key bits, 8 bits per pass, ping-ponging between
-// buf0 (input) and buf1.  Returns the buffer holding the sorted items.
-uint64_t *fb_radix_sort_items(fb_ctx *ctx, int64_t n, uint64_t *buf0, uint64_t *buf1, int nbits, int *status)
+// buf0 (input) and buf1, on the lane's stream.  Returns the buffer holding the sorted items.
+uint64_t *fb_radix_sort_items(fb_ctx *ctx, FbLane &ln, int64_t n, uint64_t *buf0, uint64_t *buf1, int nbits, int *status)
 {
     *status = 0;
     const int nblocks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
     const size_t hist_need = (size_t)256 * nblocks;
-    if (fb_reserve_sort(ctx, n)) { *status = -50; return nullptr; }
+    if (fb_reserve_sort(ctx, ln, n)) { *status = -50; return nullptr; }
     uint64_t *src = buf0, *dst = buf1;
     for (int shift = 32; shift < 32 + nbits; shift += 8) {
-        uint32_t *digit_total = ctx->d_hist + hist_need;            // 256 counters behind the (digit, block) table
-        if (cudaMemsetAsync(digit_total, 0, sizeof(uint32_t) * 256, ctx->stream) != cudaSuccess) { *status = -51; ctx->err = "radix sort: memset failed"; return nullptr; }
-        k_sort_hist<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, src, shift, ctx->d_hist, nblocks, digit_total);
-        k_sort_scan<<<256, 1024, 0, ctx->stream>>>(ctx->d_hist, nblocks, digit_total);
-        k_sort_scatter<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(n, src, shift, ctx->d_hist, nblocks, dst);
+        uint32_t *digit_total = ln.d_hist + hist_need;            // 256 counters behind the (digit, block) table
+        if (cudaMemsetAsync(digit_total, 0, sizeof(uint32_t) * 256, ln.stream) != cudaSuccess) { *status = -51; ctx->err = "radix sort: memset failed"; return nullptr; }
+        k_sort_hist<<<nblocks, SORT_THREADS, 0, ln.stream>>>(n, src, shift, ln.d_hist, nblocks, digit_total);
+        k_sort_scan<<<256, 1024, 0, ln.stream>>>(ln.d_hist, nblocks, digit_total);
+        k_sort_scatter<<<nblocks, SORT_THREADS, 0, ln.stream>>>(n, src, shift, ln.d_hist, nblocks, dst);
         uint64_t *t = src; src = dst; dst = t;
     }
     if (cudaGetLastError() != cudaSuccess) { *status = -51; ctx->err = "radix sort: launch failed"; return nullptr; }
     return src;
 }
 
-int fb_items_from_keys(fb_ctx *ctx, int64_t n, const int32_t *dev_keys, uint64_t *items)
+int fb_items_from_keys(fb_ctx *ctx, FbLane &ln, int64_t n, const int32_t *dev_keys, uint64_t *items)
 {
-    k_items_from_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, dev_keys, items);
+    k_items_from_keys<<<(unsigned)((n + 255) / 256), 256, 0, ln.stream>>>(n, dev_keys, items);
     FB_CUDA(cudaGetLastError());
     return 0;
 }
 
-// Sort ctx->d_rec[0..n) by baseline bin and write ctx->d_a/d_sw/d_swV/d_kz (padded to n_pad) and ctx->d_perm.
-int fb_launch_sort(fb_ctx *ctx, int64_t n, int64_t n_pad, double a_max)
+// Sort the lane's records [0, n) by (channel, baseline bin) and write the padded SoA arrays, the permutation, the
+// per-tile ranges and the channel segments.  Enqueue only.
+int fb_enqueue_sort(fb_ctx *ctx, FbLane &ln, int chunk, int64_t n, const int32_t *chan, int nchan)
 {
-    if (n <= 0) return 0;
     const int nbits = ctx->sort_bits;
     const int kmax = (1 << nbits) - 1;
-    const double key_scale = a_max > 0 ? ((double)kmax + 0.5) / a_max : 0.0;
-    const double4 *rec = (const double4 *)ctx->d_rec;
-    uint64_t *buf0 = ctx->d_items, *buf1 = ctx->d_items + ctx->cap;
-    k_items_from_rec<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, rec, key_scale, kmax, buf0);
-    int st = 0;
-    uint64_t *sorted = fb_radix_sort_items(ctx, n, buf0, buf1, nbits, &st);
-    if (st) return st;
-    k_sort_gather<<<(unsigned)((n_pad + 255) / 256), 256, 0, ctx->stream>>>(n, n_pad, sorted, rec, ctx->d_a, ctx->d_sw, ctx->d_swV,
-                                                                         ctx->d_kz, ctx->d_perm, ctx->d_amid);
+    int chanbits = 0;
+    while ((1 << chanbits) < nchan) chanbits++;
+    const double4 *rec = (const double4 *)ln.d_rec;
+    uint64_t *buf0 = ln.d_items, *buf1 = ln.d_items + ln.cap;
+    const uint64_t *sorted = buf0;
+    if (n > 0) {
+        k_items_from_rec<<<(unsigned)((n + 255) / 256), 256, 0, ln.stream>>>(n, rec, ctx->d_chunkred + 4 * chunk, ctx->invQmax, kmax,
+                                                                            nbits, nchan > 1 ? chan : nullptr, nchan, buf0);
+        int st = 0;
+        sorted = fb_radix_sort_items(ctx, ln, n, buf0, buf1, nbits + chanbits, &st);
+        if (st) return st;
+        if (nchan > 1) {
+            const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 16);
+            k_chan_starts<<<grid, 256, 0, ln.stream>>>(n, sorted, nbits, nchan, ln.d_seg);
+        }
+    }
+    k_seg_finish<<<1, 1, 0, ln.stream>>>(n, nchan, ln.d_seg);
+    const int64_t n_slots = (n + FB_TV - 1) / FB_TV * FB_TV + (int64_t)FB_TV * (nchan - 1);
+    if (n_slots > 0)
+        k_sort_gather<<<(unsigned)((n_slots + 255) / 256), 256, 0, ln.stream>>>(n_slots, nchan, ln.d_seg, sorted, rec, ln.d_a, ln.d_sw,
+                                                                              ln.d_swV, ln.d_kz, ln.d_perm, ln.d_amid);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

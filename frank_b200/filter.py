@@ -104,7 +104,21 @@ class CriticalFilter(object):
         self._Tinv = banded_inverse(self._ldl)
 
     def update_power_spectrum(self, fit, device=None):
-        """One fixed-point update of the power spectrum for the current fit (frank/filter.py:154-177)."""
+        """One fixed-point update of the power spectrum for the current fit (frank/filter.py:154-177).
+
+        Dispatches on the fit, as the reference's `fit.MAP` / `fit.Dsolve` interface does: a log-normal fit updates with
+        its own Hessian factor, a Gaussian fit with a Cholesky factor runs one step of the device loop, and a Gaussian
+        fit that went through the SVD pseudo-inverse branch (statistical_models.py:747-755) takes the reference's
+        generic formula on its `Dsolve`."""
+        if hasattr(fit, '_update_power_spectrum'):                       # LogNormalMAPModel
+            return fit._update_power_spectrum(self._alpha, self._p_0, self._Tinv)
+        if getattr(fit, '_Dsvd', None) is not None:
+            Ykm = self._DHT.coefficients()
+            Tr1 = np.dot(Ykm, fit.MAP) ** 2
+            Tr2 = np.einsum('ij,ji->i', Ykm, fit.Dsolve(Ykm.T))
+            pi = fit.power_spectrum
+            beta = (self._p_0 + 0.5 * (Tr1 + Tr2)) / pi - (self._alpha - 1.0 + 0.5 * self._rho)
+            return np.exp(np.dot(self._Tinv, beta + np.log(pi)))
         ctx = _lib.get_context(device)
         ctx.dht_setup(self._DHT)
         # one pass of the device loop: max_iter = 0 lets exactly one update through (count <= max_iter)

@@ -239,8 +239,10 @@ class FrankFitter(FourierBesselFitter):
         out = ctx.frank_normal_loop(self._M, self._j, pI, self._filter._alpha, self._filter._p_0, self._filter._Tinv,
                                     self._tol, self._max_iter, want_chol=True, hist_cap=hist_cap)
         if out['status'] == _lib.FB_E_NOTPD:
-            raise np.linalg.LinAlgError("posterior precision matrix lost positive definiteness during the "
-                                        "power-spectrum iteration")
+            # a Cholesky pivot failed inside the device loop.  The reference's GaussianModel would have switched to its SVD
+            # pseudo-inverse for that solve and carried on (statistical_models.py:747-755): redo the iteration sequenced
+            # from the host, one GaussianModel (device Cholesky, device SVD on failure) per step
+            return self._fit_sequenced(pI)
         count = int(out['niter'][0])
         pI = out['p'][0]
         fit = GaussianModel(self._DHT, self._M, self._j, pI, noise_likelihood=self._H0, device=self._device,
@@ -256,25 +258,96 @@ class FrankFitter(FourierBesselFitter):
         self._ps_cov = None
         return self._sol
 
+    def _fit_sequenced(self, pI):
+        """The Normal iteration of frank/radial_fitters.py:765-785 sequenced from the host: only used when a factorisation
+        failed inside the device-resident loop, so that the SVD fallback of individual solves is honoured."""
+        fit = self._perform_fit(pI, fit_method='Normal')
+        count, pi_old = 0, 0
+        while (not self._filter.check_convergence(pI, pi_old)) and count <= self._max_iter:
+            pi_old = pI.copy()
+            pI = self._filter.update_power_spectrum(fit, device=self._device)
+            fit = self._perform_fit(pI, guess=fit.MAP, fit_method='Normal')
+            if self._store_iteration_diagnostics:
+                self._iteration_diagnostics['power_spectrum'].append(pI)
+                self._iteration_diagnostics['MAP'].append(fit.MAP)
+            count += 1
+        self._report_convergence(count)
+        if self._store_iteration_diagnostics:
+            self._iteration_diagnostics['num_iterations'] = count
+        self._sol = FrankGaussianFit(self._vis_map, fit, self._info, geometry=self._geometry.clone())
+        self._ps = pI
+        self._ps_cov = None
+        return self._sol
+
+    # -- hyper-parameter sweeps (BASELINE config 4) -------------------------------------------------------------------
+    def fit_sweep(self, u, v, V, weights=1, alphas=(1.05,), weights_smooths=(1e-4,), group=None):
+        r"""Fit the same visibilities for every (alpha, w_smooth) pair of a grid.
+
+        The reference's `run_multiple_fits` (frank/fit.py:493-563) loops `perform_fit` over the pairs and re-maps the
+        visibilities every time although M and j do not depend on the hyper-parameters.  Here the data are mapped once
+        and all grid points run as ONE batched device loop (`fb_frank_normal_loop` with B = number of points); with
+        torch.distributed initialised the points are sharded over the ranks and the results all-gathered
+        (frank_b200.distributed.sweep_sharded), so every rank returns the full grid.
+
+        Returns a list of FrankGaussianFit in the reference's loop order (alpha outer, w_smooth inner);
+        `self.sweep_diagnostics` holds alpha, wsmooth, num_iterations and converged per point."""
+        self._geometry.fit(u, v, V, weights)
+        mapping = self.preprocess_visibilities(u, v, V, weights)
+        return self.fit_sweep_preprocessed(mapping, alphas, weights_smooths, group=group)
+
+    def fit_sweep_preprocessed(self, preproc_vis, alphas=(1.05,), weights_smooths=(1e-4,), group=None):
+        if self._method != 'Normal':
+            raise ValueError("fit_sweep batches the Normal method; loop FrankFitter(method='LogNormal') over the grid instead")
+        from frank_b200 import distributed
+        self._build_matrices(preproc_vis)
+        pI = self._starting_spectrum()                        # the warm-up fits do not depend on (alpha, w_smooth)
+        grid = [(float(a), float(w)) for a in np.atleast_1d(alphas) for w in np.atleast_1d(weights_smooths)]
+        ctx = _lib.get_context(self._device)
+        ctx.dht_setup(self._DHT)
+        N = self.size
+
+        def solve_points(idx):
+            filters = [CriticalFilter(self._DHT, grid[i][0], self._filter._p_0, grid[i][1], self._tol) for i in idx]
+            out = ctx.frank_normal_loop(self._M, self._j, np.tile(pI, (len(idx), 1)), [f._alpha for f in filters],
+                                        [f._p_0 for f in filters], np.stack([f._Tinv for f in filters]), self._tol,
+                                        self._max_iter, want_chol=False)
+            if out['status'] == _lib.FB_E_NOTPD:
+                raise np.linalg.LinAlgError("a posterior precision matrix of the sweep lost positive definiteness")
+            return {'p': out['p'], 'mu': out['mu'], 'niter': out['niter'], 'converged': out['converged']}
+
+        res = distributed.sweep_sharded(solve_points, len(grid), N, group=group, ctx=ctx)
+        self.sweep_diagnostics = {'alpha': [g[0] for g in grid], 'wsmooth': [g[1] for g in grid],
+                                  'num_iterations': res['niter'].tolist(), 'converged': res['converged'].tolist()}
+        sols = []
+        for k, (a, w) in enumerate(grid):
+            fit = GaussianModel(self._DHT, self._M, self._j, res['p'][k], noise_likelihood=self._H0, device=self._device,
+                                _solution=(res['mu'][k], None))      # the factor is recomputed on demand (Dsolve, covariance)
+            info = dict(self._info, alpha=a, wsmooth=w)
+            sols.append(FrankGaussianFit(self._vis_map, fit, info, geometry=self._geometry.clone()))
+        return sols
+
     def _fit_lognormal(self):
-        """LogNormal branch of frank/radial_fitters.py:754-785: log-space start, then the same fixed-point loop with
-        LogNormalMAPModel solves (Newton decisions on the host, arithmetic on the device)."""
+        """LogNormal branch of frank/radial_fitters.py:754-785: log-space start, then the fixed-point loop with
+        LogNormalMAPModel solves, device resident (fb_frank_lognormal_loop)."""
         pI = self._starting_spectrum()
         fit = self._perform_fit(pI, fit_method='Normal')
         s = np.log(np.maximum(fit.MAP, 1e-3 * fit.MAP.max()))
         s -= self._s_scale
         pI = np.max(self._DHT.transform(s) ** 2)
         pI = pI * (self.q / self.q[0]) ** -4
-        fit = self._perform_fit(pI, guess=s)
-        count, pi_old = 0, 0
-        while (not self._filter.check_convergence(pI, pi_old)) and count <= self._max_iter:
-            pi_old = pI.copy()
-            pI = fit._update_power_spectrum(self._filter._alpha, self._filter._p_0, self._filter._Tinv)
-            fit = self._perform_fit(pI, guess=fit.MAP)
-            if self._store_iteration_diagnostics:
-                self._iteration_diagnostics['power_spectrum'].append(pI)
-                self._iteration_diagnostics['MAP'].append(fit.MAP)
-            count += 1
+        # first log-normal fit and the whole fixed-point iteration in one device-resident call
+        ctx = _lib.get_context(self._device)
+        ctx.dht_setup(self._DHT)
+        hist_cap = self._max_iter + 2 if self._store_iteration_diagnostics else 0
+        out = ctx.frank_lognormal_loop(self._M, self._j, pI, s, self._s_scale, alpha=self._filter._alpha, p0=self._filter._p_0,
+                                       Tinv=self._filter._Tinv, tol=self._tol, max_iter=self._max_iter, hist_cap=hist_cap)
+        LogNormalMAPModel._raise_for_status(out['status'])
+        count, pI = out['niter'], out['p']
+        fit = LogNormalMAPModel(self._DHT, self._M, self._j, pI, guess=out['s'], s0=self._s_scale, noise_likelihood=self._H0,
+                                device=self._device, _solution=(out['s'], np.triu(out['chol']), out['newton']))
+        if self._store_iteration_diagnostics:
+            self._iteration_diagnostics['power_spectrum'] = [out['hist_p'][i].copy() for i in range(count)]
+            self._iteration_diagnostics['MAP'] = [out['hist_s'][i].copy() for i in range(count)]
         self._report_convergence(count)
         if self._store_iteration_diagnostics:
             self._iteration_diagnostics['num_iterations'] = count

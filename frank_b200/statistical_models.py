@@ -84,43 +84,80 @@ class VisibilityMapping(object):
             return float(np.cos(g.inc * deg_to_rad))                                   # :486-490
         return 1.0
 
-    def _map_one(self, ctx, u, v, V, w, w_stride):
-        """One channel through fb_map_visibilities_{host,dev}: returns M, j, H0, qmin, qmax."""
+    def _map(self, ctx, u, v, V, w, w_stride, chan=None, nchan=1):
+        """All channels through one fb_map_visibilities_{host,dev} call: returns M [nchan, N, N], j [nchan, N], H0,
+        qmin, qmax."""
         import torch
         N = self.size
         n = int(u.shape[0])
         geom = self._geometry.device_scalars()
         q_last = float(self.q[-1])
-        on_device = _is_cuda_tensor(u)
-        if on_device:
-            dev = u.device
-            out = torch.empty(N * N + N + 1, dtype=torch.float64, device=dev)
-            M, j, H0 = out[:N * N], out[N * N:N * N + N], out[N * N + N:]
-            Vr = torch.view_as_real(V) if V.is_complex() else torch.stack([V, torch.zeros_like(V)], dim=-1)
-            Vr = Vr.contiguous()
-            rc, qmin, qmax = ctx.map_visibilities(n, u.contiguous(), v.contiguous(), Vr, w, w_stride, geom,
-                                                  _lib.MODEL_CODE[self._vis_model], self._model_scale(), self._H2,
-                                                  self.check_qbounds, q_last, M, j, H0, host=False)
-            if rc == 0:
-                host = out.cpu().numpy()
+        nM, nj = nchan * N * N, nchan * N
+        if _is_cuda_tensor(u):
+            out = torch.empty(nM + nj + 1, dtype=torch.float64, device=u.device)
+            M, j, H0 = out[:nM], out[nM:nM + nj], out[nM + nj:]
+            # the library runs on its own stream: everything the caller (or the conversions above) enqueued on torch's
+            # current stream must have finished before the kernels read it
+            torch.cuda.current_stream(u.device).synchronize()
+            rc, qmin, qmax = ctx.map_visibilities(n, u, v, V, w, w_stride, geom, _lib.MODEL_CODE[self._vis_model],
+                                                  self._model_scale(), self._H2, self.check_qbounds, q_last, M, j, H0,
+                                                  host=False, chan=chan, nchan=nchan)
+            host = out.cpu().numpy() if rc == 0 else None
         else:
-            host = np.empty(N * N + N + 1)
-            M, j, H0 = host[:N * N], host[N * N:N * N + N], host[N * N + N:]
+            host = np.empty(nM + nj + 1)
+            M, j, H0 = host[:nM], host[nM:nM + nj], host[nM + nj:]
             rc, qmin, qmax = ctx.map_visibilities(n, u, v, V, w, w_stride, geom, _lib.MODEL_CODE[self._vis_model],
                                                   self._model_scale(), self._H2, self.check_qbounds, q_last,
-                                                  M, j, H0, host=True)
+                                                  M, j, H0, host=True, chan=chan, nchan=nchan)
         self._timing = ctx.last_map_timing()
         if rc == _lib.FB_E_QRANGE:
             self._raise_qrange(qmax)
-        return host[:N * N].reshape(N, N).copy(), host[N * N:N * N + N].copy(), float(host[N * N + N]), qmin, qmax
+        return (host[:nM].reshape(nchan, N, N).copy(), host[nM:nM + nj].reshape(nchan, N).copy(), float(host[nM + nj]),
+                qmin, qmax)
+
+    @staticmethod
+    def _device_inputs(u, v, V, weights):
+        """Validate / convert CUDA-tensor inputs: contiguous float64 u, v, weights and complex128 V on one device.
+        Returns u, v, V as a real [n, 2] view, weights, w_stride."""
+        import torch
+        dev = u.device
+        n = u.numel()
+
+        def f64(t, name):
+            if not (hasattr(t, 'is_cuda') and t.is_cuda and t.device == dev):
+                raise ValueError(f"map_visibilities: {name} must be a CUDA tensor on {dev} like u")
+            if t.numel() != n:
+                raise ValueError(f"map_visibilities: {name} has {t.numel()} elements, u has {n}")
+            return t.reshape(-1).to(torch.float64).contiguous()
+        u, v = f64(u, 'u'), f64(v, 'v')
+        if not (hasattr(V, 'is_cuda') and V.is_cuda and V.device == dev and V.numel() == n):
+            raise ValueError("map_visibilities: V must be a CUDA tensor of the same length and device as u")
+        V = V.reshape(-1)
+        if V.is_complex():
+            Vr = torch.view_as_real(V.to(torch.complex128).contiguous())
+        else:
+            Vr = torch.stack([V.to(torch.float64), torch.zeros_like(V, dtype=torch.float64)], dim=-1).contiguous()
+        w_stride = 1
+        if not hasattr(weights, 'data_ptr'):
+            weights = torch.full((1,), float(weights), dtype=torch.float64, device=dev)
+            w_stride = 0
+        elif weights.numel() == 1:
+            weights = weights.reshape(1).to(device=dev, dtype=torch.float64).contiguous()
+            w_stride = 0
+        else:
+            weights = f64(weights, 'weights')
+        return u, v, Vr, weights, w_stride
 
     def map_visibilities(self, u, v, V, weights, frequencies=None, geometry=None):
         r"""Compute M = H^T w H, j = H^T w V and the null likelihood H0 from the visibilities
         (frank/statistical_models.py:109-237).
 
-        u, v, V, weights may be NumPy arrays (host memory; copied to the GPU inside the call) or
+        u, v, V, weights may be NumPy arrays (host memory, pinned or pageable; streamed to the GPU inside the call) or
         torch CUDA tensors (used in place).  Returns the reference's dict:
         ``mult_freq, channels, M, j, null_likelihood, hash``.
+
+        With `frequencies` the Gram matrices of all channels come out of ONE device call (the channel index is the
+        high part of the kernel's sort key, statistical_models.py:175-214); nothing is split on the host.
 
         As in the reference the deprojection always uses the geometry given at construction;
         a `geometry` argument only lands in the returned hash (statistical_models.py:158-165, 227).
@@ -132,52 +169,44 @@ class VisibilityMapping(object):
         ctx = self._context()
         on_device = _is_cuda_tensor(u)
         if on_device:
-            import torch
-            w_stride = 1
-            if not hasattr(weights, 'data_ptr'):
-                weights = torch.full((1,), float(weights), dtype=torch.float64, device=u.device)
-                w_stride = 0
-            elif weights.numel() == 1:
-                weights = weights.reshape(1).to(torch.float64)
-                w_stride = 0
-            V = V if V.is_complex() else V.to(torch.float64)
+            u, v, V, weights, w_stride = self._device_inputs(u, v, V, weights)
         else:
-            u = np.ascontiguousarray(u, dtype=np.float64)
-            v = np.ascontiguousarray(v, dtype=np.float64)
-            V = np.ascontiguousarray(V, dtype=np.complex128)
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+            V = np.ascontiguousarray(V, dtype=np.complex128).reshape(-1)
+            if v.size != u.size or V.size != u.size:
+                raise ValueError("map_visibilities: u, v and V must have the same length")
             weights = np.asarray(weights, dtype=np.float64)
             w_stride = 1
             if weights.ndim == 0 or weights.size == 1:
                 weights = weights.reshape(1).copy()
                 w_stride = 0
             else:
-                weights = np.ascontiguousarray(weights)
+                weights = np.ascontiguousarray(weights).reshape(-1)
+                if weights.size != u.size:
+                    raise ValueError("map_visibilities: weights must be a scalar or have the length of u")
 
         multi_freq = frequencies is not None
         if not multi_freq:
-            M, j, H0, qmin, qmax = self._map_one(ctx, u, v, V, weights, w_stride)
+            M, j, H0, qmin, qmax = self._map(ctx, u, v, V, weights, w_stride)
             self._warn_qmin(qmin)
-            return {'mult_freq': False, 'channels': None, 'M': M, 'j': j, 'null_likelihood': H0,
+            return {'mult_freq': False, 'channels': None, 'M': M[0], 'j': j[0], 'null_likelihood': H0,
                     'hash': [False, self._DHT, geometry, self._vis_model, self._scale_height]}
 
-        # multi-frequency: one Gram per channel (statistical_models.py:180-214); H0 over all data
+        # multi-frequency: channel index = position in np.unique(frequencies) (statistical_models.py:180-189)
         if on_device:
             import torch
-            channels = torch.unique(frequencies)
-            sel = [frequencies == f for f in channels]
+            channels, chan = torch.unique(frequencies.reshape(-1), return_inverse=True)
+            chan = chan.to(torch.int32).contiguous()
             channels = channels.cpu().numpy()
         else:
-            frequencies = np.asarray(frequencies)
-            channels = np.unique(frequencies)
-            sel = [frequencies == f for f in channels]
-        N = self.size
-        Ms, js, H0 = np.zeros([len(channels), N, N]), np.zeros([len(channels), N]), 0.0
-        qlo, qhi = np.inf, -np.inf
-        for c, idx in enumerate(sel):
-            wc = weights if w_stride == 0 else weights[idx]
-            Ms[c], js[c], h0c, qmin, qmax = self._map_one(ctx, u[idx], v[idx], V[idx], wc, w_stride)
-            H0 += h0c
-            qlo, qhi = min(qlo, qmin), max(qhi, qmax)
+            channels, chan = np.unique(np.asarray(frequencies).reshape(-1), return_inverse=True)
+            chan = np.ascontiguousarray(chan, dtype=np.int32)
+        if chan.shape[0] != u.shape[0]:
+            raise ValueError("map_visibilities: frequencies must have the length of u")
+        if len(channels) > 64:
+            raise ValueError("frank_b200 maps at most 64 frequency channels per call")
+        Ms, js, H0, qlo, qhi = self._map(ctx, u, v, V, weights, w_stride, chan=chan, nchan=len(channels))
         self._warn_qmin(qlo)
         return {'mult_freq': True, 'channels': channels, 'M': Ms, 'j': js, 'null_likelihood': H0,
                 'hash': [True, self._DHT, geometry, self._vis_model, self._scale_height]}
@@ -326,7 +355,8 @@ class GaussianModel(object):
         self._cov = None
         self._Sinv_cache = None
         if _solution is not None:
-            self._mu, self._U = _solution
+            self._mu, self._U = _solution                 # U may be None: factorised on first use (see _factor)
+            self._Dsvd = None
         else:
             self._fit()
 
@@ -356,8 +386,18 @@ class GaussianModel(object):
             self._Sinv_cache = np.dot(Y.T * (1 / self._p[0]), Y)
         return self._Sinv_cache
 
+    def _factor(self):
+        """The upper Cholesky factor of D^-1; computed on the device on first use for fits that arrived without one
+        (batched sweeps return only p and mu)."""
+        if self._U is None and getattr(self, '_Dsvd', None) is None:
+            mu = self._mu
+            self._fit()
+            self._mu = mu
+        return self._U
+
     def Dsolve(self, b):
         r"""D b through the GPU-computed Cholesky factor (post-fit helper, statistical_models.py:762-781)."""
+        self._factor()
         if getattr(self, '_Dsvd', None) is not None:                                   # :778-781
             U, s1, V = self._Dsvd
             b = np.asarray(b)
@@ -411,14 +451,13 @@ class LogNormalMAPModel(object):
     r"""Maximum a posteriori field of the log-normal model, P(s|V,p) ∝ G(H exp(s + s0) - V, M) G(s, S(p)).
 
     API mirror of frank.statistical_models.LogNormalMAPModel (frank/statistical_models.py:907-1295) for one
-    channel, one field and unit scale (what FrankFitter uses).  The objective, gradient, Hessian, its
-    factorisation and the Newton solves run on the GPU (fb_ln_* in include/frankb200.h); the Newton / line-search
-    decisions are taken on the host (frank_b200/minimizer.py).
+    channel, one field and unit scale (what FrankFitter uses).  The whole fit -- objective, gradient, Hessian, its
+    factorisation, the Newton solves and the line search -- is one device-resident call (fb_frank_lognormal_loop in
+    include/frankb200.h; the host thread of the call only reads the scalars the line-search decisions need).
     """
 
     def __init__(self, DHT, M, j, p=None, scale=None, s0=None, guess=None, Nfields=None, full_hessian=1,
-                 noise_likelihood=0, device=None):
-        from frank_b200.minimizer import LineSearch, MinimizeNewton
+                 noise_likelihood=0, device=None, _solution=None):
         self._DHT = DHT
         self._full_hess = full_hessian
         M = np.asarray(M)
@@ -450,35 +489,44 @@ class LogNormalMAPModel(object):
 
         ctx = _lib.get_context(device)
         ctx.dht_setup(DHT)
-        ctx.ln_setup(M, j, self._s0, full_hessian)
-        ctx.ln_set_spectrum(p)
         self._ctx = ctx
+        if _solution is not None:                  # produced by the device-resident loop of FrankFitter
+            self._s_MAP, self._U, self._status = _solution
+            return
+        # MinimizeNewton + LineSearch + the factor of the Hessian at the MAP point, device resident (fb_frank_lognormal_loop
+        # with max_iter < 0; statistical_models.py:1073-1160, minimizer.py:74-283)
+        out = ctx.frank_lognormal_loop(M, j, p, guess, self._s0, full_hessian=full_hessian, max_iter=-1)
+        self._raise_for_status(out['status'])
+        self._s_MAP = out['s']
+        self._status = out['newton']
+        self._U = np.triu(out['chol'])
 
-        def limit_step(dx, x):                                                        # :1136-1140
-            return min(1.1 * np.min(np.abs(x / dx)), 1) * dx
-
-        def newton_dir(x, refactor):
-            g, dx, rc = ctx.ln_newton_direction(x, refactor)
-            if rc == _lib.FB_E_NOTPD:
-                # The reference factorises with LU and would still get a (not necessarily descending) direction;
-                # an indefinite Hessian here makes the step fall back to gradient descent (minimizer.py:250-253).
-                # Not met on any fit path tested (0 of 1.2e5 Hessians in the reference runs).
-                return g, None
-            return g, dx
-
-        search = LineSearch(reduce_step=limit_step)
-        x0 = np.array(guess, dtype=np.float64).reshape(Nr)
-        s, self._status = MinimizeNewton(lambda x: ctx.ln_eval(x), lambda x: ctx.ln_eval(x, True)[1], newton_dir, x0,
-                                         search, tol=1e-7)
-        self._s_MAP = s
-        chol, _, rc = ctx.ln_posterior(s, p)                                          # cho_factor(hess(s)), :1148-1150
-        self._U = np.triu(chol)
+    @staticmethod
+    def _raise_for_status(rc):
+        if rc == _lib.FB_E_SLOPE:
+            raise ValueError("Round off in slope calculation")                        # minimizer.py:130-133
+        if rc == _lib.FB_E_BADP:
+            raise ValueError("Bad value in power spectrum. The power"
+                             " spectrum must be positive and not contain"
+                             " any NaN values. This is likely due to"
+                             " your UVtable (incorrect units or weights), "
+                             " or the deprojection being applied (incorrect"
+                             " geometry and/or phase center). Else you may"
+                             " want to increase `rout` by 10-20% or `n` so"
+                             " that it is large, >~300.")
+        if rc == _lib.FB_E_NOTPD:
+            # the reference switches to an SVD pseudo-inverse of the Hessian here (:1152-1158); on every case tried its
+            # next power-spectrum update then aborts with "Bad value in power spectrum" (tests/golden/make_golden.py,
+            # gen_config3): report the loss of definiteness instead of carrying an unusable factor
+            raise np.linalg.LinAlgError("LogNormalMAPModel: the Hessian at the MAP point is not positive definite")
 
     def _update_power_spectrum(self, alpha, p0, Tinv):
         """CriticalFilter.update_power_spectrum with this model's Hessian factor (device)."""
+        self._ctx.dht_setup(self._DHT)            # the process-wide context may have served another DHT since
         self._ctx.ln_setup(self._M, self._j, self._s0, self._full_hess)
         self._ctx.ln_set_spectrum(self._p)
-        _, p_new, _ = self._ctx.ln_posterior(self._s_MAP, self._p, alpha, p0, Tinv, want_chol=False)
+        _, p_new, rc = self._ctx.ln_posterior(self._s_MAP, self._p, alpha, p0, Tinv, want_chol=False)
+        self._raise_for_status(rc)
         return p_new
 
     def Dsolve(self, b):

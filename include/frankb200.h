@@ -12,6 +12,10 @@
  *                frank/statistical_models.py:747)
  *   FB_E_BADP    non-positive / NaN power spectrum (reference ValueError, statistical_models.py:688-698)
  *   FB_E_NOCONV  the Jacobi SVD of the fallback path did not converge (scipy.linalg.svd raises LinAlgError)
+ *   FB_E_SLOPE   the line search met a non-descending slope (reference: ValueError("Round off in slope calculation"),
+ *                frank/minimizer.py:130-133)
+ *   FB_E_RETRY   (fb_map_sync only) the data reach beyond the device's J0 table; the table has been rebuilt and the
+ *                asynchronous call must be submitted again (the synchronous entry points do this themselves)
  * Nothing throws or aborts across the ABI.  A context is bound to one device; calls on one context are
  * serialised on its stream and are complete (host-visible) when the function returns unless stated.
  * "dev" pointers are device memory on the context's device, "host" pointers are host memory.
@@ -27,6 +31,8 @@ extern "C" {
 #define FB_E_NOTPD 2
 #define FB_E_BADP 3
 #define FB_E_NOCONV 4
+#define FB_E_RETRY 5
+#define FB_E_SLOPE 6
 
 #define FB_MODEL_OPT_THICK 0
 #define FB_MODEL_OPT_THIN 1
@@ -48,6 +54,10 @@ int fb_ctx_create(fb_ctx **ctx, int device);
 int fb_ctx_destroy(fb_ctx *ctx);
 const char *fb_last_error(fb_ctx *ctx);
 int fb_version(void);
+/* Tuning knobs (also read from the environment at fb_ctx_create): "map_chunk" = visibilities per chunk of the host
+ * entry point's copy / compute pipeline (FB_MAP_CHUNK, default 1.25e6), "stage_threads" = host threads that gather
+ * pageable inputs into the pinned staging ring (FB_STAGE_THREADS, default 4). */
+int fb_set_option(fb_ctx *ctx, const char *name, double value);
 
 /* ---- DiscreteHankelTransform tables (frank/hankel.py:55-93) ---------------------------------
  * Host-side tables are O(N^2) setup and are passed in; the library builds the device-side J0
@@ -75,20 +85,59 @@ int fb_dht_setup(fb_ctx *ctx, int N, double Qmax, const double *host_j_nk, const
  *   check_qbounds nonzero: return FB_E_QRANGE (outputs untouched except qminmax) when q_last < max(q)
  *   q_last       last collocation frequency q[N-1]
  * Outputs (dev or host according to the entry point):
- *   M [nchan*N*N] row-major, j [nchan*N], H0 [1] null likelihood, qminmax [2] = min(q), max(q).
- * In a multi-GPU job each rank passes its slice and sums (M, j, H0) / min-maxes qminmax across ranks
- * afterwards (the sums are over independent visibilities). */
+ *   M [nchan*N*N] row-major, j [nchan*N], H0 [1] null likelihood (over all channels), qminmax [2] = min(q), max(q).
+ * Multi-frequency data (statistical_models.py:175-214): chan[i] is the index of visibility i's frequency in
+ * np.unique(frequencies); the channel becomes the high part of the sort key, every channel's run is padded to whole
+ * tiles and accumulated by its own Gram launch -- one call, no host-side splitting.
+ * In a multi-GPU job each rank passes its slice; with a communicator attached (fb_comm_init) the partial (M, j, H0)
+ * are summed and qminmax / the status combined over the ranks inside the call, on the library's stream, before
+ * anything is read back; without one the caller combines them (the sums are over independent visibilities).
+ *
+ * fb_map_visibilities_dev        inputs and outputs resident on the device; returns when the results are complete.
+ * fb_map_visibilities_dev_async  the same, enqueue only: no host synchronisation and no host read anywhere in the call
+ *                                (range check, J0-table check, sort scale, channel segments and the work table all
+ *                                live on the device), so it can be overlapped with other work or followed by further
+ *                                stream-ordered work of the library; fb_map_sync waits and returns the status
+ *                                (0, FB_E_QRANGE, or FB_E_RETRY) and qminmax.
+ * fb_map_visibilities_host       host arrays (pinned or pageable): a K-deep chunk pipeline (chunks of FB_MAP_CHUNK
+ *                                = 1.25e6 visibilities by default) copies chunk k+1 while chunk k is in the kernels;
+ *                                pageable inputs are gathered into a pinned staging ring by FB_STAGE_THREADS (4) host
+ *                                threads first.  Chunks are summed in order: deterministic for a given n. */
 int fb_map_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v,
                             const double *dev_V_reim, const double *dev_w, int w_stride,
                             const int32_t *dev_chan, int nchan, const fb_geometry *geom, int vis_model,
                             double model_scale, const double *host_H2, int check_qbounds, double q_last,
                             double *dev_M, double *dev_j, double *dev_H0, double *host_qminmax);
 
+int fb_map_visibilities_dev_async(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v,
+                                  const double *dev_V_reim, const double *dev_w, int w_stride,
+                                  const int32_t *dev_chan, int nchan, const fb_geometry *geom, int vis_model,
+                                  double model_scale, const double *host_H2, int check_qbounds, double q_last,
+                                  double *dev_M, double *dev_j, double *dev_H0);
+int fb_map_sync(fb_ctx *ctx, double *host_qminmax);
+
 int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const double *host_v,
                              const double *host_V_reim, const double *host_w, int w_stride,
                              const int32_t *host_chan, int nchan, const fb_geometry *geom, int vis_model,
                              double model_scale, const double *host_H2, int check_qbounds, double q_last,
                              double *host_M, double *host_j, double *host_H0, double *host_qminmax);
+
+/* ---- multi-GPU: one process per GPU, one communicator per context ----------------------------------
+ * The reference is a single process (no collective anywhere in frank/*.py); the visibility axis it already blocks over
+ * (statistical_models.py:192-214) is the data-parallel axis here.
+ *   fb_comm_unique_id   rank 0 creates the 128-byte NCCL id; the host framework broadcasts it (torch.distributed, MPI...)
+ *   fb_comm_init        every rank joins with it (ncclCommInitRank on the context's device); from then on the mapping
+ *                       entry points all-reduce their outputs in-call
+ *   fb_comm_allgather   `count` doubles per rank, host buffers, rank order (results of a sweep sharded by grid point)
+ *   fb_comm_allreduce_sum_dev   in-place sum of a device buffer on the library stream (asynchronous)
+ *   fb_comm_info        returns 1 when a communicator is attached; rank / nranks optional
+ * NCCL is loaded with dlopen at fb_comm_init: a single-GPU user never needs it. */
+int fb_comm_unique_id(void *out128);
+int fb_comm_init(fb_ctx *ctx, int nranks, int rank, const void *id128);
+int fb_comm_destroy(fb_ctx *ctx);
+int fb_comm_info(fb_ctx *ctx, int *rank, int *nranks);
+int fb_comm_allgather(fb_ctx *ctx, const double *host_send, int64_t count, double *host_recv);
+int fb_comm_allreduce_sum_dev(fb_ctx *ctx, double *dev_buf, int64_t count);
 
 /* Timing of the most recent map call, milliseconds by CUDA events on the context's stream:
  * out[0] prepass (deproject / phase shift / hypot / H0 / min-max), out[1] J0+Gram kernel,
@@ -170,6 +219,29 @@ int fb_ln_eval(fb_ctx *ctx, const double *host_s, double *host_f, double *host_g
 int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, double *host_g, double *host_dx, int *host_info);
 int fb_ln_posterior(fb_ctx *ctx, const double *host_s, const double *host_p, double alpha, double p0, const double *host_Tinv,
                     double *host_chol, double *host_p_new, int *host_info);
+
+/* The whole log-normal fit in one call (K7): LogNormalMAPModel._fit = MinimizeNewton + LineSearch (statistical_models.py:
+ * 1073-1160, minimizer.py:74-283) and, for max_iter >= 0, the power-spectrum iteration of FrankFitter._fit around it
+ * (radial_fitters.py:765-785):
+ *     fit = LogNormalMAPModel(p_init, guess)
+ *     while not converged(p, p_old) and count <= max_iter:
+ *         p_old = p ; p = CriticalFilter.update_power_spectrum(fit) ; fit = LogNormalMAPModel(p, guess=fit.MAP) ; count += 1
+ * Every vector stays on the device; the host thread of the call takes the scalar decisions of the line search and of the
+ * Newton iteration from a few doubles in mapped pinned memory.  The Hessian is factorised by the blocked Cholesky of
+ * the Normal path where the reference uses LU (minimizer.py:238): the Hessians of a descending iteration are positive
+ * definite; an indefinite one makes that step fall back to gradient descent, like a non-descending Newton direction
+ * does in the reference (:244-253).  max_iter < 0: the single fit only (what LogNormalMAPModel's constructor does).
+ * Host pointers: M [N*N], j [N], p_init [N], guess [N] (s = log I - s0), Tinv [N*N] as in fb_frank_normal_loop.
+ * Outputs: s [N] the MAP point of the last fit, p [N] its power spectrum, chol [N*N] (optional) the upper factor of the
+ * Hessian at s, niter = count, converged, info (potrf), stats [7] (optional) = Newton steps, function evaluations,
+ * Hessians, and how many fits ended with MinimizeNewton status 0, 1, 2, 3; hist_p / hist_s [hist_cap*N] (optional).
+ * Returns FB_E_BADP when an update produced a non-positive / NaN spectrum (reference: ValueError), FB_E_NOTPD when the
+ * Hessian at a MAP point is not positive definite (reference: SVD pseudo-inverse, :1152-1158), FB_E_SLOPE. */
+int fb_frank_lognormal_loop(fb_ctx *ctx, const double *host_M, const double *host_j, const double *host_p_init,
+                            const double *host_guess, double s0, double full_hessian, double alpha, double p0,
+                            const double *host_Tinv, double tol, int max_iter, double newton_tol, double *host_s,
+                            double *host_p, double *host_chol, int *host_niter, int *host_converged, int *host_info,
+                            long long *host_stats, double *host_hist_p, double *host_hist_s, int hist_cap);
 
 /* ---- UVDataBinner (frank/utilities.py:180-400) -------------------------------------------------------------
  * fb_uv_max: max(uv) (the caller forms nbins = ceil(max / width) with the reference's guard, utilities.py:205-208).

@@ -23,6 +23,16 @@ whatever the reference's public API returns for them:
   svd_fallback.npz   GaussianModel solutions through the reference's SVD pseudo-inverse branch (indefinite and
                      rank-deficient systems, statistical_models.py:747-755)
   gauss_kat.npz      the reference's analytic Gaussian Hankel-pair test inputs (tests.py:37-130)
+  config1_normal_1e6_N300.npz   BASELINE.json configs[0]: FrankFitter Normal fit, 1e6 visibilities, N=300, alpha=1.05,
+                     wsmooth=1e-4 -- the reference's M, j, H0, MAP, power spectrum, iteration count and its own
+                     self-noise (M under permutation / block_size, profile under permutation).  Inputs are NOT stored:
+                     they are regenerated bit for bit by oracle.frank_oracle.synthetic_disc (NumPy/SciPy only; input
+                     checksums stored)
+  config3_lognormal_N500.npz    configs[2] shape: LogNormal MAP fit, N=500, Rmax=1.0", alpha=1.3, wsmooth=1e-2 on 5e4 visibilities
+                     (at Rmax=1.6" the reference itself aborts, see gen_config3):
+                     M (upper triangle), j, H0, s_MAP, MAP, power spectrum, iteration count, Newton statistics
+  config5_debris_N2000.npz      configs[4] shape: N=2000, 4 channels, debris scale height, 2e4 visibilities:
+                     j, H0, channels, the diagonal and 6000 seeded sample entries of every channel's M
 """
 import os
 import sys
@@ -159,7 +169,139 @@ def gen_svd_fallback():
                         Vfit_c=sol.predict(u, v), s1_c=sol._fit._Dsvd[1])
 
 
+def gen_lognormal(g):
+    """FrankFitter(method='LogNormal') at N = 40 with the whole iteration history (the stopping iteration of this path is
+    round-off sensitive: the history lets the tests compare trajectories at equal iteration count)."""
+    Nl = 40
+    ul, vl, Vl, wl, _ = synthetic(4000, Nl, seed=777)
+    FL = FrankFitter(1.6, Nl, g, alpha=1.3, weights_smooth=1e-2, method='LogNormal', verbose=False,
+                     store_iteration_diagnostics=True)
+    sl = FL.fit(ul, vl, Vl, wl)
+    dl = FL.iteration_diagnostics
+    np.savez_compressed(os.path.join(OUT, 'fit_lognormal.npz'), N=Nl, u=ul, v=vl, V=Vl, w=wl, M=FL._M, j=FL._j, MAP=sl.MAP, power_spectrum=sl.power_spectrum,
+                        num_iterations=dl['num_iterations'], s_MAP=sl._fit.MAP,
+                        p_first=np.array(dl['power_spectrum'][:3]), MAP_first=np.array(dl['MAP'][:3]),
+                        p_hist=np.array(dl['power_spectrum']), s_hist=np.array(dl['MAP']),
+                        self_noise=self_noise(lambda kw: FrankFitter(1.6, Nl, g, alpha=1.3, weights_smooth=1e-2, method='LogNormal',
+                                                                     verbose=False, **kw), ul, vl, Vl, wl, sl.MAP, nperm=1))
+    return ul, vl, Vl, wl
+
+
+def _upper(M):
+    return M[np.triu_indices(M.shape[0])]
+
+
+def gen_config1():
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case (1e6 visibilities, N=300, Normal)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import frank_oracle as fo
+    import time
+    n, N = 1_000_000, 300
+    u, v, V, w, _ = fo.synthetic_disc(n, N)               # seed 12345, SURVEY 8(d) shape; regenerated by the tests
+    g = FixedGeometry(30., 40., 1e-3, -2e-3)
+    FF = FrankFitter(1.6, N, g, alpha=1.05, weights_smooth=1e-4, verbose=False, store_iteration_diagnostics=True)
+    t0 = time.time()
+    sol = FF.fit(u, v, V, w)
+    print('config1: reference fit', time.time() - t0, 's', FF.iteration_diagnostics['num_iterations'], 'iterations', flush=True)
+    M, j, H0 = FF._M.copy(), FF._j.copy(), FF._H0
+    # the reference's own round-off floor on this data set: same visibilities permuted / another block_size
+    perm = np.random.default_rng(1000).permutation(n)
+    FP = FrankFitter(1.6, N, g, alpha=1.05, weights_smooth=1e-4, verbose=False)
+    solp = FP.fit(u[perm], v[perm], V[perm], w[perm])
+    Mp = FP._M
+    vm = VisibilityMapping(FF._DHT, g, verbose=False, block_size=20000)
+    Mb = vm.map_visibilities(u, v, V, w)['M']
+    d = np.sqrt(np.diag(M))
+    self_M_entry = max(np.max(np.abs(Mp - M) / np.abs(M)), np.max(np.abs(Mb - M) / np.abs(M)))
+    self_M_cs = max(np.max(np.abs(Mp - M) / np.outer(d, d)), np.max(np.abs(Mb - M) / np.outer(d, d)))
+    self_M_max = max(np.max(np.abs(Mp - M)), np.max(np.abs(Mb - M))) / np.max(np.abs(M))
+    self_prof = np.max(np.abs(solp.MAP - sol.MAP)) / np.max(np.abs(sol.MAP))
+    print('config1: self-noise M per-entry %.3e  /sqrt(MkkMll) %.3e  max-norm %.3e  profile %.3e' %
+          (self_M_entry, self_M_cs, self_M_max, self_prof), flush=True)
+    np.savez_compressed(os.path.join(OUT, 'config1_normal_1e6_N300.npz'), n_vis=n, N=N, Rmax=1.6,
+                        geom=np.array([30., 40., 1e-3, -2e-3]), alpha=1.05, wsmooth=1e-4,
+                        in_check=np.array([u.sum(), v.sum(), V.real.sum(), V.imag.sum(), w.sum(), u[123456], V[654321].real]),
+                        M=M, j=j, H0=H0, MAP=sol.MAP, power_spectrum=sol.power_spectrum,
+                        num_iterations=FF.iteration_diagnostics['num_iterations'],
+                        self_noise_M_entry=self_M_entry, self_noise_M_cs=self_M_cs, self_noise_M_max=self_M_max,
+                        self_noise=self_prof, num_iterations_permuted=-1)
+
+
+def gen_config3():
+    """BASELINE.json configs[2] shape: LogNormal MAP fit at N=500 on 5e4 visibilities, Rmax = 1.0".
+
+    With the SURVEY disc at Rmax = 1.6" the REFERENCE cannot run this configuration: for N >= 300 the Hessian of its first
+    log-normal fit is numerically indefinite, cho_factor fails, the SVD pseudo-inverse branch (statistical_models.py:1152-1158)
+    takes over and the first power-spectrum update returns zeros and infinities -> ValueError('Bad value in power
+    spectrum'), for every (alpha, wsmooth) and every n_vis tried (2e4 .. 1e6; N = 250 is the largest N that completes).
+    At Rmax = 1.0" (the disc ends at ~0.85") and 5e4 visibilities (seed 31) the reference completes at N = 500, which is what
+    is pinned here -- when generated with OMP_NUM_THREADS=2.  With 1e5 visibilities of the same seed, or with the same 5e4
+    visibilities and 1 or 4 BLAS threads (a different summation order inside dgemm), it aborts again: at this N the
+    reference's log-normal path sits on the edge of its own numerical failure, which is why the GPU test compares the solver
+    on the reference's M and j at the authors' tolerance and not bit for bit.."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import frank_oracle as fo
+    import time
+    import frank.minimizer as fm
+    n, N, Rmax = int(os.environ.get('C3_NVIS', 50_000)), 500, 1.0
+    u, v, V, w, _ = fo.synthetic_disc(n, N, Rmax, seed=31)
+    g = FixedGeometry(30., 40., 1e-3, -2e-3)
+    stats = []
+    orig = fm.MinimizeNewton
+
+    def spy(*a, **k):
+        x, st = orig(*a, **k)
+        stats.append(st)
+        return x, st
+    import frank.statistical_models as fsm
+    fsm.MinimizeNewton = spy
+    FL = FrankFitter(Rmax, N, g, alpha=1.3, weights_smooth=1e-2, method='LogNormal', verbose=False,
+                     store_iteration_diagnostics=True)
+    t0 = time.time()
+    sl = FL.fit(u, v, V, w)
+    fsm.MinimizeNewton = orig
+    dl = FL.iteration_diagnostics
+    print('config3: reference LogNormal fit', time.time() - t0, 's', dl['num_iterations'], 'iterations', flush=True)
+    st = np.array(stats)
+    np.savez_compressed(os.path.join(OUT, 'config3_lognormal_N500.npz'), n_vis=n, N=N, Rmax=Rmax, seed=31, alpha=1.3, wsmooth=1e-2,
+                        in_check=np.array([u.sum(), v.sum(), V.real.sum(), V.imag.sum(), w.sum()]),
+                        M_upper=_upper(FL._M), j=FL._j, H0=FL._H0, MAP=sl.MAP, s_MAP=sl._fit.MAP,
+                        power_spectrum=sl.power_spectrum, num_iterations=dl['num_iterations'],
+                        p_first=np.array(dl['power_spectrum'][:3]), MAP_first=np.array(dl['MAP'][:3]),
+                        p_hist=np.array(dl['power_spectrum'])[::4], s_hist=np.array(dl['MAP'])[::4],
+                        newton_stats=st)
+
+
+def gen_config5():
+    """BASELINE.json configs[4] shape: N=2000, 4 channels, debris model (2e4 visibilities)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import frank_oracle as fo
+    n, N = 20_000, 2000
+    u, v, V, w, _ = fo.synthetic_disc(n, N, seed=55)
+    freqs = np.random.default_rng(56).choice(np.array([2.1e11, 2.3e11, 3.3e11, 3.4e11]), n)
+    g = FixedGeometry(30., 40., 1e-3, -2e-3)
+    dht = DiscreteHankelTransform(1.6 / rad_to_arcsec, N)
+    vm = VisibilityMapping(dht, g, vis_model='debris', scale_height=lambda r: 0.05 * r, verbose=False)
+    m = vm.map_visibilities(u, v, V, w, frequencies=freqs)
+    M = m['M']
+    rng = np.random.default_rng(57)
+    rows, cols = rng.integers(0, N, 6000), rng.integers(0, N, 6000)
+    np.savez_compressed(os.path.join(OUT, 'config5_debris_N2000.npz'), n_vis=n, N=N, seed=55,
+                        in_check=np.array([u.sum(), v.sum(), V.real.sum(), V.imag.sum(), w.sum(), freqs.sum()]),
+                        channels=m['channels'], j=m['j'], H0=m['null_likelihood'], H2=vm._H2,
+                        M_diag=np.array([np.diag(Mc) for Mc in M]), rows=rows, cols=cols,
+                        M_sample=np.array([Mc[rows, cols] for Mc in M]),
+                        M_absmax=np.array([np.max(np.abs(Mc)) for Mc in M]),
+                        M_sum=np.array([Mc.sum() for Mc in M]))
+    print('config5 written', flush=True)
+
+
 def main():
+    for name, fn in (('config1', gen_config1), ('config3', gen_config3), ('config5', gen_config5),
+                     ('lognormal', lambda: gen_lognormal(FixedGeometry(30., 40., 1e-3, -2e-3)))):
+        if sys.argv[1:] == [name]:
+            fn()
+            return
     if sys.argv[1:] == ['svd_fallback']:
         gen_svd_fallback()
         return
@@ -244,17 +386,7 @@ def main():
                         self_noise=self_noise(lambda kw: FourierBesselFitter(1.6, 20, g, verbose=False, **kw), u, v, V, w, sb.MAP))
 
     # ---- LogNormal fit --------------------------------------------------------------------
-    Nl = 40
-    ul, vl, Vl, wl, _ = synthetic(4000, Nl, seed=777)
-    FL = FrankFitter(1.6, Nl, g, alpha=1.3, weights_smooth=1e-2, method='LogNormal', verbose=False,
-                     store_iteration_diagnostics=True)
-    sl = FL.fit(ul, vl, Vl, wl)
-    dl = FL.iteration_diagnostics
-    np.savez_compressed(os.path.join(OUT, 'fit_lognormal.npz'), N=Nl, u=ul, v=vl, V=Vl, w=wl, M=FL._M, j=FL._j, MAP=sl.MAP, power_spectrum=sl.power_spectrum,
-                        num_iterations=dl['num_iterations'], s_MAP=sl._fit.MAP,
-                        p_first=np.array(dl['power_spectrum'][:3]), MAP_first=np.array(dl['MAP'][:3]),
-                        self_noise=self_noise(lambda kw: FrankFitter(1.6, Nl, g, alpha=1.3, weights_smooth=1e-2, method='LogNormal',
-                                                                     verbose=False, **kw), ul, vl, Vl, wl, sl.MAP, nperm=1))
+    ul, vl, Vl, wl = gen_lognormal(g)
 
     # ---- debris Normal fit ----------------------------------------------------------------
     FD = FrankDebrisFitter(1.6, 40, g, lambda r: 0.05 * r, alpha=1.3, weights_smooth=1e-2, verbose=False,

@@ -73,3 +73,54 @@ def test_shard_bounds_cover():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _sweep_worker(rank, world, port, out_dir):
+    """Sweep sharded by grid point: every rank solves its share of a 3 x 3 (alpha, wsmooth) grid (oracle solver standing in
+    for the batched device loop) and the all-gather returns the whole grid to every rank."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from frank_b200.distributed import sweep_sharded
+    N = 24
+    u, v, V, w, dht = fo.synthetic_disc(3000, N, seed=5)
+    m = fo.map_visibilities(dht, u, v, V, w, 30., 40., 1e-3, -2e-3)
+    grid = [(a, ws) for a in (1.05, 1.2, 1.4) for ws in (1e-3, 1e-2, 1e-1)]
+    solved = []
+
+    def solve_points(idx):
+        solved.extend(int(i) for i in idx)
+        fits = [fo.frank_fit(dht, m['M'], m['j'], alpha=grid[i][0], weights_smooth=grid[i][1], max_iter=60) for i in idx]
+        return {'p': np.array([f['power_spectrum'] for f in fits]), 'mu': np.array([f['MAP'] for f in fits]),
+                'niter': np.array([f['num_iterations'] for f in fits]), 'converged': np.array([f['converged'] for f in fits])}
+
+    res = sweep_sharded(solve_points, len(grid), N)
+    np.savez(os.path.join(out_dir, f's{rank}.npz'), solved=np.array(solved), **res)
+    dist.destroy_process_group()
+
+
+def test_sweep_sharded_by_grid_point_gloo(tmp_path):
+    world = 2
+    mp.spawn(_sweep_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / 's0.npz'), np.load(tmp_path / 's1.npz')
+    assert list(r0['solved']) == [0, 1, 2, 3, 4] and list(r1['solved']) == [5, 6, 7, 8]      # each point solved exactly once
+    for k in ('p', 'mu', 'niter', 'converged'):
+        assert np.array_equal(r0[k], r1[k])                                                  # every rank holds the whole grid
+    # equal to the unsharded sweep, bit for bit
+    N = 24
+    u, v, V, w, dht = fo.synthetic_disc(3000, N, seed=5)
+    m = fo.map_visibilities(dht, u, v, V, w, 30., 40., 1e-3, -2e-3)
+    grid = [(a, ws) for a in (1.05, 1.2, 1.4) for ws in (1e-3, 1e-2, 1e-1)]
+    for i, (a, ws) in enumerate(grid):
+        f = fo.frank_fit(dht, m['M'], m['j'], alpha=a, weights_smooth=ws, max_iter=60)
+        assert np.array_equal(r0['mu'][i], f['MAP']) and np.array_equal(r0['p'][i], f['power_spectrum'])
+        assert int(r0['niter'][i]) == f['num_iterations'] and bool(r0['converged'][i]) == f['converged']
+
+
+def test_sweep_sharded_single_process():
+    from frank_b200.distributed import sweep_sharded, sweep_shard
+    assert list(sweep_shard(64, 3, 8)) == list(range(24, 32))
+    res = sweep_sharded(lambda idx: {'p': np.outer(idx, np.ones(3)), 'mu': np.outer(idx, 2 * np.ones(3)),
+                                     'niter': idx * 10, 'converged': idx % 2}, 5, 3)
+    assert np.array_equal(res['p'][:, 0], np.arange(5)) and np.array_equal(res['niter'], np.arange(5) * 10)
+    assert list(res['converged']) == [False, True, False, True, False]
