@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libfrankb200.so')
+LIB_PATH = os.environ.get('FRANK_B200_LIB') or os.path.join(_HERE, 'lib', 'libfrankb200.so')     # (override: kernel A/B builds)
 
 FB_E_QRANGE, FB_E_NOTPD, FB_E_BADP, FB_E_NOCONV, FB_E_RETRY, FB_E_SLOPE = 1, 2, 3, 4, 5, 6
 MODEL_CODE = {'opt_thick': 0, 'opt_thin': 1, 'debris': 2}
@@ -57,6 +57,8 @@ _SIGNATURES = {
     'fb_chol_solve': ([_c_p, _c_p, _c_i, _c_p, _c_p], _c_i),
     'fb_gaussian_svd': ([_c_p, _c_p, _c_p, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_predict_visibilities': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
+    'fb_predict_visibilities_dev': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
+    'fb_predict_sky_dev': ([_c_p, _c_l, _c_p, _c_p, ctypes.POINTER(FBGeometry), _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
     'fb_apply_correction_dev': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_uv_max': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_uv_bin': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
@@ -402,6 +404,32 @@ class Context(object):
         V = np.empty_like(q)
         self.check(self._lib.fb_predict_visibilities(self._h, q.size, _ptr(q), _ptr(kzc), _ptr(I), int(vis_model), float(model_scale),
                                                      _ptr(H2c), _ptr(V)), 'fb_predict_visibilities')
+        return V
+
+    def predict_visibilities_dev(self, q, kz, I, vis_model, model_scale, H2):
+        """fb_predict_visibilities_dev on float64 CUDA tensors q [n] (and kz [n] for the debris model); returns V [n] on the device."""
+        import torch
+        I = np.ascontiguousarray(I, dtype=np.float64)
+        H2c = None if H2 is None else np.ascontiguousarray(H2, dtype=np.float64)
+        q = q.reshape(-1).to(torch.float64).contiguous()
+        kzc = None if kz is None else kz.reshape(-1).to(torch.float64).contiguous()
+        V = torch.empty_like(q)
+        torch.cuda.current_stream(q.device).synchronize()
+        self.check(self._lib.fb_predict_visibilities_dev(self._h, q.numel(), _ptr(q), _ptr(kzc), _ptr(I), int(vis_model), float(model_scale),
+                                                         _ptr(H2c), _ptr(V)), 'fb_predict_visibilities_dev')
+        return V
+
+    def predict_sky_dev(self, u, v, geom, I, vis_model, model_scale, H2):
+        """fb_predict_sky_dev: sky-plane prediction for float64 CUDA tensors u, v [n]; returns a complex128 CUDA tensor [n]."""
+        import torch
+        I = np.ascontiguousarray(I, dtype=np.float64)
+        H2c = None if H2 is None else np.ascontiguousarray(H2, dtype=np.float64)
+        u = u.reshape(-1).to(torch.float64).contiguous()
+        v = v.reshape(-1).to(torch.float64).contiguous()
+        V = torch.empty(u.numel(), dtype=torch.complex128, device=u.device)
+        torch.cuda.current_stream(u.device).synchronize()
+        self.check(self._lib.fb_predict_sky_dev(self._h, u.numel(), _ptr(u), _ptr(v), ctypes.byref(geom), _ptr(I), int(vis_model),
+                                                float(model_scale), _ptr(H2c), _ptr(torch.view_as_real(V))), 'fb_predict_sky_dev')
         return V
 
     # -- uv binning -----------------------------------------------------------------------------

@@ -63,7 +63,7 @@ int fb_ctx_destroy(fb_ctx *ctx)
     for (void *p : {(void *)ctx->d_jk, (void *)ctx->d_ck, (void *)ctx->d_Y, (void *)ctx->d_tab, (void *)ctx->d_types,
                     (void *)ctx->d_tile_panel, (void *)ctx->d_panel_t0, (void *)ctx->d_panel_nt, (void *)ctx->d_pair_code,
                     (void *)ctx->d_work, (void *)ctx->d_S, (void *)ctx->d_chunkred, (void *)ctx->d_result, (void *)ctx->d_status,
-                    (void *)ctx->d_H2, (void *)ctx->d_out, (void *)ctx->d_binstart, (void *)ctx->d_pack,
+                    (void *)ctx->d_H2, (void *)ctx->d_predI, (void *)ctx->d_out, (void *)ctx->d_binstart, (void *)ctx->d_pack,
                     (void *)ctx->sv_D, (void *)ctx->sv_p, (void *)ctx->sv_mu, (void *)ctx->sv_tr2, (void *)ctx->sv_alpha,
                     (void *)ctx->sv_p0, (void *)ctx->sv_Tinv, (void *)ctx->sv_M, (void *)ctx->sv_j, (void *)ctx->sv_Z,
                     (void *)ctx->sv_flags, (void *)ctx->sv_hist, (void *)ctx->sv_rhs, (void *)ctx->sv_notconv, (void *)ctx->sv_rdiag, (void *)ctx->ln_S, (void *)ctx->ln_vec, (void *)ctx->ln_ws})

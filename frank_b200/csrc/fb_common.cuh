@@ -103,6 +103,8 @@ struct fb_ctx {
     uint32_t *d_binstart = nullptr;   // uv binner: segment starts of the sorted items [nbins + 1]
     size_t bin_cap = 0;
     double *d_H2 = nullptr;
+    double *d_predI = nullptr;     // prediction: brightness profile [N] and behind it the table-overflow flag (2 words)
+    int predI_cap = 0;
     double *d_out = nullptr;       // host entry point: M | j | H0 on the device
     size_t out_cap = 0;
     int map_chunks = 1;            // chunks of the most recent call (timing)
@@ -163,6 +165,33 @@ struct fb_ctx {
         ctx->err = (msg);       \
         return (code);          \
     } while (0)
+
+// np.hypot = glibc's non-FMA kernel (sysdeps/ieee754/dbl-64/e_hypot.c, glibc >= 2.35), one correctly rounded operation at
+// a time: q, and with it every J0 argument, is bit-equal to NumPy's (tests/test_gpu_mapping.py::test_prepass_bits).
+#ifdef __CUDACC__
+__device__ __forceinline__ double hypot_glibc(double x, double y)
+{
+    double ax = fabs(x), ay = fabs(y);
+    if (ax < ay) { double t = ax; ax = ay; ay = t; }
+    // scaling branches of glibc (huge / tiny operands) are irrelevant for baselines in wavelengths
+    // (1 .. 1e9) but kept for exactness of the common-case predicate
+    if (ax >= __ddiv_rn(ay, 0x1p-54)) return __dadd_rn(ax, ay);
+    double h = __dsqrt_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+    double t1, t2;
+    if (h <= __dmul_rn(2.0, ay)) {
+        double delta = __dsub_rn(h, ay);
+        t1 = __dmul_rn(ax, __dsub_rn(__dmul_rn(2.0, delta), ax));
+        t2 = __dmul_rn(__dsub_rn(delta, __dmul_rn(2.0, __dsub_rn(ax, ay))), delta);
+    } else {
+        double delta = __dsub_rn(h, ax);
+        t1 = __dmul_rn(__dmul_rn(2.0, delta), __dsub_rn(ax, __dmul_rn(2.0, ay)));
+        t2 = __dadd_rn(__dmul_rn(__dsub_rn(__dmul_rn(4.0, delta), ay), ay), __dmul_rn(delta, delta));
+    }
+    h = __dsub_rn(h, __ddiv_rn(__dadd_rn(t1, t2), __dmul_rn(2.0, h)));
+    return h;
+}
+
+#endif
 
 // kernels / launchers implemented in the .cu files
 struct FbMapJob {              // arguments of one mapping call, shared by its chunks

@@ -204,6 +204,68 @@ __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sba
     }
 }
 
+// Variant of the J0 phase with one column per HALF-warp and four visibilities per lane (lane16, lane16 + 16, + 32, + 48):
+// the five 16-byte loads of a column's row (centre / j_k and four coefficient pairs) are issued once for TWO columns --
+// the two half-warps of a load instruction read two different rows -- so a column costs half the shared-memory
+// wavefronts of its coefficient fetch (the sweep of j0_columns is bound by them: 15 wavefronts against 10 clocks of
+// FP64-pipe time per column), at the price of two more Horner chains' worth of registers.
+template <bool DEBRIS>
+__device__ __forceinline__ void j0_columns4(const GramArgs &p, const uint32_t sbase, const int buf, const int ncol,
+                                            const int warp, const int lane, const int last_row)
+{
+    const int l16 = lane & 15, half = lane >> 4;
+    const uint32_t s_vis = sbase + SMB_VIS + buf * (GS * 32);
+    double av[4], kk[4];             // a of this lane's four visibilities (sqrt w is re-read at the store: registers)
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        av[m] = lds_f64(s_vis + (l16 + 16 * m) * 32);
+        kk[m] = 0.0;
+        if (DEBRIS) { const double k = lds_f64(s_vis + (l16 + 16 * m) * 32 + 16); kk[m] = -k * k; }
+    }
+    const int c0 = 2 * warp + half;
+    uint32_t a_row = sbase + SMB_ROW + buf * (GCOLS * ROWB) + c0 * 16;
+    uint32_t a_cen = sbase + SMB_CEN + (buf * GCOLS + c0) * 16;
+    uint32_t a_g = sbase + SMB_G + (c0 * GLD + l16) * 8;
+#pragma unroll 1
+    for (int sc = c0; sc < ncol; sc += 2 * NW) {
+        const double2 cv = lds_v2f64(a_cen);                             // (centre, +j_k | -j_k: gather | -0: no store)
+        const double2 c67 = lds_v2f64(a_row + 3 * GCOLS * 16), c45 = lds_v2f64(a_row + 2 * GCOLS * 16),
+                      c23 = lds_v2f64(a_row + GCOLS * 16), c01 = lds_v2f64(a_row);
+        const double jk = fabs(cv.y);
+        const bool plain = __double2hiint(cv.y) >= 0;                    // one staged row serves the tile
+        const bool gather = !plain && cv.y != 0.0;                       // half-warp-uniform, rare
+        double h2 = 0.0;
+        if (DEBRIS) h2 = lds_f64(sbase + SMB_H2 + sc * 8);
+        // two passes of two chains: the row stays in registers, only two evaluations are live at a time (four live chains
+        // next to the 60 accumulator registers made ptxas spill inside the DMMA loops)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const double x0 = __dmul_rn(av[2 * h], jk), x1 = __dmul_rn(av[2 * h + 1], jk);       // a * j_k as the reference rounds it
+            const double u0 = __dsub_rn(x0, cv.x), u1 = __dsub_rn(x1, cv.x);                     // exact
+            double g0 = fma(c67.y, u0, c67.x), g1 = fma(c67.y, u1, c67.x);
+            g0 = fma(g0, u0, c45.y); g1 = fma(g1, u1, c45.y);
+            g0 = fma(g0, u0, c45.x); g1 = fma(g1, u1, c45.x);
+            g0 = fma(g0, u0, c23.y); g1 = fma(g1, u1, c23.y);
+            g0 = fma(g0, u0, c23.x); g1 = fma(g1, u1, c23.x);
+            g0 = fma(g0, u0, c01.y); g1 = fma(g1, u1, c01.y);
+            g0 = fma(g0, u0, c01.x); g1 = fma(g1, u1, c01.x);
+            if (gather) {
+                g0 = j0_tab(x0, p.tab, last_row);
+                g1 = j0_tab(x1, p.tab, last_row);
+            }
+            if (DEBRIS) {
+                g0 *= exp_neg(kk[2 * h] * h2);
+                g1 *= exp_neg(kk[2 * h + 1] * h2);
+            }
+            if (plain || gather) {                                       // the data column and the padding are written elsewhere
+                sts_f64(a_g + 32 * h * 8, g0 * lds_f64(s_vis + (l16 + 32 * h) * 32 + 8));
+                sts_f64(a_g + (32 * h + 16) * 8, g1 * lds_f64(s_vis + (l16 + 32 * h + 16) * 32 + 8));
+            }
+        }
+        a_row += 2 * NW * 16; a_cen += 2 * NW * 16; a_g += 2 * NW * GLD * 8;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // One work item for one warp: per stage, the DMMAs of stage s, then the warp's J0 segments of stage s + 1
 // ---------------------------------------------------------------------------------------------
@@ -323,7 +385,11 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
             const int vv = tid - (FB_GRAM_THREADS - GS);
             sts_f64(sbase + SMB_G + (it.dcol * GLD + vv) * 8, lds_f64(sbase + SMB_VIS + buf * (GS * 32) + vv * 32 + 24));
         }
+#ifdef FB_J0_HALFWARP
+        j0_columns4<DEBRIS>(p, sbase, buf, it.ncol, tid >> 5, lane, last_row);
+#else
         j0_columns<DEBRIS>(p, sbase, buf, it.ncol, tid >> 5, lane, last_row);
+#endif
     };
 
     const long long q0 = it.q0;
@@ -527,11 +593,31 @@ k_gram_scale(int N, int NT, int npairs, const double *__restrict__ S, const doub
 }
 
 // K8: predicted visibilities V_i = sum_k H_ik I_k, H_ik = c_k J0(a_i j_k) scale_ik   (statistical_models.py:279-329).
-// One warp per visibility, lanes stride over the modes; fixed shuffle tree.
+// One warp per visibility, lanes stride over the modes; fixed shuffle tree.  Arguments beyond the J0 table raise `flag`
+// (flag[0] = 1, flag[1] = bits of the largest argument met): the host grows the table and repeats the call.
+__device__ __forceinline__ double predict_row(double a, double kk, int N, const double *__restrict__ jk, const double *__restrict__ ck,
+                                              const double *__restrict__ Ik, const double *__restrict__ H2, double scale,
+                                              const double2 *__restrict__ tab, int rows, int lane, unsigned long long *flag)
+{
+    const double x_table = (double)(rows - 3) * FB_J0_H;
+    double acc = 0.0;
+    for (int k = lane; k < N; k += 32) {
+        const double x = __dmul_rn(a, jk[k]);
+        if (x > x_table) { flag[0] = 1ull; atomicMax(flag + 1, (unsigned long long)__double_as_longlong(x)); }
+        double h = ck[k] * j0_tab(x, tab, rows - 1);
+        h *= H2 ? exp(kk * H2[k]) : scale;
+        acc = fma(h, Ik[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    return acc;                      // valid in lane 0
+}
+
 __global__ void __launch_bounds__(256)
 k_predict(int64_t n, int N, const double *__restrict__ q, const double *__restrict__ kz, double invQmax,
           const double *__restrict__ jk, const double *__restrict__ ck, const double *__restrict__ Ik,
-          const double *__restrict__ H2, double scale, const double2 *__restrict__ tab, int rows, double *__restrict__ V)
+          const double *__restrict__ H2, double scale, const double2 *__restrict__ tab, int rows, double *__restrict__ V,
+          unsigned long long *__restrict__ flag)
 {
     const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -539,15 +625,39 @@ k_predict(int64_t n, int N, const double *__restrict__ q, const double *__restri
     const double a = __dmul_rn(q[i], invQmax);
     double kk = 0.0;
     if (H2) { kk = kz[i]; kk = -kk * kk; }
-    double acc = 0.0;
-    for (int k = lane; k < N; k += 32) {
-        double h = ck[k] * j0_tab(__dmul_rn(a, jk[k]), tab, rows - 1);
-        h *= H2 ? exp(kk * H2[k]) : scale;
-        acc = fma(h, Ik[k], acc);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    const double acc = predict_row(a, kk, N, jk, ck, Ik, H2, scale, tab, rows, lane, flag);
     if (lane == 0) V[i] = acc;
+}
+
+// FrankRadialFit.predict (radial_fitters.py:56-98) in one pass over sky-plane baselines: deproject (geometry.py:111-131),
+// q = hypot, V = H(q) I, then undo_correction (geometry.py:239-265): re-project the deprojected baseline and rotate the
+// phase, V_sky = V (cos phi + i sin phi) -- every step a single correctly rounded operation in the reference's order.
+__global__ void __launch_bounds__(256)
+k_predict_sky(int64_t n, int N, const double *__restrict__ u, const double *__restrict__ v, fb_geometry g, double invQmax,
+              const double *__restrict__ jk, const double *__restrict__ ck, const double *__restrict__ Ik,
+              const double *__restrict__ H2, double scale, const double2 *__restrict__ tab, int rows, double2 *__restrict__ Vsky,
+              unsigned long long *__restrict__ flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const double ui = u[i], vi = v[i];
+    double up = __dsub_rn(__dmul_rn(ui, g.cos_pa), __dmul_rn(vi, g.sin_pa));
+    const double vp = __dadd_rn(__dmul_rn(ui, g.sin_pa), __dmul_rn(vi, g.cos_pa));
+    const double kz = __dmul_rn(up, g.sin_inc);
+    up = __dmul_rn(up, g.cos_inc);
+    const double a = __dmul_rn(hypot_glibc(up, vp), invQmax);
+    const double acc = predict_row(a, -kz * kz, N, jk, ck, Ik, H2, scale, tab, rows, lane, flag);
+    if (lane == 0) {
+        // reproject: u'' = u' / cos(inc); rotate by -PA (sin(PA) * -1), geometry.py:115-127
+        const double ud = __ddiv_rn(up, g.cos_inc), nst = __dmul_rn(g.sin_pa, -1.0);
+        const double ur = __dsub_rn(__dmul_rn(ud, g.cos_pa), __dmul_rn(vp, nst));
+        const double vr = __dadd_rn(__dmul_rn(ud, nst), __dmul_rn(vp, g.cos_pa));
+        const double phi = __dadd_rn(__dmul_rn(ur, g.a_ra), __dmul_rn(vr, g.a_dec));
+        double s, c;
+        sincos(phi, &s, &c);
+        Vsky[i] = make_double2(acc * c, acc * s);
+    }
 }
 
 // far = 0: the row nearest to x (|t| <= 1/32, the gather path); far = 1: the neighbouring row on the other side
@@ -881,6 +991,79 @@ extern "C" int fb_debug_j0_far(fb_ctx *ctx, int64_t n, const double *host_x, dou
     return debug_j0_impl(ctx, n, host_x, host_out, 1);
 }
 
+// shared driver of the prediction entry points: upload I (and H2), run `launch`, grow the J0 table and repeat if the
+// kernel met arguments beyond it
+template <typename Launch>
+static int predict_driver(fb_ctx *ctx, const double *host_I, int vis_model, const double *host_H2, Launch launch)
+{
+    const int N = ctx->N;
+    const bool debris = vis_model == FB_MODEL_DEBRIS;
+    if (ctx->predI_cap < N) {
+        FB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_predI) FB_CUDA(cudaFree(ctx->d_predI));
+        ctx->d_predI = nullptr;
+        FB_CUDA(cudaMalloc(&ctx->d_predI, sizeof(double) * (N + 2)));
+        ctx->predI_cap = N;
+    }
+    unsigned long long *d_flag = (unsigned long long *)(ctx->d_predI + ctx->predI_cap);
+    if (debris) {
+        std::vector<double> h2(ctx->NC, 0.0);
+        for (int k = 0; k < N; k++) h2[k] = host_H2[k];
+        if (h2 != ctx->h_H2) {
+            FB_CUDA(cudaDeviceSynchronize());
+            FB_CUDA(cudaMemcpy(ctx->d_H2, h2.data(), sizeof(double) * ctx->NC, cudaMemcpyHostToDevice));
+            ctx->h_H2 = h2;
+        }
+    }
+    FB_CUDA(cudaMemcpyAsync(ctx->d_predI, host_I, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        FB_CUDA(cudaMemsetAsync(d_flag, 0, 16, ctx->stream));
+        launch(ctx->d_predI, debris ? ctx->d_H2 : nullptr, d_flag);
+        FB_CUDA(cudaGetLastError());
+        unsigned long long fl[2] = {0, 0};
+        FB_CUDA(cudaMemcpyAsync(fl, d_flag, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (!fl[0]) return 0;
+        double xneed;
+        memcpy(&xneed, &fl[1], 8);
+        int rc = fb_build_j0_table(ctx, xneed * 1.05);
+        if (rc) return rc;
+    }
+    FB_FAIL(-17, "fb_predict_visibilities: J0 table could not be grown to cover the data");
+}
+
+extern "C" int fb_predict_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_q, const double *dev_kz, const double *host_I,
+                                           int vis_model, double model_scale, const double *host_H2, double *dev_V)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0) FB_FAIL(-11, "fb_predict_visibilities: fb_dht_setup has not been called");
+    if (n < 0 || !dev_q || !host_I || !dev_V) FB_FAIL(-12, "fb_predict_visibilities: bad arguments");
+    if (vis_model == FB_MODEL_DEBRIS && (!host_H2 || !dev_kz)) FB_FAIL(-15, "fb_predict_visibilities: debris model needs kz and H2");
+    if (n == 0) return 0;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    return predict_driver(ctx, host_I, vis_model, host_H2, [&](const double *d_I, const double *d_H2, unsigned long long *d_flag) {
+        k_predict<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(n, ctx->N, dev_q, dev_kz, ctx->invQmax, ctx->d_jk, ctx->d_ck, d_I, d_H2,
+                                                                  model_scale, ctx->d_tab, ctx->tab_rows, dev_V, d_flag);
+    });
+}
+
+extern "C" int fb_predict_sky_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v, const fb_geometry *geom,
+                                  const double *host_I, int vis_model, double model_scale, const double *host_H2, double *dev_V_reim)
+{
+    if (!ctx) return -1;
+    if (ctx->N == 0) FB_FAIL(-11, "fb_predict_sky: fb_dht_setup has not been called");
+    if (n < 0 || !dev_u || !dev_v || !geom || !host_I || !dev_V_reim) FB_FAIL(-12, "fb_predict_sky: bad arguments");
+    if (vis_model == FB_MODEL_DEBRIS && !host_H2) FB_FAIL(-15, "fb_predict_sky: debris model needs H2");
+    if (n == 0) return 0;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    const fb_geometry g = *geom;
+    return predict_driver(ctx, host_I, vis_model, host_H2, [&](const double *d_I, const double *d_H2, unsigned long long *d_flag) {
+        k_predict_sky<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(n, ctx->N, dev_u, dev_v, g, ctx->invQmax, ctx->d_jk, ctx->d_ck, d_I, d_H2,
+                                                                      model_scale, ctx->d_tab, ctx->tab_rows, (double2 *)dev_V_reim, d_flag);
+    });
+}
+
+// host arrays: staged through the lane-0 input buffer
 extern "C" int fb_predict_visibilities(fb_ctx *ctx, int64_t n, const double *host_q, const double *host_kz, const double *host_I,
                                        int vis_model, double model_scale, const double *host_H2, double *host_V)
 {
@@ -890,35 +1073,22 @@ extern "C" int fb_predict_visibilities(fb_ctx *ctx, int64_t n, const double *hos
     if (vis_model == FB_MODEL_DEBRIS && (!host_H2 || !host_kz)) FB_FAIL(-15, "fb_predict_visibilities: debris model needs kz and H2");
     if (n == 0) return 0;
     FB_CUDA(cudaSetDevice(ctx->device));
-    const int N = ctx->N;
-    double qmax = 0.0;
-    for (int64_t i = 0; i < n; i++) qmax = host_q[i] > qmax ? host_q[i] : qmax;
-    const double xneed = qmax * ctx->invQmax * ctx->h_jk[N - 1];
-    if (fb_j0_rows_for(xneed) > ctx->tab_rows) {
-        int rc = fb_build_j0_table(ctx, xneed * 1.05);
-        if (rc) return rc;
+    FbLane &ln = ctx->lane[0];
+    const int64_t need = 3 * n + 8;
+    if (need > ln.in_cap) {
+        FB_CUDA(cudaDeviceSynchronize());
+        if (ln.d_in) FB_CUDA(cudaFree(ln.d_in));
+        ln.d_in = nullptr;
+        FB_CUDA(cudaMalloc(&ln.d_in, sizeof(double) * need));
+        ln.in_cap = need;
     }
+    double *d_q = ln.d_in, *d_kz = d_q + n, *d_V = d_kz + n;
     const bool debris = vis_model == FB_MODEL_DEBRIS;
-    double *d_q = nullptr, *d_kz = nullptr, *d_I = nullptr, *d_V = nullptr;
-    FB_CUDA(cudaMalloc(&d_q, sizeof(double) * n));
-    FB_CUDA(cudaMalloc(&d_V, sizeof(double) * n));
-    FB_CUDA(cudaMalloc(&d_I, sizeof(double) * N));
     FB_CUDA(cudaMemcpyAsync(d_q, host_q, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    FB_CUDA(cudaMemcpyAsync(d_I, host_I, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-    if (debris) {
-        FB_CUDA(cudaMalloc(&d_kz, sizeof(double) * n));
-        FB_CUDA(cudaMemcpyAsync(d_kz, host_kz, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-        std::vector<double> h2(ctx->NC, 0.0);
-        for (int k = 0; k < N; k++) h2[k] = host_H2[k];
-        FB_CUDA(cudaMemcpyAsync(ctx->d_H2, h2.data(), sizeof(double) * ctx->NC, cudaMemcpyHostToDevice, ctx->stream));
-        FB_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
-    k_predict<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(n, N, d_q, d_kz, ctx->invQmax, ctx->d_jk, ctx->d_ck, d_I,
-                                                              debris ? ctx->d_H2 : nullptr, model_scale, ctx->d_tab, ctx->tab_rows, d_V);
-    FB_CUDA(cudaGetLastError());
+    if (debris) FB_CUDA(cudaMemcpyAsync(d_kz, host_kz, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = fb_predict_visibilities_dev(ctx, n, d_q, debris ? d_kz : nullptr, host_I, vis_model, model_scale, host_H2, d_V);
+    if (rc) return rc;
     FB_CUDA(cudaMemcpyAsync(host_V, d_V, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_q); cudaFree(d_V); cudaFree(d_I);
-    if (d_kz) cudaFree(d_kz);
     return 0;
 }

@@ -21,28 +21,6 @@ namespace {
 constexpr int PREP_THREADS = 256;
 constexpr int PREP_ITEMS = 8;     // visibilities per thread -> 2048 per block
 
-__device__ __forceinline__ double hypot_glibc(double x, double y)
-{
-    double ax = fabs(x), ay = fabs(y);
-    if (ax < ay) { double t = ax; ax = ay; ay = t; }
-    // scaling branches of glibc (huge / tiny operands) are irrelevant for baselines in wavelengths
-    // (1 .. 1e9) but kept for exactness of the common-case predicate
-    if (ax >= __ddiv_rn(ay, 0x1p-54)) return __dadd_rn(ax, ay);
-    double h = __dsqrt_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
-    double t1, t2;
-    if (h <= __dmul_rn(2.0, ay)) {
-        double delta = __dsub_rn(h, ay);
-        t1 = __dmul_rn(ax, __dsub_rn(__dmul_rn(2.0, delta), ax));
-        t2 = __dmul_rn(__dsub_rn(delta, __dmul_rn(2.0, __dsub_rn(ax, ay))), delta);
-    } else {
-        double delta = __dsub_rn(h, ax);
-        t1 = __dmul_rn(__dmul_rn(2.0, delta), __dsub_rn(ax, __dmul_rn(2.0, ay)));
-        t2 = __dadd_rn(__dmul_rn(__dsub_rn(__dmul_rn(4.0, delta), ay), ay), __dmul_rn(delta, delta));
-    }
-    h = __dsub_rn(h, __ddiv_rn(__dadd_rn(t1, t2), __dmul_rn(2.0, h)));
-    return h;
-}
-
 // deterministic block reduction (fixed shuffle tree, fixed warp order)
 template <typename Op>
 __device__ __forceinline__ double block_reduce(double v, double *scratch, Op op, double ident)

@@ -4,7 +4,8 @@ API mirror of frank.geometry (frank/geometry.py:41-763).  On the fit path the pe
 GPU (frank_b200/csrc/fb_prep.cu); the NumPy helpers here serve the small host-side uses (re-projection of a handful
 of points, `undo_correction` of predicted visibilities) and define the host scalars handed to the device
 (`device_scalars`).  `FitGeometryFourierBessel` is a pure caller of the hot path: every
-residual evaluation of its Levenberg-Marquardt search is one GPU mapping + solve + GPU prediction.
+residual evaluation of its Levenberg-Marquardt search is one GPU mapping + solve + GPU prediction on visibilities that
+stay resident on the device.
 """
 import logging
 
@@ -14,7 +15,7 @@ from scipy.optimize import least_squares
 from frank_b200.constants import rad_to_arcsec, deg_to_rad
 
 __all__ = ['apply_phase_shift', 'deproject', 'rescale_total_flux', 'SourceGeometry', 'FixedGeometry',
-           'FitGeometryGaussian', 'FitGeometryFourierBessel']
+           'FitGeometryFourierBessel']
 
 
 def _is_cuda_tensor(x):
@@ -130,172 +131,104 @@ class FixedGeometry(SourceGeometry):
         return "FixedGeometry(inc={}, PA={}, dRA={}, dDEC={})".format(self.inc, self.PA, self.dRA, self.dDec)
 
 
-class FitGeometryGaussian(SourceGeometry):
-    """Determine the disc geometry by fitting a Gaussian in Fourier space (frank/geometry.py:404-620).
+class _TrialGeometryResidual(object):
+    """Weighted residual of the non-parametric fit under a trial geometry, with the visibilities resident on the GPU.
 
-    Same parameters and behaviour as the reference: `inc_pa` / `phase_centre` fix part of the geometry, `guess` is
-    [inc, PA, dRA, dDec].  Like the reference this is a host-side SciPy Levenberg-Marquardt fit of six parameters
-    (not on the GPU path: SURVEY 8f keeps it out of the hot path)."""
+    The data are uploaded once; an evaluation is a mapping call on the resident arrays (fb_map_visibilities_dev), an
+    N x N solve, one fused prediction pass (fb_predict_sky_dev: deproject, H(q) I, re-project, phase rotation) and one
+    elementwise residual; only the 2 n residual values travel back for the optimiser."""
 
-    def __init__(self, inc_pa=None, phase_centre=None, guess=None):
-        super(FitGeometryGaussian, self).__init__()
-        self._inc_pa = inc_pa
-        self._phase_centre = phase_centre
-        if guess is None:
-            guess = [10.0, 10.0, 0.0, 0.0, 1.0, 1.0]
-        else:
-            guess.extend([1.0, 1.0])
-        if self._inc_pa is not None:
-            guess[0], guess[1] = self._inc_pa
-        if self._phase_centre is not None:
-            guess[2], guess[3] = self._phase_centre
-        self._guess = guess
+    def __init__(self, Rmax, N, u, v, vis, weights, device=None):
+        import torch
+        from frank_b200 import _lib
+        ctx = _lib.get_context(device)
+        dev = torch.device('cuda', ctx.device)
+        self._Rmax, self._N, self._device = Rmax, N, ctx.device
+        self._u = torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64)).to(dev)
+        self._v = torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
+        self._vis = torch.as_tensor(np.ascontiguousarray(vis, dtype=np.complex128)).to(dev)
+        w = np.ones(len(u)) * np.asarray(weights, dtype=np.float64)
+        self._root_w = torch.as_tensor(w ** 0.5).to(dev)
+        self._w_fit = self._root_w * self._root_w           # the reference fits with sqrt(w)**2 (geometry.py:690)
+        self._host = torch.empty(2 * len(u), dtype=torch.float64).pin_memory()
+        self.evaluations = 0
 
-    def fit(self, u, v, V, weights):
-        if self._inc_pa and self._phase_centre:
-            logging.info('    You requested a Gaussian fit to determine the geometry,'
-                         ' but you provided values for inclination, PA, and the phase offset.'
-                         ' --> Using your provided values (not fitting for the geometry)')
-            self._inc, self._PA = self._inc_pa
-            self._dRA, self._dDec = self._phase_centre
-        else:
-            logging.info('    Fitting Gaussian to determine geometry')
-            inc, PA, dRA, dDec = _fit_geometry_gaussian(u, v, V, weights, guess=self._guess, inc_pa=self._inc_pa,
-                                                        phase_centre=self._phase_centre)
-            if not self._inc_pa:
-                inc, PA = _fix_inc_and_PA_ranges(inc, PA)
-            self._inc, self._PA, self._dRA, self._dDec = inc, PA, dRA, dDec
-
-
-def _fit_geometry_gaussian(u, v, V, weights, guess, inc_pa=None, phase_centre=None):
-    """Gaussian fit in uv-space by Levenberg-Marquardt (frank/geometry.py:497-626)."""
-    fac = 2 * np.pi / rad_to_arcsec
-    w = np.sqrt(weights)
-
-    if inc_pa is not None:
-        inc, PA = inc_pa
-        inc *= deg_to_rad
-        PA *= deg_to_rad
-
-    if phase_centre is not None:
-        dRA, dDec = phase_centre
-        phi = dRA * fac * u + dDec * fac * v
-        V = V * (np.cos(phi) - 1j * np.sin(phi))
-
-    guess[0] *= deg_to_rad
-    guess[1] *= deg_to_rad
-
-    def wrap(fun):
-        return np.concatenate([fun.real, fun.imag])
-
-    def _gauss_fun(params):
-        inc, PA, dRA, dDec, norm, scal = params
-        if phase_centre is None:
-            phi = dRA * fac * u + dDec * fac * v
-            Vp = V * (np.cos(phi) - 1j * np.sin(phi))
-        else:
-            Vp = V
-        c_t, s_t, c_i = np.cos(PA), np.sin(PA), np.cos(inc)
-        up = (u * c_t - v * s_t) * c_i / (scal * rad_to_arcsec)
-        vp = (u * s_t + v * c_t) / (scal * rad_to_arcsec)
-        return wrap(w * (norm * np.exp(-0.5 * (up * up + vp * vp)) - Vp))
-
-    def _gauss_jac(params):
-        inc, PA, dRA, dDec, norm, scal = params
-        jac = np.zeros([6, 2 * len(w)])
-        if phase_centre is None:
-            phi = dRA * fac * u + dDec * fac * v
-            dVp = - w * V * (-np.sin(phi) - 1j * np.cos(phi)) * fac
-            jac[2] = wrap(dVp * u)
-            jac[3] = wrap(dVp * v)
-        c_t, s_t, c_i, s_i = np.cos(PA), np.sin(PA), np.cos(inc), np.sin(inc)
-        up = (u * c_t - v * s_t)
-        vp = (u * s_t + v * c_t)
-        uv = (up * up * c_i * c_i + vp * vp)
-        G = w * np.exp(-0.5 * uv / (scal * rad_to_arcsec) ** 2)
-        norm = norm / (scal * rad_to_arcsec) ** 2
-        if inc_pa is None:
-            jac[0] = wrap(norm * G * up * up * c_i * s_i)
-            jac[1] = wrap(norm * G * up * vp * (c_i * c_i - 1) / 2)
-        jac[4] = wrap(G)
-        jac[5] = wrap(norm * G * uv / scal)
-        return jac.T
-
-    res = least_squares(_gauss_fun, guess, jac=_gauss_jac, method='lm')
-    inc, PA, dRA, dDec, _, _ = res.x
-    if inc_pa is not None:
-        inc, PA = inc_pa
-    else:
-        inc /= deg_to_rad
-        PA /= deg_to_rad
-    if phase_centre is not None:
-        dRA, dDec = phase_centre
-    return inc, PA, dRA, dDec
+    def __call__(self, inc, PA, dRA, dDec):
+        import torch
+        from frank_b200.radial_fitters import FourierBesselFitter
+        trial = FixedGeometry(inc, PA, dRA, dDec)
+        fitter = FourierBesselFitter(self._Rmax, self._N, trial, verbose=False, device=self._device)
+        model = fitter.fit(self._u, self._v, self._vis, self._w_fit).predict(self._u, self._v)
+        miss = self._root_w * (model - self._vis)
+        n = miss.numel()
+        self._host[:n].copy_(miss.real)
+        self._host[n:].copy_(miss.imag)
+        torch.cuda.current_stream(miss.device).synchronize()
+        self.evaluations += 1
+        return self._host.numpy().copy()
 
 
 class FitGeometryFourierBessel(SourceGeometry):
-    """Determine the disc geometry by minimising the chi^2 of a non-parametric Fourier-Bessel fit
+    """Determine the disc geometry by minimising the weighted chi^2 of a non-parametric Fourier-Bessel fit
     (frank/geometry.py:623-763).
 
-    Parameters as in the reference: Rmax (arcsec), N, inc_pa, phase_centre, guess, verbose.  Each residual
-    evaluation builds a `FourierBesselFitter` for the trial geometry, fits (GPU mapping + N x N solve) and predicts
-    the visibilities at the data's (u, v) (GPU); SciPy's Levenberg-Marquardt drives the search exactly as in the
-    reference (finite-difference Jacobian, `method='lm'`)."""
+    Parameters as in the reference: Rmax (arcsec), N, inc_pa, phase_centre, guess = [inc, PA, dRA, dDec], verbose;
+    `device` selects the GPU.  SciPy's Levenberg-Marquardt (`least_squares(method='lm')`, finite-difference Jacobian)
+    drives the search as in the reference; every residual evaluation runs on GPU-resident visibilities
+    (_TrialGeometryResidual).  Parameters fixed through `inc_pa` / `phase_centre` are held at the given values inside every
+    evaluation and reported back unchanged.
 
-    def __init__(self, Rmax, N, inc_pa=None, phase_centre=None, guess=None, verbose=False):
+    (frank's FitGeometryGaussian, a 6-parameter uv-plane Gaussian fit, is outside the hot path and is not provided: use
+    frank's own and pass the result in as a FixedGeometry.)"""
+
+    def __init__(self, Rmax, N, inc_pa=None, phase_centre=None, guess=None, verbose=False, device=None):
         super(FitGeometryFourierBessel, self).__init__()
-        self._N = N
-        self._R = Rmax
-        self._inc_pa = inc_pa
-        self._phase_centre = phase_centre
-        if guess is None:
-            guess = [10., 10., 0., 0.]
-        if self._inc_pa is not None:
-            guess[0], guess[1] = self._inc_pa
-        if self._phase_centre is not None:
-            guess[2], guess[3] = self._phase_centre
-        self._guess = guess
+        self._Rmax_fit, self._N_fit = Rmax, N
+        self._fixed_inc_pa = None if inc_pa is None else tuple(inc_pa)
+        self._fixed_centre = None if phase_centre is None else tuple(phase_centre)
+        start = [10., 10., 0., 0.] if guess is None else list(guess)
+        if self._fixed_inc_pa is not None:
+            start[0:2] = self._fixed_inc_pa
+        if self._fixed_centre is not None:
+            start[2:4] = self._fixed_centre
+        self._start = start
         self._verbose = verbose
+        self._device = device
+        self._nfev = 0
 
-    def _residual(self, params, uvdata=None):
-        from frank_b200.radial_fitters import FourierBesselFitter
-        inc, pa, dRA, dDec = params
-        if self._inc_pa is not None:
-            inc, pa = self._inc_pa
-        if self._phase_centre is not None:
-            dRA, dDec = self._phase_centre
-        geom = FixedGeometry(inc, pa, dRA, dDec)
-        FBF = FourierBesselFitter(self._R, self._N, geom, verbose=False)
-        u, v, vis, w_half = uvdata
-        sol = FBF.fit(u, v, vis, w_half * w_half)
-        error = w_half * (sol.predict(u, v) - vis)
-        if self._verbose:
-            Chi2 = 0.5 * np.sum(error.real ** 2 + error.imag ** 2) / len(w_half)
-            print('\n      FitGeometryFourierBessel: Iteration {}, chi^2={:.8f}, inc={:.3f} PA={:.3f} dRA={:.5f} dDec={:.5f}'
-                  ''.format(self._counter, Chi2, inc, pa, dRA, dDec), end='', flush=True)
-            self._counter += 1
-        return np.concatenate([error.real, error.imag])
+    def _pin(self, params):
+        """Trial parameters with the user-fixed ones substituted (geometry.py:679-683)."""
+        inc, PA, dRA, dDec = params
+        if self._fixed_inc_pa is not None:
+            inc, PA = self._fixed_inc_pa
+        if self._fixed_centre is not None:
+            dRA, dDec = self._fixed_centre
+        return inc, PA, dRA, dDec
 
     def fit(self, u, v, vis, w):
-        if self._inc_pa and self._phase_centre:
+        if self._fixed_inc_pa and self._fixed_centre:
             logging.info('    You requested a nonparametric fit to determine the geometry,'
                          ' but you provided values for inclination, PA, and the phase offset.'
                          ' --> Using your provided values (not fitting for the geometry)')
-            self._inc, self._PA = self._inc_pa
-            self._dRA, self._dDec = self._phase_centre
-        else:
-            logging.info('    Fitting nonparametric form to determine geometry')
-            uvdata = [u, v, vis, w ** 0.5]
-            self._counter = 0
-            result = least_squares(self._residual, self._guess, kwargs={'uvdata': uvdata}, method='lm')
-            if not result.success:
-                raise RuntimeError("FitGeometryFourierBessel failed to converge")
-            inc, pa, dRA, dDec = result.x
-            if self._inc_pa:
-                inc, pa = self._inc_pa
-            if self._phase_centre:
-                dRA, dDec = self._phase_centre
-            if not self._inc_pa:
-                inc, pa = _fix_inc_and_PA_ranges(inc, pa)
-            self._inc, self._PA, self._dRA, self._dDec = inc, pa, dRA, dDec
-            self._nfev = result.nfev
+            self._inc, self._PA = self._fixed_inc_pa
+            self._dRA, self._dDec = self._fixed_centre
+            return
+        logging.info('    Fitting nonparametric form to determine geometry')
+        residual = _TrialGeometryResidual(self._Rmax_fit, self._N_fit, u, v, vis, w, device=self._device)
+
+        def objective(params):
+            trial = self._pin(params)
+            r = residual(*trial)
+            if self._verbose:
+                print('\n      FitGeometryFourierBessel: Iteration {}, chi^2={:.8f}, inc={:.3f} PA={:.3f} dRA={:.5f} dDec={:.5f}'
+                      ''.format(residual.evaluations - 1, 0.5 * float(np.dot(r, r)) / (len(r) // 2), *trial), end='', flush=True)
+            return r
+
+        result = least_squares(objective, self._start, method='lm')
+        if not result.success:
+            raise RuntimeError("FitGeometryFourierBessel failed to converge")
+        inc, PA, dRA, dDec = self._pin(result.x)
+        if self._fixed_inc_pa is None:
+            inc, PA = _fix_inc_and_PA_ranges(inc, PA)
+        self._inc, self._PA, self._dRA, self._dDec = inc, PA, dRA, dDec
+        self._nfev = result.nfev

@@ -34,6 +34,9 @@ class FrankRadialFit(metaclass=abc.ABCMeta):
             geometry = self._geometry
         if I is None:
             I = self.I
+        if geometry is not None and hasattr(u, 'is_cuda') and u.is_cuda:
+            # device-resident baselines: deprojection, H(q) I and undo_correction fused in one pass (fb_predict_sky_dev)
+            return self._vis_map.predict_sky(I, u, v, geometry)
         if geometry is not None:
             u, v, wz = geometry.deproject(u, v, use3D=True)
         else:

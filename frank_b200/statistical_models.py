@@ -252,14 +252,27 @@ class VisibilityMapping(object):
     def predict_visibilities(self, I, q, k=None, geometry=None):
         r"""Predicted (deprojected-plane) visibilities of the profile I at baselines q
         (frank/statistical_models.py:279-329); k is the vertical uv-distance, needed by the debris model."""
-        q = np.asarray(q, dtype=np.float64)
         ctx = self._context()
+        if _is_cuda_tensor(q):                      # device-resident baselines: the result stays on the device
+            if self._vis_model == 'debris' and k is None:
+                raise ValueError("the debris model needs the vertical uv-distance k")
+            return ctx.predict_visibilities_dev(q, k if self._vis_model == 'debris' else None, I, _lib.MODEL_CODE[self._vis_model],
+                                                1.0 if self._vis_model == 'debris' else self._model_scale(geometry),
+                                                self._H2).reshape(q.shape)
+        q = np.asarray(q, dtype=np.float64)
         if self._vis_model == 'debris':
             if k is None:
                 raise ValueError("the debris model needs the vertical uv-distance k")
             return ctx.predict_visibilities(q.reshape(-1), np.asarray(k).reshape(-1), I, 2, 1.0, self._H2).reshape(q.shape)
         return ctx.predict_visibilities(q.reshape(-1), None, I, _lib.MODEL_CODE[self._vis_model],
                                         self._model_scale(geometry), None).reshape(q.shape)
+
+    def predict_sky(self, I, u, v, geometry):
+        r"""Sky-plane visibilities of the profile I at device-resident sky baselines u, v (CUDA tensors): what
+        FrankRadialFit.predict computes (frank/radial_fitters.py:56-98), in one fused device pass."""
+        ctx = self._context()
+        return ctx.predict_sky_dev(u, v, geometry.device_scalars(), I, _lib.MODEL_CODE[self._vis_model],
+                                   1.0 if self._vis_model == 'debris' else self._model_scale(geometry), self._H2).reshape(u.shape)
 
     def invert_visibilities(self, V, R, geometry=None):
         r"""Brightness at radii R / arcsec from visibilities at the collocation frequencies

@@ -262,9 +262,19 @@ int fb_uv_bin_dev(fb_ctx *ctx, int64_t n, const double *dev_uv, const double *de
 
 /* ---- VisibilityMapping.predict_visibilities (frank/statistical_models.py:279-329) ---------------------------
  * V_i = sum_k H_ik I_k with the same design rows as the mapping; q [n] deprojected baselines, kz [n] (debris model
- * only), I [N] brightness at the collocation points, V [n] out. */
+ * only), I [N] brightness at the collocation points (host), V [n] out.  The J0 table grows by itself when q reaches beyond it.
+ *   fb_predict_visibilities      host arrays
+ *   fb_predict_visibilities_dev  q, kz, V resident on the device
+ *   fb_predict_sky_dev           FrankRadialFit.predict (frank/radial_fitters.py:56-98) in one pass over device-resident
+ *                                SKY-plane baselines u, v [n]: deproject (geometry.py:111-131), q = hypot, H(q) I, then
+ *                                undo_correction (geometry.py:239-265: re-project, rotate the phase); V_reim [2n] interleaved
+ *                                complex out.  The inner loop of FitGeometryFourierBessel (geometry.py:678-703). */
 int fb_predict_visibilities(fb_ctx *ctx, int64_t n, const double *host_q, const double *host_kz, const double *host_I,
                             int vis_model, double model_scale, const double *host_H2, double *host_V);
+int fb_predict_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_q, const double *dev_kz, const double *host_I,
+                                int vis_model, double model_scale, const double *host_H2, double *dev_V);
+int fb_predict_sky_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v, const fb_geometry *geom,
+                       const double *host_I, int vis_model, double model_scale, const double *host_H2, double *dev_V_reim);
 
 /* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]).
  * fb_debug_j0 uses the table row nearest to x (the per-visibility gather path); fb_debug_j0_far uses the

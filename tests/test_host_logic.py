@@ -102,19 +102,3 @@ def test_j0_table_accuracy(tmp_path):
     # (half an ulp of the value itself is 1.1e-16 / 5.6e-17 / 2.8e-17 / 1.4e-17 at the top of these ranges)
     assert near[0] <= 1.2e-16 and near[1] <= 7e-17 and near[2] <= 3.5e-17 and near[3] <= 1.5e-17
     assert far[0] <= 1.3e-16 and far[1] <= 7e-17 and far[2] <= 3.5e-17 and far[3] <= 1.5e-17
-
-
-def test_fit_geometry_gaussian(golden):
-    """FitGeometryGaussian (frank/geometry.py:404-626) is host-side SciPy in the reference and here: same numbers."""
-    from frank_b200.geometry import FitGeometryGaussian
-    g = golden('geomfit.npz')
-    u, v, V, w = g['u'], g['v'], g['V'], g['w']
-    gg = FitGeometryGaussian()
-    gg.fit(u, v, V, w)
-    assert np.allclose([gg.inc, gg.PA, gg.dRA, gg.dDec], g['gauss'], rtol=1e-9, atol=1e-12)
-    gg2 = FitGeometryGaussian(phase_centre=(0.021, -0.034), guess=[20., 60., 0., 0.])
-    gg2.fit(u, v, V, w)
-    assert np.allclose([gg2.inc, gg2.PA, gg2.dRA, gg2.dDec], g['gauss_fixed_centre'], rtol=1e-9, atol=1e-12)
-    both = FitGeometryGaussian(inc_pa=(30., 40.), phase_centre=(0.0, 0.1))
-    both.fit(u, v, V, w)
-    assert (both.inc, both.PA, both.dRA, both.dDec) == (30., 40., 0.0, 0.1)
