@@ -114,7 +114,8 @@ constexpr int SMB_JK = SMB_CEN + 2 * GCOLS * 16;           // [GCOLS] ints (+ pa
 constexpr int SMB_H2 = SMB_JK + GCOLS * 8;                 // [GCOLS] doubles           debris H2_k
 constexpr int SMB_VIS = SMB_H2 + GCOLS * 8;                // [2][GS][4] doubles        (a, sqrt w, kz, sqrt w Re V) per visibility of a tile
 constexpr int SMB_AR = SMB_VIS + 2 * GS * 32;               // [2] double2               (min a, max a) of the tiles being staged
-constexpr int GRAM_SMEM_BYTES = SMB_AR + 32;
+constexpr int SMB_SW = SMB_AR + 32;                        // [2][GS] doubles           sqrt w, compact (conflict-free re-reads of the half-warp sweep)
+constexpr int GRAM_SMEM_BYTES = SMB_SW + 2 * GS * 8;
 
 __host__ __device__ __forceinline__ int split4_size(int n, int i) { return n / 4 + (i < n % 4 ? 1 : 0); }
 __host__ __device__ __forceinline__ int split4_start(int n, int i) { return i * (n / 4) + (i < n % 4 ? i : n % 4); }
@@ -215,6 +216,7 @@ __device__ __forceinline__ void j0_columns4(const GramArgs &p, const uint32_t sb
 {
     const int l16 = lane & 15, half = lane >> 4;
     const uint32_t s_vis = sbase + SMB_VIS + buf * (GS * 32);
+    const uint32_t s_sw = sbase + SMB_SW + buf * (GS * 8);
     double av[4], kk[4];             // a of this lane's four visibilities (sqrt w is re-read at the store: registers)
 #pragma unroll
     for (int m = 0; m < 4; m++) {
@@ -258,8 +260,8 @@ __device__ __forceinline__ void j0_columns4(const GramArgs &p, const uint32_t sb
                 g1 *= exp_neg(kk[2 * h + 1] * h2);
             }
             if (plain || gather) {                                       // the data column and the padding are written elsewhere
-                sts_f64(a_g + 32 * h * 8, g0 * lds_f64(s_vis + (l16 + 32 * h) * 32 + 8));
-                sts_f64(a_g + (32 * h + 16) * 8, g1 * lds_f64(s_vis + (l16 + 32 * h + 16) * 32 + 8));
+                sts_f64(a_g + 32 * h * 8, g0 * lds_f64(s_sw + (l16 + 32 * h) * 8));
+                sts_f64(a_g + (32 * h + 16) * 8, g1 * lds_f64(s_sw + (l16 + 32 * h + 16) * 8));
             }
         }
         a_row += 2 * NW * 16; a_cen += 2 * NW * 16; a_g += 2 * NW * GLD * 8;
@@ -372,6 +374,9 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
             const uint32_t d = sbase + SMB_VIS + buf * (GS * 32) + tid * 32;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(p.a + v) : "memory");
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8), "l"(p.sw + v) : "memory");
+#ifdef FB_J0_HALFWARP
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + SMB_SW + (buf * GS + tid) * 8), "l"(p.sw + v) : "memory");
+#endif
             if (DEBRIS) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 16), "l"(p.kz + v) : "memory");
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 24), "l"(p.swV + v) : "memory");
         }

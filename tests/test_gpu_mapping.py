@@ -285,7 +285,8 @@ def test_config1_mapping_and_fit_vs_reference_golden(fb, golden):
     print(f"\nconfig1 M: strict per-entry {e_entry:.3e} (reference vs itself {float(g['self_noise_M_entry']):.3e}), "
           f"/sqrt(MkkMll) {e_cs:.3e} ({float(g['self_noise_M_cs']):.3e}), max-norm {e_max:.3e} ({float(g['self_noise_M_max']):.3e})")
     assert gram_ok(FF._M, g['M']) <= 1.0
-    assert e_cs <= 16 * EPS and e_max <= 2e-14
+    # closer to the reference than the reference is to itself under a permutation of its visibilities
+    assert e_cs <= float(g['self_noise_M_cs']) and e_cs <= 64 * EPS and e_max <= 2e-14
     assert np.max(np.abs(FF._j - g['j'])) <= 1e-12 * np.max(np.abs(g['j']))
     assert abs(FF._H0 - float(g['H0'])) <= 1e-12 * abs(float(g['H0']))
     assert FF.iteration_diagnostics['num_iterations'] == int(g['num_iterations'])
