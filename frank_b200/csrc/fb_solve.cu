@@ -685,13 +685,14 @@ k_trsm_tr2_blocked(int N, int nb, const double *__restrict__ U_all, const double
 // block update done by all threads.
 __global__ void __launch_bounds__(1024)
 k_solve_mu(int N, int PR, const double *__restrict__ U_all, const double *__restrict__ rdiag_all, const double *__restrict__ jvec,
-           int j_stride, const int *__restrict__ active, double *__restrict__ mu_all)
+           int j_stride, const int *__restrict__ active, double *__restrict__ mu_all, int shared_factor = 0)
 {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
-    const double *U = U_all + (size_t)b * N * N;
+    const size_t ub = shared_factor ? 0 : b;                // shared_factor: every CTA solves with factor 0 (many right-hand sides)
+    const double *U = U_all + ub * N * N;
     extern __shared__ double shm[];
-    const double *rdiag = rdiag_all + (size_t)b * N;
+    const double *rdiag = rdiag_all + ub * N;
     double *x = shm;                       // [N]  right-hand side / solution
     double *zp = shm + N;                  // [32] panel solution
     double *S = shm + N + 32;              // [PR][N] panel of U rows
@@ -1259,12 +1260,11 @@ static int launch_solve_rhs(fb_ctx *ctx, int B, const int *d_active, cudaStream_
         FB_CUDA(cudaGetLastError());
         return 0;
     }
-    if (shared_factor) FB_FAIL(-34, "fb_chol_solve: N > 512 is not supported on the device");
     int PR = 32;
     while (PR > 1 && sizeof(double) * ((size_t)N + 32 + (size_t)PR * N) > 200 * 1024) PR /= 2;
     const size_t smem = sizeof(double) * ((size_t)N + 32 + (size_t)PR * N);
     FB_CUDA(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve_mu<<<B, 1024, smem, stream>>>(N, PR, ctx->sv_D, ctx->sv_rdiag, rhs, rhs_stride, d_active, out);
+    k_solve_mu<<<B, 1024, smem, stream>>>(N, PR, ctx->sv_D, ctx->sv_rdiag, rhs, rhs_stride, d_active, out, shared_factor);
     FB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1413,7 +1413,6 @@ int fb_chol_solve(fb_ctx *ctx, const double *host_U, int nrhs, const double *hos
     if (!host_U || !host_B || !host_X || nrhs < 1) FB_FAIL(-31, "fb_chol_solve: bad arguments");
     FB_CUDA(cudaSetDevice(ctx->device));
     const size_t N = ctx->N;
-    if (N > 512) FB_FAIL(-34, "fb_chol_solve: N > 512 is not supported on the device");
     int rc = ensure_solver_ws(ctx, 1);
     if (rc) return rc;
     std::vector<double> rd(N);
@@ -1786,6 +1785,7 @@ int fb_ln_setup(fb_ctx *ctx, const double *host_M, const double *host_j, double 
 int fb_ln_set_spectrum(fb_ctx *ctx, const double *host_p)
 {
     if (!ctx || !ctx->ln_S) return -1;
+    if (ctx->ln_N != ctx->N) FB_FAIL(-38, "fb_ln_set_spectrum: fb_ln_setup has not been called for the current transform size");
     FB_CUDA(cudaSetDevice(ctx->device));
     const size_t N = ctx->N;
     for (size_t i = 0; i < N; i++)
@@ -1816,6 +1816,7 @@ static int ln_eval_device(fb_ctx *ctx, const double *host_s)
 int fb_ln_eval(fb_ctx *ctx, const double *host_s, double *host_f, double *host_g)
 {
     if (!ctx || !ctx->ln_S || !host_s || !host_f) return -1;
+    if (ctx->ln_N != ctx->N) FB_FAIL(-38, "fb_ln_eval: fb_ln_setup has not been called for the current transform size");
     FB_CUDA(cudaSetDevice(ctx->device));
     int rc = ln_eval_device(ctx, host_s);
     if (rc) return rc;
@@ -1832,6 +1833,7 @@ int fb_ln_eval(fb_ctx *ctx, const double *host_s, double *host_f, double *host_g
 int fb_ln_newton_direction(fb_ctx *ctx, const double *host_s, int refactor, double *host_g, double *host_dx, int *host_info)
 {
     if (!ctx || !ctx->ln_S || !host_s || !host_dx) return -1;
+    if (ctx->ln_N != ctx->N) FB_FAIL(-38, "fb_ln_newton_direction: fb_ln_setup has not been called for the current transform size");
     FB_CUDA(cudaSetDevice(ctx->device));
     const size_t N = ctx->N;
     int rc = ln_eval_device(ctx, host_s);

@@ -131,7 +131,6 @@ class CriticalFilter(object):
 
     def covariance_MAP(self, fit, ret_inv=False):
         """Covariance of the power spectrum at maximum likelihood (frank/filter.py:184-227); post-fit helper."""
-        import scipy.linalg
         Ykm = self._DHT.coefficients()
         mq = np.dot(Ykm, fit.MAP)
         mqq = np.outer(mq, mq)
@@ -141,7 +140,13 @@ class CriticalFilter(object):
             - 0.5 * np.outer(1 / p, 1 / p) * (2 * mqq + Dqq) * Dqq
         if ret_inv:
             return hess
-        return scipy.linalg.cho_solve(scipy.linalg.cho_factor(hess), np.eye(self._DHT.size))
+        # inverse through a device Cholesky factorisation (fb_gaussian_fit without a prior) and N device solves
+        ctx = _lib.get_context(getattr(fit, '_device', None))
+        ctx.dht_setup(self._DHT)
+        _, chol, _, rc = ctx.gaussian_fit(hess, np.zeros(self._DHT.size), None)
+        if rc == _lib.FB_E_NOTPD:
+            raise np.linalg.LinAlgError("covariance_MAP: the Hessian of the power-spectrum posterior is not positive definite")
+        return ctx.chol_solve(np.triu(chol[0]), np.eye(self._DHT.size))
 
     def log_prior(self, p):
         """log P(p) up to a constant (frank/filter.py:229-263)."""

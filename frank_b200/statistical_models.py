@@ -16,8 +16,8 @@ from frank_b200.constants import rad_to_arcsec, deg_to_rad
 __all__ = ['VisibilityMapping', 'GaussianModel', 'LogNormalMAPModel']
 
 
-# Dsolve through fb_chol_solve (device; N <= 512) rather than SciPy on the GPU-computed factor; FRANK_B200_DEVICE_DSOLVE=0
-# selects the SciPy helper
+# Dsolve through fb_chol_solve (device) rather than SciPy on the GPU-computed factor; FRANK_B200_DEVICE_DSOLVE=0 selects the
+# SciPy helper (diagnostics)
 _DEVICE_DSOLVE = os.environ.get('FRANK_B200_DEVICE_DSOLVE', '1') == '1'
 
 
@@ -415,7 +415,7 @@ class GaussianModel(object):
             U, s1, V = self._Dsvd
             b = np.asarray(b)
             return np.dot(V.T, (np.dot(U.T, b).T * s1).T)
-        if _DEVICE_DSOLVE and self._DHT.size <= 512:
+        if _DEVICE_DSOLVE:
             ctx = _lib.get_context(self._device)
             ctx.dht_setup(self._DHT)
             return ctx.chol_solve(self._U, b)
@@ -543,6 +543,10 @@ class LogNormalMAPModel(object):
         return p_new
 
     def Dsolve(self, b):
+        r"""(Hessian at the MAP)^-1 b through its GPU-computed Cholesky factor (statistical_models.py:1160-1170)."""
+        if _DEVICE_DSOLVE:
+            self._ctx.dht_setup(self._DHT)
+            return self._ctx.chol_solve(self._U, b)
         import scipy.linalg
         return scipy.linalg.cho_solve((self._U, False), b)
 

@@ -174,7 +174,8 @@ int fb_gaussian_fit(fb_ctx *ctx, int B, const double *host_M, const double *host
 
 /* GaussianModel.Dsolve (frank/statistical_models.py:762-781, the Cholesky branch): X = (U^T U)^-1 B for nrhs right-hand sides
  * with the upper factor U [N*N] returned by fb_gaussian_fit / fb_frank_normal_loop.  B and X are [nrhs * N], one right-hand
- * side per row (host).  N <= 512.  Used for the posterior covariance (Dsolve of the identity) and the Laplace evidence. */
+ * side per row (host); one CTA per right-hand side (register-resident sweeps for N <= 512, shared-memory panels above).
+ * Used for the posterior covariance (Dsolve of the identity), covariance_MAP and the Laplace evidence. */
 int fb_chol_solve(fb_ctx *ctx, const double *host_U, int nrhs, const double *host_B, double *host_X);
 
 /* SVD fallback of GaussianModel._fit (frank/statistical_models.py:747-755: scipy.linalg.svd(Dinv) when cho_factor
