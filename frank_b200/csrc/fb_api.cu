@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 extern "C" {
 
@@ -37,6 +38,11 @@ int fb_ctx_create(fb_ctx **out, int device)
         cudaMalloc(&ctx->d_result, sizeof(double) * 8) != cudaSuccess || cudaMalloc(&ctx->d_status, sizeof(int) * 4) != cudaSuccess ||
         cudaHostAlloc(&ctx->h_result, sizeof(double) * 8, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return -9; }
     cudaMemset(ctx->d_status, 0, sizeof(int) * 4);
+    {   // host threads for the staging gather: at most 8, and a fair share of the cores when several ranks share the host
+        int share = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) share /= std::max(1, atoi(e));
+        ctx->stage_threads = std::max(1, std::min(8, share));
+    }
     if (const char *e = getenv("FB_STAGE_THREADS")) ctx->stage_threads = std::max(1, atoi(e));
     if (const char *e = getenv("FB_MAP_CHUNK")) ctx->map_chunk = std::max<int64_t>(FB_TV, (int64_t)atof(e));
     if (const char *e = getenv("FB_MAP_GROWTH")) ctx->map_growth = std::max(1.0, atof(e));
