@@ -45,7 +45,7 @@ int fb_ctx_create(fb_ctx **out, int device)
     }
     if (const char *e = getenv("FB_STAGE_THREADS")) ctx->stage_threads = std::max(1, atoi(e));
     if (const char *e = getenv("FB_MAP_CHUNK")) ctx->map_chunk = std::max<int64_t>(FB_TV, (int64_t)atof(e));
-    if (const char *e = getenv("FB_MAP_GROWTH")) ctx->map_growth = std::max(1.0, atof(e));
+    if (const char *e = getenv("FB_MAP_GROWTH")) ctx->map_growth = atof(e) < 1.0 ? 0.0 : atof(e);
     if (const char *e = getenv("FB_MAP_KMAX")) ctx->map_kmax = std::max(1, atoi(e));
     *out = ctx;
     return 0;
@@ -98,7 +98,7 @@ int fb_set_option(fb_ctx *ctx, const char *name, double value)
     if (!ctx || !name) return -1;
     const std::string k(name);
     if (k == "map_chunk") { ctx->map_chunk = std::max<int64_t>(FB_TV, (int64_t)value); return 0; }
-    if (k == "map_growth") { ctx->map_growth = std::max(1.0, value); return 0; }
+    if (k == "map_growth") { ctx->map_growth = value < 1.0 ? 0.0 : value; return 0; }      // 0: adaptive
     if (k == "map_kmax") { ctx->map_kmax = std::max(1, (int)value); return 0; }
     if (k == "force_staging") { ctx->force_staging = value != 0.0; return 0; }
     if (k == "stage_threads") { ctx->stage_threads = std::max(1, (int)value); return 0; }
@@ -412,7 +412,15 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
     int K = 1;
     std::vector<int64_t> csize(1, n);
     if (n >= 2 * ctx->map_chunk) {
-        const double r = std::max(1.0, ctx->map_growth);
+        // growth: the configured factor, or (map_growth = 0, the default) what the rates measured on the previous call
+        // allow -- a chunk's copy has to fit under its predecessor's kernels: ratio <= 0.85 x (kernel time per visibility) /
+        // (copy or staging time per visibility), between 1.25 and 3; 2 before anything has been measured
+        double r = ctx->map_growth;
+        if (!(r >= 1.0)) {
+            r = 2.0;
+            if (ctx->rate_copy_ns > 0.0 && ctx->rate_gram_ns > 0.0 && ctx->rate_N == ctx->N)
+                r = std::min(3.0, std::max(1.25, 0.85 * ctx->rate_gram_ns / ctx->rate_copy_ns));
+        }
         K = std::max(1, std::min(ctx->map_kmax, FB_MAX_CHUNKS));
         auto first = [&](int k) { return r == 1.0 ? (double)n / k : (double)n * (r - 1.0) / (std::pow(r, k) - 1.0); };
         while (K > 1 && first(K) < (double)ctx->map_chunk) K--;
@@ -431,7 +439,20 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
     }
     const bool pinned = ctx->force_staging ? false : n == 0 || (is_pinned(host_u) && is_pinned(host_v) && is_pinned(host_V_reim) && (!w_stride || is_pinned(host_w)) &&
                                    (!host_chan || is_pinned(host_chan)));
-    // staging layout of a lane's slot (doubles), L = the lane's largest chunk: u [L] | v [L] | V [2 L] | w [L or 1] | chan [L / 2 + 1]
+    // Device staging holds the WHOLE call: u [n] | v [n] | V [2 n] | w [n or 1] | chan [n / 2 + 1], so the copy stream never waits
+    // for a slot to be consumed -- copies run back to back from the first byte, whatever the kernels are doing.  Pageable
+    // inputs pass through a ring of two pinned slots (one per lane, sized for the lane's largest chunk).
+    const int64_t D_v = n, D_V = 2 * n, D_w = 4 * n, D_c = 5 * n, d_need = 5 * n + n / 2 + 8;
+    {
+        FbLane &l0 = ctx->lane[0];
+        if (d_need > l0.in_cap) {
+            FB_CUDA(cudaDeviceSynchronize());
+            if (l0.d_in) FB_CUDA(cudaFree(l0.d_in));
+            l0.d_in = nullptr;
+            FB_CUDA(cudaMalloc(&l0.d_in, sizeof(double) * d_need));
+            l0.in_cap = d_need;
+        }
+    }
     for (int l = 0; l < (K > 1 ? 2 : 1); l++) {
         FbLane &ln = ctx->lane[l];
         const int64_t L = l ? cs2 : cs, slot = 5 * L + L / 2 + 8;
@@ -439,14 +460,6 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
         if (rc) return rc;
         rc = reserve_partials(ctx, ln, nchan);
         if (rc) return rc;
-        if (slot > ln.in_cap) {
-            FB_CUDA(cudaStreamSynchronize(ln.stream));
-            FB_CUDA(cudaStreamSynchronize(ctx->stream_copy));
-            if (ln.d_in) FB_CUDA(cudaFree(ln.d_in));
-            ln.d_in = nullptr;
-            FB_CUDA(cudaMalloc(&ln.d_in, sizeof(double) * slot));
-            ln.in_cap = slot;
-        }
         if (!pinned && slot > ln.pin_cap) {
             FB_CUDA(cudaStreamSynchronize(ctx->stream_copy));
             if (ln.h_pin) FB_CUDA(cudaFreeHost(ln.h_pin));
@@ -471,17 +484,18 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
         for (int k = 0; k < K; off += csize[k], k++) {
             FbLane &ln = ctx->lane[k & 1];
             const int64_t cnt = csize[k], L = (k & 1) ? cs2 : cs;
-            const int64_t off_v = L, off_V = 2 * L, off_w = 4 * L, off_c = 5 * L;
-            double *d = ln.d_in;
+            const int64_t off_v = L, off_V = 2 * L, off_w = 4 * L, off_c = 5 * L;      // layout of the lane's pinned slot
+            double *dbase = ctx->lane[0].d_in;
+            double *d_u = dbase + off, *d_v = dbase + D_v + off, *d_V = dbase + D_V + 2 * off, *d_w = dbase + D_w + (w_stride ? off : 0);
+            int32_t *d_c = (int32_t *)(dbase + D_c) + off;
             cudaStream_t sc = ctx->stream_copy;
-            if (k >= 2) FB_CUDA(cudaStreamWaitEvent(sc, ln.ev_done, 0));                   // chunk k - 2 has consumed the device slot
             if (pinned) {
-                FB_CUDA(cudaMemcpyAsync(d, host_u + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
-                FB_CUDA(cudaMemcpyAsync(d + off_v, host_v + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
-                FB_CUDA(cudaMemcpyAsync(d + off_V, host_V_reim + 2 * off, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, sc));
-                if (w_stride) FB_CUDA(cudaMemcpyAsync(d + off_w, host_w + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
-                else if (k < 2) FB_CUDA(cudaMemcpyAsync(d + off_w, host_w, sizeof(double), cudaMemcpyHostToDevice, sc));
-                if (host_chan) FB_CUDA(cudaMemcpyAsync(d + off_c, host_chan + off, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, sc));
+                FB_CUDA(cudaMemcpyAsync(d_u, host_u + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
+                FB_CUDA(cudaMemcpyAsync(d_v, host_v + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
+                FB_CUDA(cudaMemcpyAsync(d_V, host_V_reim + 2 * off, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, sc));
+                if (w_stride) FB_CUDA(cudaMemcpyAsync(d_w, host_w + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
+                else if (k == 0) FB_CUDA(cudaMemcpyAsync(d_w, host_w, sizeof(double), cudaMemcpyHostToDevice, sc));
+                if (host_chan) FB_CUDA(cudaMemcpyAsync(d_c, host_chan + off, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, sc));
             } else {
                 if (k >= 2) FB_CUDA(cudaEventSynchronize(ln.ev_copied));                   // the pinned slot has left for the device
                 double *h = ln.h_pin;
@@ -494,17 +508,15 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
                 else h[off_w] = host_w[0];
                 if (host_chan) pc[np++] = {h + off_c, host_chan + off, sizeof(int32_t) * (size_t)cnt};
                 parallel_gather(pc, np, ctx->stage_threads);
-                // one transfer per array (the slot is laid out for the lane's LARGEST chunk: the arrays are not adjacent)
-                FB_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
-                FB_CUDA(cudaMemcpyAsync(d + off_v, h + off_v, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
-                FB_CUDA(cudaMemcpyAsync(d + off_V, h + off_V, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, sc));
-                FB_CUDA(cudaMemcpyAsync(d + off_w, h + off_w, sizeof(double) * (w_stride ? cnt : 1), cudaMemcpyHostToDevice, sc));
-                if (host_chan) FB_CUDA(cudaMemcpyAsync(d + off_c, h + off_c, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, sc));
+                FB_CUDA(cudaMemcpyAsync(d_u, h, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
+                FB_CUDA(cudaMemcpyAsync(d_v, h + off_v, sizeof(double) * cnt, cudaMemcpyHostToDevice, sc));
+                FB_CUDA(cudaMemcpyAsync(d_V, h + off_V, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, sc));
+                if (w_stride || k == 0) FB_CUDA(cudaMemcpyAsync(d_w, h + off_w, sizeof(double) * (w_stride ? cnt : 1), cudaMemcpyHostToDevice, sc));
+                if (host_chan) FB_CUDA(cudaMemcpyAsync(d_c, h + off_c, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, sc));
             }
             FB_CUDA(cudaEventRecord(ln.ev_copied, sc));
             FB_CUDA(cudaStreamWaitEvent(ln.stream, ln.ev_copied, 0));
-            rc = enqueue_chunk(ctx, ln, k, cnt, d, d + off_v, d + off_V, d + off_w, w_stride,
-                               host_chan ? (const int32_t *)(d + off_c) : nullptr, job, prev);
+            rc = enqueue_chunk(ctx, ln, k, cnt, d_u, d_v, d_V, d_w, w_stride, host_chan ? d_c : nullptr, job, prev);
             if (rc) { cudaDeviceSynchronize(); return rc; }
             prev = &ln;
         }
@@ -523,6 +535,11 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
         cudaEventElapsedTime(&copy_ms, ev_c0, ev_c1);
         collect_timing(ctx, K, copy_ms);
         ctx->map_chunks = K;
+        if (n >= 2 * ctx->map_chunk && copy_ms > 0.f) {           // arrival and kernel rates of this call steer the next call's chunking
+            ctx->rate_copy_ns = 1e6 * (double)copy_ms / (double)n;
+            ctx->rate_gram_ns = 1e6 * (ctx->timing[0] + ctx->timing[1]) / (double)n;
+            ctx->rate_N = ctx->N;
+        }
         rc = map_status(ctx, host_qminmax);
         if (rc == 0) *host_H0 = ctx->h_result[0];
         if (rc != FB_E_RETRY) return rc;

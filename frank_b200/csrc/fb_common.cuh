@@ -112,9 +112,11 @@ struct fb_ctx {
     std::vector<double> h_H2;      // debris H2 currently on the device
     int stage_threads = 8;         // host threads gathering pageable inputs into the pinned staging ring
     int64_t map_chunk = 250000;    // smallest first chunk of the host entry point's pipeline (visibilities)
-    double map_growth = 2.0;       // ratio of consecutive chunk sizes (2: the copy of a chunk needs half the H2D rate its
-                                   // predecessor's kernels could absorb, so eight ranks sharing one host stay in step)
-    int map_kmax = 4;              // most chunks per call
+    double map_growth = 1.5;       // ratio of consecutive chunk sizes (fixed: a given n always gives the same chunks, hence the same
+                                   // bits); 0 = adapt to the copy / kernel rates measured on the previous call
+    double rate_copy_ns = 0.0, rate_gram_ns = 0.0;      // ns per visibility measured on the previous host call, for N = rate_N
+    int rate_N = 0;
+    int map_kmax = 8;              // most chunks per call
     bool force_staging = false;    // treat every host input as pageable (tests)
     // multi-GPU: NCCL communicator attached by fb_comm_init (library loaded with dlopen)
     void *nccl_lib = nullptr;

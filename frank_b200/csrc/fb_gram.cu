@@ -275,7 +275,8 @@ struct ItemCtx {
     uint32_t sbase;
     const double *G;       // generic pointer to the G stages
     int r0, c0, ncolA, nmod, ncol;
-    long long q0;
+    long long q0;          // first tile of the item; its tiles are q0, q0 + qs, q0 + 2 qs, ...
+    int qs;
     int nst;
     int ld;
     double *out;
@@ -397,12 +398,12 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
 #endif
     };
 
-    const long long q0 = it.q0;
+    const long long q0 = it.q0, qs = it.qs;
     const int nst = it.nst;
     // ---- prologue: rows and scalars of the first tile, range of the second --------------------------------------
     stage_math(p.arange[q0], 0);
     __syncthreads();
-    stage_copy(0, q0, nst > 1 ? q0 + 1 : -1);
+    stage_copy(0, q0, nst > 1 ? q0 + qs : -1);
     // ---- main loop: J0 phase, DMMA phase ------------------------------------------------------------------------
     long long t_j0 = 0, t_mma = 0, t_last = clock64();
     for (int s = 0; s < nst; s++) {
@@ -414,7 +415,7 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
         if (s + 1 < nst) stage_math(lds_v2f64(sbase + SMB_AR + (b ^ 1) * 16), b ^ 1);
         __syncthreads();
         if (p.prof && tid == 0) { const long long t = clock64(); t_j0 += t - t_last; t_last = t; }
-        if (s + 1 < nst) stage_copy(b ^ 1, q0 + s + 1, s + 2 < nst ? q0 + s + 2 : -1);     // flies during the DMMAs
+        if (s + 1 < nst) stage_copy(b ^ 1, q0 + (s + 1) * qs, s + 2 < nst ? q0 + (s + 2) * qs : -1);     // flies during the DMMAs
         stage_dmma<KIND, NR, NC>(acc, it.G, fr0, fr1, ta, tb, cbase, it.nmod);
     }
     if (p.prof && tid == 0) {
@@ -460,13 +461,17 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
         const int type = p.items[3 * k], chunk = p.items[3 * k + 1], slot_out = p.items[3 * k + 2];
         const int Ct = p.type_tab[2 * type];
         const FbGramType ty = p.types[type];
-        const long long q0 = tile0 + (n_tiles * chunk) / Ct, q1 = tile0 + (n_tiles * (chunk + 1)) / Ct;
-        if (q0 >= q1) continue;
+        // Chunk c of a type takes the tiles c, c + Ct, c + 2 Ct, ... of the channel's run: every item sees the same mix of
+        // dense (long-baseline) and sparse (short-baseline: per-visibility gather path) tiles, so the items of a launch cost
+        // the same whatever the baseline distribution -- contiguous ranges left the items holding a type's first tiles up to
+        // twice as slow as the rest, a tail the host's cost model cannot see.
+        if (chunk >= n_tiles) continue;
         ItemCtx it;
         it.sbase = sbase;
         it.G = reinterpret_cast<const double *>(smem_raw + SMB_G);
-        it.q0 = q0;
-        it.nst = (int)(q1 - q0);
+        it.q0 = tile0 + chunk;
+        it.qs = Ct;
+        it.nst = (int)((n_tiles - chunk + Ct - 1) / Ct);
         it.ncolA = ty.a_nt * 8;
         it.ncol = (ty.a_nt + ty.b_nt) * 8;
         it.ld = ty.ld;
@@ -565,10 +570,7 @@ k_gram_accumulate(int NT, int P, int npairs, int n_items, const int *__restrict_
     const double *part = partial + (size_t)chan * n_items * FB_PSZ;
     double s = 0.0;
     const int Ct = type_tab[2 * type], first_slot = type_tab[2 * type + 1];
-    for (int c = 0; c < Ct; c++) {
-        const long long q0 = (n_tiles * c) / Ct, q1 = (n_tiles * (c + 1)) / Ct;
-        if (q1 > q0) s += part[(size_t)(first_slot + c) * FB_PSZ + idx];
-    }
+    for (int c = 0; c < Ct && c < n_tiles; c++) s += part[(size_t)(first_slot + c) * FB_PSZ + idx];      // chunk c is empty when c >= n_tiles
     double *out = S + ((size_t)chan * npairs + blockIdx.x) * 64 + threadIdx.x;
     *out = first ? s : *out + s;
 }

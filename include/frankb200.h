@@ -54,9 +54,13 @@ int fb_ctx_create(fb_ctx **ctx, int device);
 int fb_ctx_destroy(fb_ctx *ctx);
 const char *fb_last_error(fb_ctx *ctx);
 int fb_version(void);
-/* Tuning knobs (also read from the environment at fb_ctx_create): "map_chunk" = visibilities per chunk of the host
- * entry point's copy / compute pipeline (FB_MAP_CHUNK, default 1.25e6), "stage_threads" = host threads that gather
- * pageable inputs into the pinned staging ring (FB_STAGE_THREADS, default 4). */
+/* Tuning knobs of the host entry point's copy / compute pipeline (also read from the environment at fb_ctx_create):
+ * "map_chunk" = smallest first chunk in visibilities (FB_MAP_CHUNK, default 2.5e5), "map_growth" = ratio of consecutive
+ * chunk sizes (FB_MAP_GROWTH, default 1.5; 0 adapts it to the copy and kernel rates measured on the previous call, at the
+ * price of call-to-call bit-reproducibility),
+ * "map_kmax" = most chunks per call (FB_MAP_KMAX, default 8), "stage_threads" = host threads that gather pageable
+ * inputs into the pinned staging ring (FB_STAGE_THREADS, default min(8, cores / LOCAL_WORLD_SIZE)), "force_staging" = treat
+ * pinned inputs as pageable (tests). */
 int fb_set_option(fb_ctx *ctx, const char *name, double value);
 
 /* ---- DiscreteHankelTransform tables (frank/hankel.py:55-93) ---------------------------------
@@ -99,10 +103,11 @@ int fb_dht_setup(fb_ctx *ctx, int N, double Qmax, const double *host_j_nk, const
  *                                live on the device), so it can be overlapped with other work or followed by further
  *                                stream-ordered work of the library; fb_map_sync waits and returns the status
  *                                (0, FB_E_QRANGE, or FB_E_RETRY) and qminmax.
- * fb_map_visibilities_host       host arrays (pinned or pageable): a K-deep chunk pipeline (chunks of FB_MAP_CHUNK
- *                                = 1.25e6 visibilities by default) copies chunk k+1 while chunk k is in the kernels;
- *                                pageable inputs are gathered into a pinned staging ring by FB_STAGE_THREADS (4) host
- *                                threads first.  Chunks are summed in order: deterministic for a given n. */
+ * fb_map_visibilities_host       host arrays (pinned or pageable): a K-deep chunk pipeline (chunks of geometrically
+ *                                growing size, see fb_set_option) copies chunk k+1 while chunk k is in the kernels;
+ *                                pageable inputs are gathered into a pinned staging ring by a few host threads
+ *                                first.  Chunks are summed in order and their sizes follow n alone: the same bits on every
+ *                                call. */
 int fb_map_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v,
                             const double *dev_V_reim, const double *dev_w, int w_stride,
                             const int32_t *dev_chan, int nchan, const fb_geometry *geom, int vis_model,

@@ -33,10 +33,7 @@ pin = [x.cpu().pin_memory() for x in (u, v, Vr, w)]
 page = [np.array(x.numpy()) for x in pin]
 hout = np.zeros(N * N + N + 1)
 for kind, arrs in (('pinned', pin), ('pageable', page)):
-    for growth, kmax, chunk, thr in [(3.0, 4, 250000, 8), (3.0, 3, 250000, 8), (2.0, 4, 250000, 8), (4.0, 3, 250000, 8), (1.0, 8, 250000, 8),
-                                     (3.0, 4, 250000, 4), (3.0, 4, 250000, 16), (1.0, 8, 250000, 16), (1.0, 1, 250000, 8)]:
-        if kind == 'pinned' and thr != 8:
-            continue
+    for growth, kmax, chunk, thr in [(2.0, 4, 250000, 8), (3.0, 4, 250000, 8), (1.5, 6, 250000, 8), (1.0, 8, 250000, 8), (1.0, 4, 250000, 8), (1.0, 2, 250000, 8), (1.0, 1, 250000, 8)]:
         ctx.set_option('map_growth', growth); ctx.set_option('map_kmax', kmax); ctx.set_option('map_chunk', chunk)
         ctx.set_option('stage_threads', thr)
         for _ in range(2):

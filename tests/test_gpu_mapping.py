@@ -403,8 +403,8 @@ def test_chunked_host_pipeline(fb, staging):
         sc = vm.map_visibilities(hu, hv, hV, 2.5)                     # broadcast scalar weight through the ring
     finally:
         ctx.set_option('map_chunk', 250_000)
-        ctx.set_option("map_kmax", 4)
-        ctx.set_option("map_growth", 2.0)
+        ctx.set_option("map_kmax", 8)
+        ctx.set_option("map_growth", 1.5)
         ctx.set_option('force_staging', 0)
     assert np.array_equal(a['M'], b['M']) and np.array_equal(a['j'], b['j']) and a['null_likelihood'] == b['null_likelihood']
     d = np.sqrt(np.diag(dev['M']))
