@@ -59,6 +59,7 @@ _SIGNATURES = {
     'fb_predict_visibilities': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
     'fb_predict_visibilities_dev': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
     'fb_predict_sky_dev': ([_c_p, _c_l, _c_p, _c_p, ctypes.POINTER(FBGeometry), _c_p, _c_i, _c_d, _c_p, _c_p], _c_i),
+    'fb_columns_gram_dev': ([_c_p, _c_l, _c_i, _c_p, _c_p], _c_i),
     'fb_apply_correction_dev': ([_c_p, _c_l, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_i),
     'fb_uv_max': ([_c_p, _c_l, _c_p, _c_p], _c_i),
     'fb_uv_bin': ([_c_p, _c_l, _c_p, _c_p, _c_i, _c_p, _c_i, _c_d, _c_i, _c_p, _c_p, _c_p, _c_p], _c_i),
@@ -431,6 +432,18 @@ class Context(object):
         self.check(self._lib.fb_predict_sky_dev(self._h, u.numel(), _ptr(u), _ptr(v), ctypes.byref(geom), _ptr(I), int(vis_model),
                                                 float(model_scale), _ptr(H2c), _ptr(torch.view_as_real(V))), 'fb_predict_sky_dev')
         return V
+
+    def columns_gram_dev(self, cols):
+        """fb_columns_gram_dev: X^T X of up to 8 float64 CUDA vectors of equal length, summed in a fixed order; returns a
+        NumPy [K, K] array."""
+        import torch
+        K, n = len(cols), cols[0].numel()
+        cols = [c.reshape(-1).contiguous() for c in cols]
+        ptrs = (ctypes.c_void_p * K)(*[c.data_ptr() for c in cols])
+        G = np.empty((K, K))
+        torch.cuda.current_stream(cols[0].device).synchronize()
+        self.check(self._lib.fb_columns_gram_dev(self._h, n, K, ctypes.cast(ptrs, _c_p), _ptr(G)), 'fb_columns_gram_dev')
+        return G
 
     # -- uv binning -----------------------------------------------------------------------------
     def uv_max(self, uv):

@@ -267,3 +267,84 @@ int fb_enqueue_result(fb_ctx *ctx, cudaStream_t st, int nchunks, double *dev_H0)
     FB_CUDA(cudaGetLastError());
     return 0;
 }
+
+
+// ---- small deterministic Gram of K device vectors (the normal equations of the geometry fit's Levenberg-Marquardt step) ----
+// G[a][b] = sum_i x_a[i] x_b[i], a <= b < K <= 8.  Pass 1: a fixed slab per block, fixed tree inside the block; pass 2: one
+// block sums the block partials in a fixed order.  Replaces the 2n x 4 Jacobian that scipy.optimize.least_squares builds and
+// factorises on the host at every iteration of FitGeometryFourierBessel (frank/geometry.py:745-746).
+namespace {
+
+constexpr int CG_MAXK = 8, CG_PAIRS = CG_MAXK * (CG_MAXK + 1) / 2, CG_BLOCKS = 592;
+
+struct ColPtrs { const double *p[CG_MAXK]; };
+
+__global__ void __launch_bounds__(256)
+k_cols_gram(int64_t n, int K, ColPtrs cols, double *__restrict__ partial)
+{
+    __shared__ double scratch[PREP_THREADS / 32];
+    double acc[CG_PAIRS];
+#pragma unroll
+    for (int e = 0; e < CG_PAIRS; e++) acc[e] = 0.0;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x, i0 = (int64_t)blockIdx.x * per, i1 = i0 + per < n ? i0 + per : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        double x[CG_MAXK];
+#pragma unroll
+        for (int a = 0; a < CG_MAXK; a++) x[a] = a < K ? cols.p[a][i] : 0.0;
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < CG_MAXK; a++)
+#pragma unroll
+            for (int b = a; b < CG_MAXK; b++, e++) acc[e] = fma(x[a], x[b], acc[e]);
+    }
+    int e = 0;
+    for (int a = 0; a < CG_MAXK; a++)
+        for (int b = a; b < CG_MAXK; b++, e++) {
+            if (a >= K || b >= K) continue;
+            const double r = block_reduce(acc[e], scratch, OpAdd(), 0.0);
+            if (threadIdx.x == 0) partial[(size_t)blockIdx.x * CG_PAIRS + e] = r;
+        }
+}
+
+__global__ void __launch_bounds__(64)
+k_cols_gram_final(int nblocks, int K, const double *__restrict__ partial, double *__restrict__ G)
+{
+    const int e = threadIdx.x;
+    if (e >= CG_PAIRS) return;
+    int a = 0, rem = e;
+    while (rem >= CG_MAXK - a) { rem -= CG_MAXK - a; a++; }
+    const int b = a + rem;
+    if (a >= K || b >= K) return;
+    double s = 0.0;
+    for (int k = 0; k < nblocks; k++) s += partial[(size_t)k * CG_PAIRS + e];
+    G[a * K + b] = s;
+    G[b * K + a] = s;
+}
+
+}  // namespace
+
+extern "C" int fb_columns_gram_dev(fb_ctx *ctx, int64_t n, int K, const double *const *dev_cols, double *host_G)
+{
+    if (!ctx) return -1;
+    if (n < 1 || K < 1 || K > CG_MAXK || !dev_cols || !host_G) FB_FAIL(-12, "fb_columns_gram_dev: bad arguments (1 <= K <= 8)");
+    FB_CUDA(cudaSetDevice(ctx->device));
+    FbLane &ln = ctx->lane[0];
+    const int need = CG_BLOCKS * CG_PAIRS / 3 + 64;                  // d_red holds 3 doubles per entry of red_cap
+    if (need > ln.red_cap) {
+        FB_CUDA(cudaStreamSynchronize(ln.stream));
+        if (ln.d_red) FB_CUDA(cudaFree(ln.d_red));
+        ln.d_red = nullptr;
+        FB_CUDA(cudaMalloc(&ln.d_red, sizeof(double) * (3 * (size_t)need + 8)));
+        ln.red_cap = need;
+    }
+    ColPtrs cols;
+    for (int a = 0; a < CG_MAXK; a++) cols.p[a] = a < K ? dev_cols[a] : nullptr;
+    double *d_G = ln.d_red + (size_t)CG_BLOCKS * CG_PAIRS;
+    const int nblocks = (int)std::min<int64_t>(CG_BLOCKS, (n + 255) / 256);
+    k_cols_gram<<<nblocks, 256, 0, ctx->stream>>>(n, K, cols, ln.d_red);
+    k_cols_gram_final<<<1, 64, 0, ctx->stream>>>(nblocks, K, ln.d_red, d_G);
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaMemcpyAsync(host_G, d_G, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -114,9 +114,10 @@ def map_visibilities_sharded(vis_map, u, v, V, weights, group=None, frequencies=
 
 
 def sweep_shard(n_points, rank, world):
-    """Grid points of rank `rank`: a contiguous block of the flattened (alpha-major) grid, sizes differing by at most one."""
-    lo, hi = shard_bounds(n_points, rank, world)
-    return np.arange(lo, hi)
+    """Grid points of rank `rank`: every world-th point of the flattened (alpha-major) grid starting at `rank`.  Strided, not
+    contiguous: the iteration count of a point grows steeply as alpha -> 1 (frank/radial_fitters.py:804-808 says as much), so
+    a contiguous block would hand one rank all the slow points."""
+    return np.arange(rank, n_points, world)
 
 
 def sweep_sharded(solve_points, n_points, N, group=None, ctx=None):
@@ -154,7 +155,7 @@ def sweep_sharded(solve_points, n_points, N, group=None, ctx=None):
         rows = np.stack([x.cpu().numpy() for x in parts])
     out = np.zeros((n_points, width))
     for r in range(world):
-        lo, hi = shard_bounds(n_points, r, world)
-        out[lo:hi] = rows[r, :hi - lo]
+        sel = sweep_shard(n_points, r, world)
+        out[sel] = rows[r, :len(sel)]
     return {'p': out[:, :N].copy(), 'mu': out[:, N:2 * N].copy(), 'niter': out[:, 2 * N].astype(np.int64),
             'converged': out[:, 2 * N + 1].astype(bool)}

@@ -153,6 +153,17 @@ class _TrialGeometryResidual(object):
         self._host = torch.empty(2 * len(u), dtype=torch.float64).pin_memory()
         self.evaluations = 0
 
+    def on_device(self, inc, PA, dRA, dDec):
+        """The residual as one float64 CUDA tensor [2 n] (real parts, then imaginary parts)."""
+        import torch
+        from frank_b200.radial_fitters import FourierBesselFitter
+        trial = FixedGeometry(inc, PA, dRA, dDec)
+        fitter = FourierBesselFitter(self._Rmax, self._N, trial, verbose=False, device=self._device)
+        model = fitter.fit(self._u, self._v, self._vis, self._w_fit).predict(self._u, self._v)
+        miss = torch.view_as_real(self._root_w * (model - self._vis))
+        self.evaluations += 1
+        return torch.cat([miss[:, 0], miss[:, 1]])
+
     def __call__(self, inc, PA, dRA, dDec):
         import torch
         from frank_b200.radial_fitters import FourierBesselFitter
@@ -168,21 +179,92 @@ class _TrialGeometryResidual(object):
         return self._host.numpy().copy()
 
 
+def _levenberg_marquardt_device(residual, x0, free, ctx, ftol=1e-8, xtol=1e-8, gtol=1e-8, max_nfev=None):
+    """Levenberg-Marquardt with every 2n-vector on the device.
+
+    What scipy.optimize.least_squares(method='lm') (MINPACK lmdif) does for the reference (frank/geometry.py:745-746), with the
+    same ingredients -- forward-difference Jacobian with step sqrt(eps) |x_j| (sqrt(eps) when x_j = 0), column scaling by the
+    largest column norm seen, tolerances ftol = xtol = gtol = 1e-8 -- but on the normal equations: an iteration needs only
+    J^T J, J^T r and r.r, which one fixed-order device reduction over the residual and the Jacobian columns delivers
+    (fb_columns_gram_dev) instead of a 2n x 4 host Jacobian and its QR factorisation.  The damping parameter follows Nielsen's
+    gain-ratio rule.  `free` lists the indices of x that are optimised.  Returns x, number of residual evaluations, converged."""
+    x = np.array(x0, dtype=np.float64)
+    k = len(free)
+    if max_nfev is None:
+        max_nfev = 100 * (len(x) + 1) * 4
+    eps = np.sqrt(np.finfo(np.float64).eps)
+    nfev = 0
+
+    def res(xv):
+        return residual.on_device(*xv)
+
+    r = res(x)
+    nfev += 1
+    scale = np.zeros(k)
+    lam, nu = None, 2.0
+    while nfev < max_nfev:
+        cols = []
+        for j in free:                                     # forward differences (MINPACK fdjac2)
+            h = eps * abs(x[j]) if x[j] != 0 else eps
+            xp = x.copy()
+            xp[j] += h
+            cols.append((res(xp) - r) / h)
+            nfev += 1
+        G = ctx.columns_gram_dev(cols + [r])               # [J | r]^T [J | r]
+        A, g, f = G[:k, :k], G[:k, k], G[k, k]
+        norms = np.sqrt(np.diag(A))
+        if f == 0 or np.max(np.abs(g) / np.where(norms > 0, norms, 1.0)) / np.sqrt(f) <= gtol:
+            return x, nfev, True                           # gradient orthogonal to the residual (MINPACK info = 4)
+        scale = np.maximum(scale, np.where(norms > 0, norms, 1.0))
+        if lam is None:
+            lam = 1e-3
+        while True:
+            step = np.linalg.solve(A + lam * np.diag(scale * scale), -g)
+            xn = x.copy()
+            xn[list(free)] += step
+            rn = res(xn)
+            nfev += 1
+            fn = float(ctx.columns_gram_dev([rn])[0, 0])
+            predicted = -(2.0 * g @ step + step @ A @ step)
+            gain = (f - fn) / predicted if predicted > 0 else -1.0
+            small_step = np.linalg.norm(scale * step) <= xtol * np.linalg.norm(scale * x[list(free)])
+            if gain > 1e-4:
+                converged = small_step or ((f - fn) <= ftol * f and predicted <= ftol * f)
+                x, r = xn, rn
+                lam *= max(1.0 / 3.0, 1.0 - (2.0 * gain - 1.0) ** 3)
+                nu = 2.0
+                if converged:
+                    return x, nfev, True
+                break
+            if small_step:
+                return x, nfev, True
+            lam *= nu
+            nu *= 2.0
+            if nfev >= max_nfev or not np.isfinite(lam):
+                return x, nfev, False
+    return x, nfev, False
+
+
 class FitGeometryFourierBessel(SourceGeometry):
     """Determine the disc geometry by minimising the weighted chi^2 of a non-parametric Fourier-Bessel fit
     (frank/geometry.py:623-763).
 
     Parameters as in the reference: Rmax (arcsec), N, inc_pa, phase_centre, guess = [inc, PA, dRA, dDec], verbose;
-    `device` selects the GPU.  SciPy's Levenberg-Marquardt (`least_squares(method='lm')`, finite-difference Jacobian)
-    drives the search as in the reference; every residual evaluation runs on GPU-resident visibilities
+    `device` selects the GPU.  Levenberg-Marquardt with a finite-difference Jacobian drives the search as in the reference
+    (`solver='scipy'`: scipy.optimize.least_squares(method='lm') itself, on residual vectors brought back to the host;
+    `solver='device'`: the same algorithm with the residual, the Jacobian columns and their reductions on the device;
+    'auto' switches at 2e5 visibilities); every residual evaluation runs on GPU-resident visibilities
     (_TrialGeometryResidual).  Parameters fixed through `inc_pa` / `phase_centre` are held at the given values inside every
     evaluation and reported back unchanged.
 
     (frank's FitGeometryGaussian, a 6-parameter uv-plane Gaussian fit, is outside the hot path and is not provided: use
     frank's own and pass the result in as a FixedGeometry.)"""
 
-    def __init__(self, Rmax, N, inc_pa=None, phase_centre=None, guess=None, verbose=False, device=None):
+    def __init__(self, Rmax, N, inc_pa=None, phase_centre=None, guess=None, verbose=False, device=None, solver='auto'):
         super(FitGeometryFourierBessel, self).__init__()
+        if solver not in ('auto', 'scipy', 'device'):
+            raise ValueError("solver must be 'auto', 'scipy' or 'device'")
+        self._solver = solver
         self._Rmax_fit, self._N_fit = Rmax, N
         self._fixed_inc_pa = None if inc_pa is None else tuple(inc_pa)
         self._fixed_centre = None if phase_centre is None else tuple(phase_centre)
@@ -224,11 +306,31 @@ class FitGeometryFourierBessel(SourceGeometry):
                       ''.format(residual.evaluations - 1, 0.5 * float(np.dot(r, r)) / (len(r) // 2), *trial), end='', flush=True)
             return r
 
-        result = least_squares(objective, self._start, method='lm')
-        if not result.success:
-            raise RuntimeError("FitGeometryFourierBessel failed to converge")
-        inc, PA, dRA, dDec = self._pin(result.x)
+        # 'scipy': the reference's driver on host residual vectors (what the small reference fixtures pin); 'device': the same
+        # algorithm on device-resident vectors, for data sets whose 2n x 4 host Jacobian is the bottleneck ('auto': from 2e5
+        # visibilities on)
+        solver = self._solver if self._solver != 'auto' else ('device' if len(u) >= 200_000 else 'scipy')
+        if solver == 'scipy':
+            result = least_squares(objective, self._start, method='lm')
+            if not result.success:
+                raise RuntimeError("FitGeometryFourierBessel failed to converge")
+            best, self._nfev = result.x, result.nfev
+        else:
+            from frank_b200 import _lib
+            free = [j for j in range(4) if not ((j < 2 and self._fixed_inc_pa is not None) or (j >= 2 and self._fixed_centre is not None))]
+            pinned_residual = residual
+            if len(free) < 4:                          # fixed parameters are substituted inside every evaluation
+                class _Pinned(object):
+                    evaluations = property(lambda s_: residual.evaluations)
+
+                    def on_device(s_, *params):
+                        return residual.on_device(*self._pin(params))
+                pinned_residual = _Pinned()
+            best, nfev, ok = _levenberg_marquardt_device(pinned_residual, self._start, free, _lib.get_context(self._device))
+            if not ok:
+                raise RuntimeError("FitGeometryFourierBessel failed to converge")
+            self._nfev = nfev
+        inc, PA, dRA, dDec = self._pin(best)
         if self._fixed_inc_pa is None:
             inc, PA = _fix_inc_and_PA_ranges(inc, PA)
         self._inc, self._PA, self._dRA, self._dDec = inc, PA, dRA, dDec
-        self._nfev = result.nfev

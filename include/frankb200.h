@@ -282,6 +282,12 @@ int fb_predict_visibilities_dev(fb_ctx *ctx, int64_t n, const double *dev_q, con
 int fb_predict_sky_dev(fb_ctx *ctx, int64_t n, const double *dev_u, const double *dev_v, const fb_geometry *geom,
                        const double *host_I, int vis_model, double model_scale, const double *host_H2, double *dev_V_reim);
 
+/* G = X^T X for K <= 8 device-resident columns x_a [n] (host array of K device pointers; G [K*K] host, row-major), summed in a
+ * fixed order.  The normal equations of a Levenberg-Marquardt step whose residual and Jacobian columns stay on the device: what
+ * FitGeometryFourierBessel (frank/geometry.py:745-746, scipy.optimize.least_squares on a 2n x 4 host Jacobian) needs per
+ * iteration is J^T J (4 x 4), J^T r (4) and r.r. */
+int fb_columns_gram_dev(fb_ctx *ctx, int64_t n, int K, const double *const *dev_cols, double *host_G);
+
 /* J0 as the Gram kernel evaluates it (device table), for accuracy tests: out[i] = J0(x[i]).
  * fb_debug_j0 uses the table row nearest to x (the per-visibility gather path); fb_debug_j0_far uses the
  * neighbouring row on the far side of x, the worst case of the one-row-per-stage path. */

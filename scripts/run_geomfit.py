@@ -16,6 +16,8 @@ Vd = np.cos(32.0 * deg_to_rad) * 2 * np.pi * sig * sig * 4e10 * np.exp(-2 * np.p
 u, v, V = gt.undo_correction(ud, vd, Vd.astype(complex))
 w = np.full(n, 2.5e3)
 V = V + (rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(w)
+# one-off process start-up (CUDA context, library load, pinned allocations) is paid by a small warm-up fit, as bench.py does
+FitGeometryFourierBessel(1.6, 20, guess=[28., 44., 0.015, -0.03], solver='device').fit(u[:5000], v[:5000], V[:5000], w[:5000])
 gf = FitGeometryFourierBessel(1.6, 20, guess=[28., 44., 0.015, -0.03])
 t0 = time.perf_counter()
 gf.fit(u, v, V, w)

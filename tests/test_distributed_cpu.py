@@ -103,7 +103,7 @@ def test_sweep_sharded_by_grid_point_gloo(tmp_path):
     world = 2
     mp.spawn(_sweep_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r0, r1 = np.load(tmp_path / 's0.npz'), np.load(tmp_path / 's1.npz')
-    assert list(r0['solved']) == [0, 1, 2, 3, 4] and list(r1['solved']) == [5, 6, 7, 8]      # each point solved exactly once
+    assert list(r0['solved']) == [0, 2, 4, 6, 8] and list(r1['solved']) == [1, 3, 5, 7]      # each point solved exactly once
     for k in ('p', 'mu', 'niter', 'converged'):
         assert np.array_equal(r0[k], r1[k])                                                  # every rank holds the whole grid
     # equal to the unsharded sweep, bit for bit
@@ -119,7 +119,7 @@ def test_sweep_sharded_by_grid_point_gloo(tmp_path):
 
 def test_sweep_sharded_single_process():
     from frank_b200.distributed import sweep_sharded, sweep_shard
-    assert list(sweep_shard(64, 3, 8)) == list(range(24, 32))
+    assert list(sweep_shard(64, 3, 8)) == list(range(3, 64, 8))
     res = sweep_sharded(lambda idx: {'p': np.outer(idx, np.ones(3)), 'mu': np.outer(idx, 2 * np.ones(3)),
                                      'niter': idx * 10, 'converged': idx % 2}, 5, 3)
     assert np.array_equal(res['p'][:, 0], np.arange(5)) and np.array_equal(res['niter'], np.arange(5) * 10)

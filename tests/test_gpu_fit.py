@@ -470,3 +470,21 @@ def test_fit_sweep_api(fb, golden):
     # the lazily factorised posterior of a sweep point serves the post-fit products
     c = sols[2].covariance
     assert np.allclose(c, c.T, rtol=0, atol=1e-9 * np.max(np.abs(c)))
+
+
+def test_fit_geometry_device_solver(golden):
+    """FitGeometryFourierBessel with the device-resident Levenberg-Marquardt (normal equations from fb_columns_gram_dev) against
+    the reference's result and against the SciPy-driven search on the same 3000 visibilities."""
+    from frank_b200.geometry import FitGeometryFourierBessel
+    g = golden('geomfit.npz')
+    u, v, V, w = g['u'], g['v'], g['V'], g['w']
+    gd = FitGeometryFourierBessel(1.6, 20, guess=[28., 44., 0.015, -0.03], solver='device')
+    gd.fit(u, v, V, w)
+    got = np.array([gd.inc, gd.PA, gd.dRA, gd.dDec])
+    print(f"\ndevice LM: {got} after {gd._nfev} residual evaluations; reference {g['fb']}")
+    assert np.all(np.abs(got[:2] - g['fb'][:2]) <= 2e-4), (got, g['fb'])
+    assert np.all(np.abs(got[2:] - g['fb'][2:]) <= 2e-6), (got, g['fb'])
+    gd2 = FitGeometryFourierBessel(1.6, 20, inc_pa=(32.0, 47.0), guess=[0., 0., 0.015, -0.03], solver='device')
+    gd2.fit(u, v, V, w)
+    assert (gd2.inc, gd2.PA) == (32.0, 47.0)
+    assert np.all(np.abs(np.array([gd2.dRA, gd2.dDec]) - g['fb_fixed_incpa'][2:]) <= 2e-6)
