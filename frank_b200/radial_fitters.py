@@ -261,19 +261,24 @@ class FrankFitter(FourierBesselFitter):
         self._ps_cov = None
         return self._sol
 
-    def _fit_sequenced(self, pI):
-        """The Normal iteration of frank/radial_fitters.py:765-785 sequenced from the host: only used when a factorisation
-        failed inside the device-resident loop, so that the SVD fallback of individual solves is honoured."""
+    def _sequenced_iteration(self, pI, filt, store=False):
+        """The Normal iteration of frank/radial_fitters.py:765-785 sequenced from the host, one GaussianModel (device Cholesky,
+        device SVD on failure, statistical_models.py:747-755) per step: the path taken when a factorisation failed inside the
+        device-resident loop, so that the reference's SVD fallback of individual solves is honoured.  Returns fit, p, count."""
         fit = self._perform_fit(pI, fit_method='Normal')
         count, pi_old = 0, 0
-        while (not self._filter.check_convergence(pI, pi_old)) and count <= self._max_iter:
+        while (not filt.check_convergence(pI, pi_old)) and count <= self._max_iter:
             pi_old = pI.copy()
-            pI = self._filter.update_power_spectrum(fit, device=self._device)
+            pI = filt.update_power_spectrum(fit, device=self._device)
             fit = self._perform_fit(pI, guess=fit.MAP, fit_method='Normal')
-            if self._store_iteration_diagnostics:
+            if store:
                 self._iteration_diagnostics['power_spectrum'].append(pI)
                 self._iteration_diagnostics['MAP'].append(fit.MAP)
             count += 1
+        return fit, pI, count
+
+    def _fit_sequenced(self, pI):
+        fit, pI, count = self._sequenced_iteration(pI, self._filter, store=self._store_iteration_diagnostics)
         self._report_convergence(count)
         if self._store_iteration_diagnostics:
             self._iteration_diagnostics['num_iterations'] = count
@@ -304,6 +309,7 @@ class FrankFitter(FourierBesselFitter):
         from frank_b200 import distributed
         self._build_matrices(preproc_vis)
         pI = self._starting_spectrum()                        # the warm-up fits do not depend on (alpha, w_smooth)
+        self._sweep_fallbacks = []
         grid = [(float(a), float(w)) for a in np.atleast_1d(alphas) for w in np.atleast_1d(weights_smooths)]
         ctx = _lib.get_context(self._device)
         ctx.dht_setup(self._DHT)
@@ -314,13 +320,20 @@ class FrankFitter(FourierBesselFitter):
             out = ctx.frank_normal_loop(self._M, self._j, np.tile(pI, (len(idx), 1)), [f._alpha for f in filters],
                                         [f._p_0 for f in filters], np.stack([f._Tinv for f in filters]), self._tol,
                                         self._max_iter, want_chol=False)
-            if out['status'] == _lib.FB_E_NOTPD:
-                raise np.linalg.LinAlgError("a posterior precision matrix of the sweep lost positive definiteness")
-            return {'p': out['p'], 'mu': out['mu'], 'niter': out['niter'], 'converged': out['converged']}
+            res = {'p': out['p'], 'mu': out['mu'], 'niter': out['niter'], 'converged': out['converged']}
+            for k in np.nonzero(out['info'])[0]:
+                # a Cholesky pivot failed for this point: redo it sequenced from the host, where a failed factorisation
+                # falls back to the SVD pseudo-inverse like the reference's GaussianModel (statistical_models.py:747-755)
+                fit, pk, count = self._sequenced_iteration(pI.copy(), filters[k])
+                res['p'][k], res['mu'][k], res['niter'][k] = pk, fit.MAP, count
+                res['converged'][k] = int(count <= self._max_iter)
+                self._sweep_fallbacks.append(int(idx[k]))
+            return res
 
         res = distributed.sweep_sharded(solve_points, len(grid), N, group=group, ctx=ctx)
         self.sweep_diagnostics = {'alpha': [g[0] for g in grid], 'wsmooth': [g[1] for g in grid],
-                                  'num_iterations': res['niter'].tolist(), 'converged': res['converged'].tolist()}
+                                  'num_iterations': res['niter'].tolist(), 'converged': res['converged'].tolist(),
+                                  'svd_fallback_points_this_rank': list(self._sweep_fallbacks)}
         sols = []
         for k, (a, w) in enumerate(grid):
             fit = GaussianModel(self._DHT, self._M, self._j, res['p'][k], noise_likelihood=self._H0, device=self._device,
