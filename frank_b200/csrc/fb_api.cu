@@ -72,7 +72,7 @@ int fb_ctx_destroy(fb_ctx *ctx)
                     (void *)ctx->d_H2, (void *)ctx->d_predI, (void *)ctx->d_out, (void *)ctx->d_binstart, (void *)ctx->d_pack,
                     (void *)ctx->sv_D, (void *)ctx->sv_p, (void *)ctx->sv_mu, (void *)ctx->sv_tr2, (void *)ctx->sv_alpha,
                     (void *)ctx->sv_p0, (void *)ctx->sv_Tinv, (void *)ctx->sv_M, (void *)ctx->sv_j, (void *)ctx->sv_Z,
-                    (void *)ctx->sv_flags, (void *)ctx->sv_hist, (void *)ctx->sv_rhs, (void *)ctx->sv_notconv, (void *)ctx->sv_rdiag, (void *)ctx->ln_S, (void *)ctx->ln_vec, (void *)ctx->ln_ws})
+                    (void *)ctx->sv_flags, (void *)ctx->sv_hist, (void *)ctx->sv_rhs, (void *)ctx->sv_notconv, (void *)ctx->sv_rdiag, (void *)ctx->sv_diag, (void *)ctx->ln_S, (void *)ctx->ln_vec, (void *)ctx->ln_ws})
         if (p) cudaFree(p);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->ln_pin) cudaFreeHost(ctx->ln_pin);

@@ -128,6 +128,7 @@ struct fb_ctx {
     int sv_B = 0, sv_N = 0;
     double *sv_D = nullptr, *sv_p = nullptr, *sv_mu = nullptr, *sv_tr2 = nullptr, *sv_alpha = nullptr, *sv_p0 = nullptr;
     double *sv_Tinv = nullptr, *sv_M = nullptr, *sv_j = nullptr, *sv_Z = nullptr, *sv_rdiag = nullptr;
+    double *sv_diag = nullptr;         // factorised diagonal blocks of the Cholesky panels, parked until the last panel is done
     int *sv_flags = nullptr;
     double *sv_rhs = nullptr;          // power-spectrum update: right-hand side beta + log p
     int *sv_notconv = nullptr;         // ... and its per-problem 'some entry moved by more than tol' flag

@@ -227,7 +227,7 @@ constexpr int SB = 16;                 // pivot sub-block
 // from the same values, as k_chol_update<true> would have done -- so that the rest of update k - 1 can run beside it.
 __global__ void __launch_bounds__(256)
 k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__restrict__ active, int *__restrict__ info,
-             double *__restrict__ rdiag_all, int fuse)
+             double *__restrict__ rdiag_all, int fuse, double *__restrict__ diag_out)
 {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
@@ -371,16 +371,33 @@ k_chol_panel(int N, int nb, int k, double *__restrict__ A_all, const int *__rest
         __syncthreads();
     }
     if (!off) {
-        for (int e = tid; e < NB * NB; e += 256) {
-            const int i = e >> 6, jj = e & 63;
-            if (i < nk && jj < nk && jj >= i) A[(size_t)(r0 + i) * N + r0 + jj] = S[i][jj];
-        }
+        // Every CTA of a block row factorises the diagonal block for itself from A; the copy that goes back must not land in A
+        // while a sibling CTA may still be loading the unfactorised block (with more CTAs than fit on the GPU at once -- 64
+        // problems at N = 300 -- the siblings of a late problem start after this CTA has finished): it is parked in `diag_out`
+        // and copied into A by k_chol_diag_writeback after the last panel.
+        double *Dk = diag_out + ((size_t)b * nb + k) * (NB * NB);
+        for (int e = tid; e < NB * NB; e += 256) Dk[e] = S[e >> 6][e & 63];
         if (tid < nk) rdiag_all[(size_t)b * N + r0 + tid] = rinv[tid];
     } else {
         for (int e = tid; e < NB * NB; e += 256) {
             const int i = e >> 6, jj = e & 63;
             if (i < nk && jj < nj) A[(size_t)(r0 + i) * N + c0 + jj] = X[i][jj];
         }
+    }
+}
+
+// the factorised diagonal blocks (upper triangles) from their parking place into A
+__global__ void __launch_bounds__(256)
+k_chol_diag_writeback(int N, int nb, double *__restrict__ A_all, const int *__restrict__ active, const double *__restrict__ diag)
+{
+    const int b = blockIdx.y, k = blockIdx.x;
+    if (active && !active[b]) return;
+    double *A = A_all + (size_t)b * N * N;
+    const double *Dk = diag + ((size_t)b * nb + k) * (NB * NB);
+    const int r0 = k * NB, nk = min(NB, N - r0);
+    for (int e = threadIdx.x; e < NB * NB; e += 256) {
+        const int i = e >> 6, jj = e & 63;
+        if (i < nk && jj < nk && jj >= i) A[(size_t)(r0 + i) * N + r0 + jj] = Dk[e];
     }
 }
 
@@ -1165,7 +1182,7 @@ static int ensure_solver_ws(fb_ctx *ctx, int B)
     if (B <= ctx->sv_B && ctx->sv_N == (int)N) return 0;
     for (void **p : {(void **)&ctx->sv_D, (void **)&ctx->sv_p, (void **)&ctx->sv_mu, (void **)&ctx->sv_tr2, (void **)&ctx->sv_alpha,
                      (void **)&ctx->sv_p0, (void **)&ctx->sv_Tinv, (void **)&ctx->sv_flags, (void **)&ctx->sv_M, (void **)&ctx->sv_j,
-                     (void **)&ctx->sv_Z, (void **)&ctx->sv_rdiag, (void **)&ctx->sv_rhs, (void **)&ctx->sv_notconv}) {
+                     (void **)&ctx->sv_Z, (void **)&ctx->sv_rdiag, (void **)&ctx->sv_rhs, (void **)&ctx->sv_notconv, (void **)&ctx->sv_diag}) {
         if (*p) FB_CUDA(cudaFree(*p));
         *p = nullptr;
     }
@@ -1174,6 +1191,7 @@ static int ensure_solver_ws(fb_ctx *ctx, int B)
     FB_CUDA(cudaMalloc(&ctx->sv_mu, sizeof(double) * B * N));
     FB_CUDA(cudaMalloc(&ctx->sv_tr2, sizeof(double) * B * N));
     FB_CUDA(cudaMalloc(&ctx->sv_rdiag, sizeof(double) * B * N));
+    FB_CUDA(cudaMalloc(&ctx->sv_diag, sizeof(double) * B * ((N + NB - 1) / NB) * NB * NB));
     FB_CUDA(cudaMalloc(&ctx->sv_rhs, sizeof(double) * B * N));
     FB_CUDA(cudaMalloc(&ctx->sv_notconv, sizeof(int) * B));
     FB_CUDA(cudaMalloc(&ctx->sv_alpha, sizeof(double) * B));
@@ -1203,13 +1221,14 @@ static int launch_factor(fb_ctx *ctx, int B, const int *d_active, int *d_info)
     FB_CUDA(cudaFuncSetAttribute(k_chol_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blku));
     if (!(fuse && upd_mma)) {
         for (int k = 0; k < nb; k++) {
-            k_chol_panel<<<dim3(nb - k, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag, 0);
+            k_chol_panel<<<dim3(nb - k, B), 256, blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag, 0, ctx->sv_diag);
             const int nt = nb - k - 1;
             if (nt > 0) {
                 if (upd_mma) k_chol_update<true><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, 0);
                 else k_chol_update<false><<<dim3(nt * (nt + 1) / 2, B), 256, blku, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, 0);
             }
         }
+        k_chol_diag_writeback<<<dim3(nb, B), 256, 0, ctx->stream>>>(N, nb, ctx->sv_D, d_active, ctx->sv_diag);
         FB_CUDA(cudaGetLastError());
         return 0;
     }
@@ -1222,7 +1241,7 @@ static int launch_factor(fb_ctx *ctx, int B, const int *d_active, int *d_info)
     for (int k = 0; k < nb; k++) {
         if (k >= 2 && nb - k >= 1 && (k - 2) + 2 <= nb - 1)                   // rest(k - 2) updated block row k
             FB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->cev[2 * (k - 2) + 1], 0));
-        k_chol_panel<<<dim3(nb - k, B), 256, k > 0 ? blk4 : blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag, k > 0 ? 1 : 0);
+        k_chol_panel<<<dim3(nb - k, B), 256, k > 0 ? blk4 : blk2, ctx->stream>>>(N, nb, k, ctx->sv_D, d_active, d_info, ctx->sv_rdiag, k > 0 ? 1 : 0, ctx->sv_diag);
         const int nt = nb - k - 2;                                            // block rows k + 2 .. nb - 1
         if (nt > 0) {
             FB_CUDA(cudaEventRecord(ctx->cev[2 * k], ctx->stream));           // panel k done
@@ -1231,6 +1250,7 @@ static int launch_factor(fb_ctx *ctx, int B, const int *d_active, int *d_info)
             FB_CUDA(cudaEventRecord(ctx->cev[2 * k + 1], ctx->stream3));      // rest(k) done
         }
     }
+    k_chol_diag_writeback<<<dim3(nb, B), 256, 0, ctx->stream>>>(N, nb, ctx->sv_D, d_active, ctx->sv_diag);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -288,7 +288,7 @@ class FrankFitter(FourierBesselFitter):
         return self._sol
 
     # -- hyper-parameter sweeps (BASELINE config 4) -------------------------------------------------------------------
-    def fit_sweep(self, u, v, V, weights=1, alphas=(1.05,), weights_smooths=(1e-4,), group=None):
+    def fit_sweep(self, u, v, V, weights=1, alphas=(1.05,), weights_smooths=(1e-4,), group=None, on_cholesky_failure='svd'):
         r"""Fit the same visibilities for every (alpha, w_smooth) pair of a grid.
 
         The reference's `run_multiple_fits` (frank/fit.py:493-563) loops `perform_fit` over the pairs and re-maps the
@@ -298,12 +298,18 @@ class FrankFitter(FourierBesselFitter):
         (frank_b200.distributed.sweep_sharded), so every rank returns the full grid.
 
         Returns a list of FrankGaussianFit in the reference's loop order (alpha outer, w_smooth inner);
-        `self.sweep_diagnostics` holds alpha, wsmooth, num_iterations and converged per point."""
+        `self.sweep_diagnostics` holds alpha, wsmooth, num_iterations and converged per point.
+
+        A grid point whose Cholesky factorisation fails inside the batched loop (alpha -> 1 with little smoothing) is, by
+        default, redone sequenced from the host with the reference's SVD fallback (`on_cholesky_failure='svd'`: thousands of
+        host-sequenced iterations, seconds per point); `'flag'` leaves it marked as not converged instead."""
         self._geometry.fit(u, v, V, weights)
         mapping = self.preprocess_visibilities(u, v, V, weights)
-        return self.fit_sweep_preprocessed(mapping, alphas, weights_smooths, group=group)
+        return self.fit_sweep_preprocessed(mapping, alphas, weights_smooths, group=group, on_cholesky_failure=on_cholesky_failure)
 
-    def fit_sweep_preprocessed(self, preproc_vis, alphas=(1.05,), weights_smooths=(1e-4,), group=None):
+    def fit_sweep_preprocessed(self, preproc_vis, alphas=(1.05,), weights_smooths=(1e-4,), group=None, on_cholesky_failure='svd'):
+        if on_cholesky_failure not in ('svd', 'flag'):
+            raise ValueError("on_cholesky_failure must be 'svd' or 'flag'")
         if self._method != 'Normal':
             raise ValueError("fit_sweep batches the Normal method; loop FrankFitter(method='LogNormal') over the grid instead")
         from frank_b200 import distributed
@@ -322,6 +328,10 @@ class FrankFitter(FourierBesselFitter):
                                         self._max_iter, want_chol=False)
             res = {'p': out['p'], 'mu': out['mu'], 'niter': out['niter'], 'converged': out['converged']}
             for k in np.nonzero(out['info'])[0]:
+                if on_cholesky_failure == 'flag':
+                    res['converged'][k] = 0
+                    self._sweep_fallbacks.append(int(idx[k]))
+                    continue
                 # a Cholesky pivot failed for this point: redo it sequenced from the host, where a failed factorisation
                 # falls back to the SVD pseudo-inverse like the reference's GaussianModel (statistical_models.py:747-755)
                 fit, pk, count = self._sequenced_iteration(pI.copy(), filters[k])
@@ -333,7 +343,7 @@ class FrankFitter(FourierBesselFitter):
         res = distributed.sweep_sharded(solve_points, len(grid), N, group=group, ctx=ctx)
         self.sweep_diagnostics = {'alpha': [g[0] for g in grid], 'wsmooth': [g[1] for g in grid],
                                   'num_iterations': res['niter'].tolist(), 'converged': res['converged'].tolist(),
-                                  'svd_fallback_points_this_rank': list(self._sweep_fallbacks)}
+                                  'cholesky_failed_points_this_rank': list(self._sweep_fallbacks)}
         sols = []
         for k, (a, w) in enumerate(grid):
             fit = GaussianModel(self._DHT, self._M, self._j, res['p'][k], noise_likelihood=self._H0, device=self._device,

@@ -104,12 +104,13 @@ if '4' in which:
     pre = FF.preprocess_visibilities(u, v, V, w)
     for _ in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        sols = FF.fit_sweep_preprocessed(pre, alphas=np.linspace(1.01, 1.5, 8), weights_smooths=np.logspace(-4, -1, 8))
+        sols = FF.fit_sweep_preprocessed(pre, alphas=np.linspace(1.01, 1.5, 8), weights_smooths=np.logspace(-4, -1, 8), on_cholesky_failure='flag')
         t1 = time.perf_counter()
     it = np.array(FF.sweep_diagnostics['num_iterations'])
     print(json.dumps({'config': '4 (FrankFitter.fit_sweep, one rank)', 'grid_points': len(sols), 'N': N, 'sweep_s': t1 - t0,
                       'iterations_min_max_sum': [int(it.min()), int(it.max()), int(it.sum())],
-                      'us_per_point_iteration': (t1 - t0) / it.sum() * 1e6, 'converged': int(np.sum(FF.sweep_diagnostics['converged']))}), flush=True)
+                      'us_per_point_iteration': (t1 - t0) / it.sum() * 1e6, 'converged': int(np.sum(FF.sweep_diagnostics['converged'])),
+                      'cholesky_failed_points': FF.sweep_diagnostics['cholesky_failed_points_this_rank']}), flush=True)
 
 if '5' in which:
     n, N = int(os.environ.get('CFG5_NVIS', 100_000_000)), 2000

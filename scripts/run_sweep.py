@@ -39,7 +39,7 @@ ctx = _lib.get_context(local)
 # single-rank batch first (reference for the bit-for-bit check and for the scaling ratio)
 for _ in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    one = FF.fit_sweep_preprocessed(pre, alphas, wss, group=None) if world == 1 else None
+    one = FF.fit_sweep_preprocessed(pre, alphas, wss, group=None, on_cholesky_failure='flag') if world == 1 else None
     t_one = time.perf_counter() - t0
 if world > 1:
     # every rank alone (no process group visible to the sweep): the 64-point batch on one GPU
@@ -48,13 +48,13 @@ if world > 1:
     fd._dist = lambda: None
     for _ in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        one = FF.fit_sweep_preprocessed(pre, alphas, wss)
+        one = FF.fit_sweep_preprocessed(pre, alphas, wss, on_cholesky_failure='flag')
         t_one = time.perf_counter() - t0
     fd._dist = saved
     distributed.init_library_comm(ctx)
     for _ in range(2):
         dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-        sols = FF.fit_sweep_preprocessed(pre, alphas, wss)
+        sols = FF.fit_sweep_preprocessed(pre, alphas, wss, on_cholesky_failure='flag')
         torch.cuda.synchronize(); t_sh = time.perf_counter() - t0
     tt = torch.tensor([t_sh], dtype=torch.float64, device='cuda')
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -488,3 +488,23 @@ def test_fit_geometry_device_solver(golden):
     gd2.fit(u, v, V, w)
     assert (gd2.inc, gd2.PA) == (32.0, 47.0)
     assert np.all(np.abs(np.array([gd2.dRA, gd2.dDec]) - g['fb_fixed_incpa'][2:]) <= 2e-6)
+
+
+def test_large_batch_problems_are_independent(fb, golden):
+    """Regression test of a race in the blocked Cholesky (round-1 bug, found by the sharded sweep): every CTA of a block row
+    factorises the diagonal block for itself, and the copy written back to A could overtake a sibling CTA that had not loaded
+    the block yet as soon as more CTAs were launched than fit on the GPU at once -- 64 problems at N = 300 made problems 59..63
+    fail with `info = 65`.  64 and 128 IDENTICAL problems must give 64 / 128 identical answers and no failed pivot."""
+    N = 300
+    u, v, V, w, odht = fo.synthetic_disc(20000, N, seed=3)
+    m = fo.map_visibilities(odht, u, v, V, w, 30., 40., 1e-3, -2e-3)
+    dht = fb.DHT(1.6 / fb.r2a, N)
+    ctx = fb.lib.get_context()
+    ctx.dht_setup(dht)
+    f = fb.CriticalFilter(dht, 1.3, 1e-15, 1e-2, 1e-3)
+    p0 = 1e10 * (dht.q / dht.q[0]) ** -2
+    for B in (64, 128):
+        out = ctx.frank_normal_loop(m['M'], m['j'], np.tile(p0, (B, 1)), np.full(B, 1.3), np.full(B, 1e-15), np.tile(f._Tinv, (B, 1, 1)),
+                                    1e-3, 30, want_chol=False)
+        assert not np.any(out['info']), out['info']
+        assert all(np.array_equal(out['p'][0], out['p'][b]) and np.array_equal(out['mu'][0], out['mu'][b]) for b in range(B))
