@@ -409,9 +409,14 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
     // Chunking: sizes grow geometrically (factor map_growth) from a first chunk of at least map_chunk visibilities, at most
     // map_kmax chunks.  The first chunk's copy is the exposed one, so it is small; each later copy (and, for pageable
     // inputs, the host-side gather into the staging ring) has the previous chunk's kernels to hide under.
+    // The floor of the first chunk scales with the work per visibility and the channels: a chunk must give every one of the
+    // Gram kernel's ~900 work items of every channel several tiles, and at large N the copy is a vanishing share of the call
+    // anyway (N = 2000, 4 channels: 220 ns of kernels against 0.8 ns of copy per visibility -> one or two chunks).
+    const double nn = (double)ctx->N / 300.0;
+    const int64_t chunk_min = (int64_t)((double)ctx->map_chunk * nchan * std::max(1.0, nn * nn));
     int K = 1;
     std::vector<int64_t> csize(1, n);
-    if (n >= 2 * ctx->map_chunk) {
+    if (n >= 2 * chunk_min) {
         // growth: the configured factor, or (map_growth = 0, the default) what the rates measured on the previous call
         // allow -- a chunk's copy has to fit under its predecessor's kernels: ratio <= 0.85 x (kernel time per visibility) /
         // (copy or staging time per visibility), between 1.25 and 3; 2 before anything has been measured
@@ -423,7 +428,7 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
         }
         K = std::max(1, std::min(ctx->map_kmax, FB_MAX_CHUNKS));
         auto first = [&](int k) { return r == 1.0 ? (double)n / k : (double)n * (r - 1.0) / (std::pow(r, k) - 1.0); };
-        while (K > 1 && first(K) < (double)ctx->map_chunk) K--;
+        while (K > 1 && first(K) < (double)chunk_min) K--;
         csize.assign(K, 0);
         double c = first(K);
         int64_t used = 0;
@@ -535,7 +540,7 @@ int fb_map_visibilities_host(fb_ctx *ctx, int64_t n, const double *host_u, const
         cudaEventElapsedTime(&copy_ms, ev_c0, ev_c1);
         collect_timing(ctx, K, copy_ms);
         ctx->map_chunks = K;
-        if (n >= 2 * ctx->map_chunk && copy_ms > 0.f) {           // arrival and kernel rates of this call steer the next call's chunking
+        if (K > 1 && copy_ms > 0.f) {           // arrival and kernel rates of this call steer the next call's chunking
             ctx->rate_copy_ns = 1e6 * (double)copy_ms / (double)n;
             ctx->rate_gram_ns = 1e6 * (ctx->timing[0] + ctx->timing[1]) / (double)n;
             ctx->rate_N = ctx->N;
