@@ -155,8 +155,9 @@ __device__ __forceinline__ double exp_neg(double x)
 // J0 phase of one warp for one tile: columns sc = warp, warp + 16, ... of the block; a lane holds two visibilities
 // (lane, lane + 32), so the column's polynomial row is fetched once (broadcast loads from the staged rows) for two
 // Horner chains.  The thread that staged the row has verified that it serves the tile's whole range of arguments
-// (validity flag); a column that needs more than one row (sparse data, or very large j_k) takes the per-visibility
-// gather path (warp-uniform branch, rare).  The data column and the zero padding are not written here.
+// (validity flag); a column that needs more than one row (sparse data, or very large j_k) is redone through the
+// per-visibility gather path AFTER the sweep, so that the sweep itself carries no branch (the reconvergence bookkeeping of
+// a rare in-loop branch cost 3 % of the kernel).  The data column and the zero padding are not written here.
 template <bool DEBRIS>
 __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sbase, const int buf, const int ncol,
                                            const int warp, const int lane, const int last_row)
@@ -171,6 +172,7 @@ __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sba
     uint32_t a_row = sbase + SMB_ROW + buf * (GCOLS * ROWB) + warp * 16;
     uint32_t a_cen = sbase + SMB_CEN + (buf * GCOLS + warp) * 16;
     uint32_t a_g = sbase + SMB_G + (warp * GLD + lane) * 8;
+    bool any_gather = false;
 #pragma unroll 1
     for (int sc = warp; sc < ncol; sc += NW) {
         const double2 cv = lds_v2f64(a_cen);                         // (centre, +j_k | -j_k: gather | -0: no store)
@@ -186,22 +188,35 @@ __device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sba
         g0 = fma(g0, u0, c23.x); g1 = fma(g1, u1, c23.x);
         g0 = fma(g0, u0, c01.y); g1 = fma(g1, u1, c01.y);
         g0 = fma(g0, u0, c01.x); g1 = fma(g1, u1, c01.x);
-        bool store = __double2hiint(cv.y) >= 0;
-        if (!store && cv.y != 0.0) {                                 // warp-uniform, rare: one row does not serve the tile
-            g0 = j0_tab(x0, p.tab, last_row);
-            g1 = j0_tab(x1, p.tab, last_row);
-            store = true;
-        }
+        // the hot loop carries no branch: columns whose tile range needs more than one row are redone after the loop
+        const bool plain = __double2hiint(cv.y) >= 0;
+        any_gather |= !plain && cv.y != 0.0;
         if (DEBRIS) {
             const double h2 = lds_f64(sbase + SMB_H2 + sc * 8);
             g0 *= exp_neg(k0 * h2);
             g1 *= exp_neg(k1 * h2);
         }
-        if (store) {                                                 // the data column and the padding are written elsewhere
+        if (plain) {                                                 // the data column and the padding are written elsewhere
             sts_f64(a_g, g0 * aw0.y);
             sts_f64(a_g + 32 * 8, g1 * aw1.y);
         }
         a_row += NW * 16; a_cen += NW * 16; a_g += NW * GLD * 8;
+    }
+    if (any_gather) {                                                // warp-uniform, rare: per-visibility rows for the columns that need them
+        for (int sc = warp; sc < ncol; sc += NW) {
+            const double2 cv = lds_v2f64(sbase + SMB_CEN + (buf * GCOLS + sc) * 16);
+            if (__double2hiint(cv.y) >= 0 || cv.y == 0.0) continue;
+            const double jk = fabs(cv.y);
+            double g0 = j0_tab(__dmul_rn(aw0.x, jk), p.tab, last_row), g1 = j0_tab(__dmul_rn(aw1.x, jk), p.tab, last_row);
+            if (DEBRIS) {
+                const double h2 = lds_f64(sbase + SMB_H2 + sc * 8);
+                g0 *= exp_neg(k0 * h2);
+                g1 *= exp_neg(k1 * h2);
+            }
+            const uint32_t ag = sbase + SMB_G + (sc * GLD + lane) * 8;
+            sts_f64(ag, g0 * aw0.y);
+            sts_f64(ag + 32 * 8, g1 * aw1.y);
+        }
     }
 }
 
