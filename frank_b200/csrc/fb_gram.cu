@@ -12,11 +12,12 @@
 //   * per tile of 64 visibilities, two phases separated by barriers (the FP64 pipe serves DMMA and DFMA alike and
 //     starves a warp that issues DFMAs while others stream DMMAs -- profiles/r01_gram_ncu_summary.txt -- so the
 //     phases are not overlapped):
-//       (1) all warps evaluate J0 for the block's columns into shared memory G[mode][vis]: a lane owns one column
-//           (its polynomial row in registers), a warp a range of visibilities, four Horner chains per lane.  The
-//           visibilities are sorted by baseline, so ONE row of the J0 table per (column, tile) serves all of them
-//           (rows overlap, fb_j0_table.h); rows are staged by cp.async one tile ahead; visibilities outside a row's
-//           validity window are redone through a per-visibility gather (rare);
+//       (1) the design-matrix tile G[mode][vis] of the block's columns is formed in shared memory -- also on the tensor
+//           pipe: the visibilities are sorted by baseline, so ONE row of the J0 table (a degree-7 polynomial; rows
+//           overlap, fb_j0_table.h) serves a (column, tile) pair, and re-centred on the tile it makes G a rank-8
+//           product of per-visibility powers and per-column coefficients (j0_gemm below).  Rows are staged by cp.async
+//           two tiles ahead and re-centred one tile ahead; columns whose tile range needs more than one row are redone
+//           per visibility from the table (rare);
 //       (2) all warps run mma.sync.m8n8k4.f64 (DMMA) over the tile;
 //   * diagonal blocks are executed as skewed strips (row r, offset d -> column (r+d) mod n) so that only the
 //     upper triangle is computed while every warp still owns a dense register block;
@@ -47,7 +48,7 @@ struct GramArgs {
     const int *type_tab;  // [2 * ntypes] (chunks, first slot)
     const double *H2;
     double *partial;
-    long long *prof;      // optional (FB_GRAM_PROF=1) [grid][2]: clocks thread 0 spent in the J0 / DMMA phases; results unaffected
+    long long *prof;      // builds with -DFB_GRAM_CLOCKS, FB_GRAM_PROF=1: [grid][2] clocks thread 0 spent in the J0 / DMMA phases
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
@@ -108,14 +109,19 @@ static_assert(FB_GRAM_THREADS == 2 * FB_GCOLS && FB_J0_ROWLEN == 8, "staging ass
 
 // shared-memory carve-up (bytes)
 constexpr int SMB_G = 0;                                   // [GCOLS][GLD] doubles      design-matrix tile
-constexpr int SMB_ROW = SMB_G + GCOLS * GLD * 8;           // [2][4][GCOLS] double2     staged J0 table rows (coefficient pair major)
-constexpr int SMB_CEN = SMB_ROW + 2 * GCOLS * ROWB;        // [2][GCOLS] double2        (centre of the staged row, +j_k row serves the tile | -j_k gather | -0 special column)
-constexpr int SMB_JK = SMB_CEN + 2 * GCOLS * 16;           // [GCOLS] ints (+ pad)      table row chosen for the tile being staged
+constexpr int SMB_ROW = SMB_G + GCOLS * GLD * 8;           // [4][GCOLS] double2        staged J0 table rows of the NEXT tile (coefficient pair major)
+constexpr int SMB_CM = SMB_ROW + GCOLS * ROWB;             // [2][2][GCOLS][4] doubles  per-column polynomials in the tile variable: (buffer, degrees 0-3 | 4-7, column, degree)
+constexpr int SMB_P = SMB_CM + 2 * 2 * GCOLS * 32;         // [2][2][GS][4] doubles     sqrt(w) * powers of the tile variable: (buffer, degrees 0-3 | 4-7, visibility, degree)
+constexpr int SMB_JK = SMB_P + 2 * 2 * GS * 32;            // [GCOLS] ints (+ pad)      table row chosen for the tile being staged
 constexpr int SMB_H2 = SMB_JK + GCOLS * 8;                 // [GCOLS] doubles           debris H2_k
 constexpr int SMB_VIS = SMB_H2 + GCOLS * 8;                // [2][GS][4] doubles        (a, sqrt w, kz, sqrt w Re V) per visibility of a tile
-constexpr int SMB_AR = SMB_VIS + 2 * GS * 32;               // [2] double2               (min a, max a) of the tiles being staged
-constexpr int SMB_SW = SMB_AR + 32;                        // [2][GS] doubles           sqrt w, compact (conflict-free re-reads of the half-warp sweep)
-constexpr int GRAM_SMEM_BYTES = SMB_SW + 2 * GS * 8;
+constexpr int SMB_AR = SMB_VIS + 2 * GS * 32;              // [4] double2               ring of (min a, max a) of the coming tiles
+constexpr int SMB_COL = SMB_AR + 4 * 16;                   // [GCOLS] double2           (column code j_k | -1 data column | -2 padding, j_k / j_ref)
+constexpr int SMB_JREF = SMB_COL + GCOLS * 16;             // double (+ pad)            largest j_k of the block: the tile variable is s = (a - a_c) j_ref
+constexpr int SMB_LIST = SMB_JREF + 16;                    // [2][GCOLS] shorts         columns the polynomial does not serve (and the data column), per buffer
+constexpr int SMB_NLIST = SMB_LIST + 2 * GCOLS * 2;        // [2] ints (+ pad)          their number
+constexpr int GRAM_SMEM_BYTES = SMB_NLIST + 16;
+static_assert(GRAM_SMEM_BYTES <= 227 * 1024, "shared memory of k_gram");
 
 __host__ __device__ __forceinline__ int split4_size(int n, int i) { return n / 4 + (i < n % 4 ? 1 : 0); }
 __host__ __device__ __forceinline__ int split4_start(int n, int i) { return i * (n / 4) + (i < n % 4 ? i : n % 4); }
@@ -152,139 +158,93 @@ __device__ __forceinline__ double exp_neg(double x)
     return k > -1021 ? y : 0.0;
 }
 
-// J0 phase of one warp for one tile: columns sc = warp, warp + 16, ... of the block; a lane holds two visibilities
-// (lane, lane + 32), so the column's polynomial row is fetched once (broadcast loads from the staged rows) for two
-// Horner chains.  The thread that staged the row has verified that it serves the tile's whole range of arguments
-// (validity flag); a column that needs more than one row (sparse data, or very large j_k) is redone through the
-// per-visibility gather path AFTER the sweep, so that the sweep itself carries no branch (the reconvergence bookkeeping of
-// a rare in-loop branch cost 3 % of the kernel).  The data column and the zero padding are not written here.
+// J0 phase of one warp for one tile, on the tensor pipe.  For the visibilities of a tile (sorted: a narrow range of
+// baselines a around the tile centre a_c) and a column k whose table row is valid over the tile,
+//     J0(a j_k) = sum_d c_d (a j_k - cen)^d = sum_d b_dk s^d,     s = (a - a_c) j_ref,
+// with b_dk the row's polynomial shifted to the tile centre and rescaled (prepare() in run_item, one thread per column), so
+// that the design-matrix tile is a rank-8 product
+//     G[v][k] = sqrt(w_v) J0(a_v j_k) = sum_d P[v][d] B[d][k],    P[v][d] = sqrt(w_v) s_v^d,
+// i.e. two m8n8k4 DMMAs per 8 x 8 block of G instead of 8 x 8 Horner chains fed by broadcast loads of the row: the sweep
+// with DFMAs was bound by those loads (15 shared-memory wavefronts per column against 10 clocks of FP64-pipe time) and ran
+// the FP64 pipe at 50 %.  A warp owns a quarter of the tile's visibilities (2 groups of 8: its A fragments, the powers,
+// stay in registers) and every fourth mode tile.
 template <bool DEBRIS>
-__device__ __forceinline__ void j0_columns(const GramArgs &p, const uint32_t sbase, const int buf, const int ncol,
-                                           const int warp, const int lane, const int last_row)
+__device__ __forceinline__ void j0_gemm(const GramArgs &p, const uint32_t sbase, const int buf, const int ntile,
+                                        const int warp, const int lane, const int last_row)
 {
+    const int qv = (warp & 3) * 16;                                       // this warp's quarter of the tile: visibilities qv .. qv + 15
+    const int lr = lane >> 2, lk = lane & 3;
     const uint32_t s_vis = sbase + SMB_VIS + buf * (GS * 32);
-    const double2 aw0 = lds_v2f64(s_vis + lane * 32), aw1 = lds_v2f64(s_vis + (lane + 32) * 32);
-    double k0 = 0.0, k1 = 0.0;
+    const uint32_t s_p = sbase + SMB_P + buf * (2 * GS * 32) + ((qv + lr) * 4 + lk) * 8;
+    const double pa00 = lds_f64(s_p), pa01 = lds_f64(s_p + GS * 32);                      // group 0: degrees 0-3 | 4-7
+    const double pa10 = lds_f64(s_p + 8 * 32), pa11 = lds_f64(s_p + GS * 32 + 8 * 32);    // group 1
+    double kq0 = 0.0, kq1 = 0.0;
     if (DEBRIS) {
-        k0 = lds_f64(s_vis + lane * 32 + 16); k1 = lds_f64(s_vis + (lane + 32) * 32 + 16);
-        k0 = -k0 * k0; k1 = -k1 * k1;                     // -kz^2
+        kq0 = lds_f64(s_vis + (qv + lr) * 32 + 16); kq1 = lds_f64(s_vis + (qv + 8 + lr) * 32 + 16);
+        kq0 = -kq0 * kq0; kq1 = -kq1 * kq1;                               // -kz^2
     }
-    uint32_t a_row = sbase + SMB_ROW + buf * (GCOLS * ROWB) + warp * 16;
-    uint32_t a_cen = sbase + SMB_CEN + (buf * GCOLS + warp) * 16;
-    uint32_t a_g = sbase + SMB_G + (warp * GLD + lane) * 8;
-    bool any_gather = false;
-#pragma unroll 1
-    for (int sc = warp; sc < ncol; sc += NW) {
-        const double2 cv = lds_v2f64(a_cen);                         // (centre, +j_k | -j_k: gather | -0: no store)
-        const double2 c67 = lds_v2f64(a_row + 3 * GCOLS * 16), c45 = lds_v2f64(a_row + 2 * GCOLS * 16),
-                      c23 = lds_v2f64(a_row + GCOLS * 16), c01 = lds_v2f64(a_row);
-        const double jk = fabs(cv.y);
-        const double x0 = __dmul_rn(aw0.x, jk), x1 = __dmul_rn(aw1.x, jk);      // a * j_k as the reference rounds it
-        const double u0 = __dsub_rn(x0, cv.x), u1 = __dsub_rn(x1, cv.x);        // exact
-        double g0 = fma(c67.y, u0, c67.x), g1 = fma(c67.y, u1, c67.x);
-        g0 = fma(g0, u0, c45.y); g1 = fma(g1, u1, c45.y);
-        g0 = fma(g0, u0, c45.x); g1 = fma(g1, u1, c45.x);
-        g0 = fma(g0, u0, c23.y); g1 = fma(g1, u1, c23.y);
-        g0 = fma(g0, u0, c23.x); g1 = fma(g1, u1, c23.x);
-        g0 = fma(g0, u0, c01.y); g1 = fma(g1, u1, c01.y);
-        g0 = fma(g0, u0, c01.x); g1 = fma(g1, u1, c01.x);
-        // the hot loop carries no branch: columns whose tile range needs more than one row are redone after the loop
-        const bool plain = __double2hiint(cv.y) >= 0;
-        any_gather |= !plain && cv.y != 0.0;
-        if (DEBRIS) {
-            const double h2 = lds_f64(sbase + SMB_H2 + sc * 8);
-            g0 *= exp_neg(k0 * h2);
-            g1 *= exp_neg(k1 * h2);
-        }
-        if (plain) {                                                 // the data column and the padding are written elsewhere
-            sts_f64(a_g, g0 * aw0.y);
-            sts_f64(a_g + 32 * 8, g1 * aw1.y);
-        }
-        a_row += NW * 16; a_cen += NW * 16; a_g += NW * GLD * 8;
-    }
-    if (any_gather) {                                                // warp-uniform, rare: per-visibility rows for the columns that need them
-        for (int sc = warp; sc < ncol; sc += NW) {
-            const double2 cv = lds_v2f64(sbase + SMB_CEN + (buf * GCOLS + sc) * 16);
-            if (__double2hiint(cv.y) >= 0 || cv.y == 0.0) continue;
-            const double jk = fabs(cv.y);
-            double g0 = j0_tab(__dmul_rn(aw0.x, jk), p.tab, last_row), g1 = j0_tab(__dmul_rn(aw1.x, jk), p.tab, last_row);
-            if (DEBRIS) {
-                const double h2 = lds_f64(sbase + SMB_H2 + sc * 8);
-                g0 *= exp_neg(k0 * h2);
-                g1 *= exp_neg(k1 * h2);
-            }
-            const uint32_t ag = sbase + SMB_G + (sc * GLD + lane) * 8;
-            sts_f64(ag, g0 * aw0.y);
-            sts_f64(ag + 32 * 8, g1 * aw1.y);
-        }
-    }
-}
+    const uint32_t s_cm = sbase + SMB_CM + buf * (2 * GCOLS * 32) + (lr * 4 + lk) * 8;
+    // The accumulator fragment holds (visibility lr, modes 2 lk, 2 lk + 1).  Rows of G are 8 banks apart (GLD = 4 mod 16
+    // doubles, what the DMMA phase's fragment loads want), mode pairs 16: stored as they come, lanes lk = 0, 2 (and 1, 3)
+    // would hit the same banks.  So a store instruction takes the even mode from lanes lk < 2 and the odd one from lanes
+    // lk >= 2, and a second one the rest: conflict free.
+    const bool lo = lk < 2;
+    const uint32_t s_g0 = sbase + SMB_G + ((2 * lk + (lo ? 0 : 1)) * GLD + qv + lr) * 8;      // first store: even mode | odd mode
+    const uint32_t s_g1 = sbase + SMB_G + ((2 * lk + (lo ? 1 : 0)) * GLD + qv + lr) * 8;      // second store: the other one
 
-// Variant of the J0 phase with one column per HALF-warp and four visibilities per lane (lane16, lane16 + 16, + 32, + 48):
-// the five 16-byte loads of a column's row (centre / j_k and four coefficient pairs) are issued once for TWO columns --
-// the two half-warps of a load instruction read two different rows -- so a column costs half the shared-memory
-// wavefronts of its coefficient fetch (the sweep of j0_columns is bound by them: 15 wavefronts against 10 clocks of
-// FP64-pipe time per column), at the price of two more Horner chains' worth of registers.
-template <bool DEBRIS>
-__device__ __forceinline__ void j0_columns4(const GramArgs &p, const uint32_t sbase, const int buf, const int ncol,
-                                            const int warp, const int lane, const int last_row)
-{
-    const int l16 = lane & 15, half = lane >> 4;
-    const uint32_t s_vis = sbase + SMB_VIS + buf * (GS * 32);
-    const uint32_t s_sw = sbase + SMB_SW + buf * (GS * 8);
-    double av[4], kk[4];             // a of this lane's four visibilities (sqrt w is re-read at the store: registers)
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-        av[m] = lds_f64(s_vis + (l16 + 16 * m) * 32);
-        kk[m] = 0.0;
-        if (DEBRIS) { const double k = lds_f64(s_vis + (l16 + 16 * m) * 32 + 16); kk[m] = -k * k; }
-    }
-    const int c0 = 2 * warp + half;
-    uint32_t a_row = sbase + SMB_ROW + buf * (GCOLS * ROWB) + c0 * 16;
-    uint32_t a_cen = sbase + SMB_CEN + (buf * GCOLS + c0) * 16;
-    uint32_t a_g = sbase + SMB_G + (c0 * GLD + l16) * 8;
-#pragma unroll 1
-    for (int sc = c0; sc < ncol; sc += 2 * NW) {
-        const double2 cv = lds_v2f64(a_cen);                             // (centre, +j_k | -j_k: gather | -0: no store)
-        const double2 c67 = lds_v2f64(a_row + 3 * GCOLS * 16), c45 = lds_v2f64(a_row + 2 * GCOLS * 16),
-                      c23 = lds_v2f64(a_row + GCOLS * 16), c01 = lds_v2f64(a_row);
-        const double jk = fabs(cv.y);
-        const bool plain = __double2hiint(cv.y) >= 0;                    // one staged row serves the tile
-        const bool gather = !plain && cv.y != 0.0;                       // half-warp-uniform, rare
-        double h2 = 0.0;
-        if (DEBRIS) h2 = lds_f64(sbase + SMB_H2 + sc * 8);
-        // two passes of two chains: the row stays in registers, only two evaluations are live at a time (four live chains
-        // next to the 60 accumulator registers made ptxas spill inside the DMMA loops)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const double x0 = __dmul_rn(av[2 * h], jk), x1 = __dmul_rn(av[2 * h + 1], jk);       // a * j_k as the reference rounds it
-            const double u0 = __dsub_rn(x0, cv.x), u1 = __dsub_rn(x1, cv.x);                     // exact
-            double g0 = fma(c67.y, u0, c67.x), g1 = fma(c67.y, u1, c67.x);
-            g0 = fma(g0, u0, c45.y); g1 = fma(g1, u1, c45.y);
-            g0 = fma(g0, u0, c45.x); g1 = fma(g1, u1, c45.x);
-            g0 = fma(g0, u0, c23.y); g1 = fma(g1, u1, c23.y);
-            g0 = fma(g0, u0, c23.x); g1 = fma(g1, u1, c23.x);
-            g0 = fma(g0, u0, c01.y); g1 = fma(g1, u1, c01.y);
-            g0 = fma(g0, u0, c01.x); g1 = fma(g1, u1, c01.x);
-            if (gather) {
-                g0 = j0_tab(x0, p.tab, last_row);
-                g1 = j0_tab(x1, p.tab, last_row);
-            }
-            if (DEBRIS) {
-                g0 *= exp_neg(kk[2 * h] * h2);
-                g1 *= exp_neg(kk[2 * h + 1] * h2);
-            }
-            if (plain || gather) {                                       // the data column and the padding are written elsewhere
-                sts_f64(a_g + 32 * h * 8, g0 * lds_f64(s_sw + (l16 + 32 * h) * 8));
-                sts_f64(a_g + (32 * h + 16) * 8, g1 * lds_f64(s_sw + (l16 + 32 * h + 16) * 8));
-            }
+    // Columns to redo per visibility from the table (the tile's range of arguments needs more than one row: sparse data,
+    // very large j_k) and the data column: items (column, half of the tile) dealt to the warps, a lane per visibility.
+    // Done first: the latency of their table loads hides behind the DMMAs of the other warps (done last, even on the warps
+    // that idle while the others prepare the next tile, they cost 0.6 % more).
+    int nl;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(nl) : "r"(sbase + SMB_NLIST + buf * 4));
+    for (int item = warp; item < 2 * nl; item += NW) {
+        unsigned short c16;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c16) : "r"(sbase + SMB_LIST + (buf * GCOLS + (item >> 1)) * 2));
+        const int c = c16, v = (item & 1) * 32 + lane;
+        const double jk = lds_f64(sbase + SMB_COL + c * 16);
+        const double2 aw = lds_v2f64(s_vis + v * 32);
+        double g;
+        if (jk >= 0.0) {
+            g = j0_tab(__dmul_rn(aw.x, jk), p.tab, last_row) * aw.y;
+            if (DEBRIS) { const double kz = lds_f64(s_vis + v * 32 + 16); g *= exp_neg(-kz * kz * lds_f64(sbase + SMB_H2 + c * 8)); }
+        } else {
+            g = lds_f64(s_vis + v * 32 + 24);                              // data column: G[N][v] = sqrt(w_v) Re V_v
         }
-        a_row += 2 * NW * 16; a_cen += 2 * NW * 16; a_g += 2 * NW * GLD * 8;
+        sts_f64(sbase + SMB_G + (c * GLD + v) * 8, g);
+    }
+    // A warp takes every fourth mode tile of its quarter.  The next tile's operands are fetched right behind the DMMAs of the
+    // current one, before its results are stored, so a warp waits for the latency of its own DMMAs only.  Columns on the list
+    // (below) carry NaN coefficients (prepare): their results are NaN for every visibility and are not stored.
+    int t = warp >> 2;
+    if (t < ntile) {
+        double bN0 = lds_f64(s_cm + t * (8 * 32)), bN1 = lds_f64(s_cm + GCOLS * 32 + t * (8 * 32));
+#pragma unroll 1
+        for (;;) {
+            const int tn = t + NW / 4;
+            double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+            dmma(d0, pa01, bN1); dmma(d1, pa11, bN1);
+            dmma(d0, pa00, bN0); dmma(d1, pa10, bN0);
+            if (tn < ntile) { bN0 = lds_f64(s_cm + tn * (8 * 32)); bN1 = lds_f64(s_cm + GCOLS * 32 + tn * (8 * 32)); }
+            if (DEBRIS) {
+                const double2 h2 = lds_v2f64(sbase + SMB_H2 + (t * 8 + 2 * lk) * 8);
+                d0[0] *= exp_neg(kq0 * h2.x); d0[1] *= exp_neg(kq0 * h2.y);
+                d1[0] *= exp_neg(kq1 * h2.x); d1[1] *= exp_neg(kq1 * h2.y);
+            }
+            const uint32_t off = t * (8 * GLD * 8);
+            const double x0 = lo ? d0[0] : d0[1], y0 = lo ? d0[1] : d0[0];
+            const double x1 = lo ? d1[0] : d1[1], y1 = lo ? d1[1] : d1[0];
+            // (NaN test on the exponent bits: an FP64 compare would queue behind the other warps' DMMAs)
+            if ((__double2hiint(x0) & 0x7ff00000) != 0x7ff00000) { sts_f64(s_g0 + off, x0); sts_f64(s_g0 + off + 64, x1); }
+            if ((__double2hiint(y0) & 0x7ff00000) != 0x7ff00000) { sts_f64(s_g1 + off, y0); sts_f64(s_g1 + off + 64, y1); }
+            if (tn >= ntile) break;
+            t = tn;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// One work item for one warp: per stage, the DMMAs of stage s, then the warp's J0 segments of stage s + 1
+// One work item: per tile, the J0 phase (design-matrix tile into shared memory), then the DMMA phase (Gram update)
 // ---------------------------------------------------------------------------------------------
 struct ItemCtx {
     uint32_t sbase;
@@ -295,32 +255,28 @@ struct ItemCtx {
     int nst;
     int ld;
     double *out;
-    double my_jk;          // column code (j_k | -1 data column | -2 padding) of column tid - 256: staging duty of this thread
     int dcol;              // local index of the data column in this block, -1 if absent
 };
 
-// DMMAs of one tile for one warp.  G: generic pointer to the tile; fr[p]: this lane's fragment offset inside a
-// tile row of parity p (the swizzle depends on the parity of the local tile index); ta / tb: first local tile index of
-// the A rows / B columns of this warp's register block.
+// DMMAs of one tile for one warp.  G: generic pointer to the tile; fr: this lane's fragment offset inside a tile row;
+// ta / tb: first local tile index of the A rows / B columns of this warp's register block.
 template <int KIND, int NR, int NC>
 __device__ __forceinline__ void stage_dmma(double (&acc)[NR * NC > 0 ? NR * NC : 1][2], const double *__restrict__ G,
-                                           const int fr0, const int fr1, const int ta, const int tb, const int cbase,
-                                           const int nmod)
+                                           const int fr, const int ta, const int tb, const int cbase, const int nmod)
 {
     if (NR * NC == 0) return;
-    const double *A0 = G + ta * 8 * GLD + ((ta & 1) ? fr1 : fr0);          // tile rows ta, ta + 2, ...
-    const double *A1 = G + ta * 8 * GLD + ((ta & 1) ? fr0 : fr1);          // tile rows ta + 1, ta + 3, ...
-    const double *B0 = G + tb * 8 * GLD + ((tb & 1) ? fr1 : fr0);
-    const double *B1 = G + tb * 8 * GLD + ((tb & 1) ? fr0 : fr1);
+    const double *A = G + ta * 8 * GLD + fr;
+    const double *B = G + tb * 8 * GLD + fr;
+    const double *Gf = G + fr;
 #pragma unroll 2
     for (int ks = 0; ks < GKS; ks++) {
         double af[NR > 0 ? NR : 1];
 #pragma unroll
-        for (int r = 0; r < NR; r++) af[r] = ((r & 1) ? A1 : A0)[r * 8 * GLD + ks * 4];
+        for (int r = 0; r < NR; r++) af[r] = A[r * 8 * GLD + ks * 4];
         if (KIND == FB_KIND_OFF) {
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                const double bf = ((c & 1) ? B1 : B0)[c * 8 * GLD + ks * 4];
+                const double bf = B[c * 8 * GLD + ks * 4];
 #pragma unroll
                 for (int r = 0; r < NR; r++) dmma(acc[r * NC + c], af[r], bf);
             }
@@ -329,7 +285,7 @@ __device__ __forceinline__ void stage_dmma(double (&acc)[NR * NC > 0 ? NR * NC :
             for (int s = 0; s < NR + NC - 1; s++) {
                 int ct = cbase + s;
                 ct = ct >= nmod ? ct - nmod : ct;
-                const double bf = G[ct * 8 * GLD + ((ct & 1) ? fr1 : fr0) + ks * 4];
+                const double bf = Gf[ct * 8 * GLD + ks * 4];
 #pragma unroll
                 for (int r = 0; r < NR; r++) {
                     const int dd = s - r;
@@ -347,98 +303,171 @@ __device__ __forceinline__ void run_item(const GramArgs &p, const ItemCtx &it, c
 #pragma unroll
     for (int i = 0; i < (NR * NC > 0 ? NR * NC : 1); i++) acc[i][0] = acc[i][1] = 0.0;
     const int last_row = p.tab_rows - 1;
-    const int fr0 = (lane >> 2) * GLD + (lane & 3), fr1 = fr0;     // fragment offset of this lane inside a tile row
+    const int fr = (lane >> 2) * GLD + (lane & 3);                 // fragment offset of this lane inside a tile row
     const int ta = it.r0, tb = KIND == FB_KIND_OFF ? it.ncolA / 8 + it.c0 : 0;
     const int cbase = KIND == FB_KIND_OFF ? 0 : (it.r0 + it.c0) % it.nmod;
     const uint32_t sbase = it.sbase;
+    const int col = tid - 256;                                     // staging duty: column `col` of the block
 
-    // Staging of everything the J0 phase of a tile needs, in two parts.
-    // stage_math(ar, buf) -- threads 256.. (the warps with one column less in the J0 phase), one column each: the table
-    //   row that serves arguments [ar.x j_k, ar.y j_k], its centre, and whether that one row covers the whole tile.
-    // stage_copy(buf, q, q2) -- all threads, cp.async only (no registers held, nothing for the FP64 pipe, so it can fly
-    //   during the DMMAs): four lanes copy the four 16-byte pieces of a row, so that a warp-wide copy touches 8 rows,
-    //   not 32; the per-visibility scalars (a, sqrt w, kz, sqrt w Re V) of tile q; the range (min a, max a) of tile q2.
-    auto stage_math = [&](const double2 ar, const int buf) {
-        const int col = tid - 256;
+    // Everything the J0 phase of a tile needs is prepared one to two tiles ahead, in three steps.
+    // select(ar)        -- thread 256 + c, J0 phase of tile s: the table row for column c over tile s + 2 (arguments
+    //                      [ar.x j_k, ar.y j_k]).
+    // stage_copy(...)   -- all threads, DMMA phase of tile s, cp.async only (no registers held, nothing for the FP64 pipe):
+    //                      the chosen rows (four lanes copy the four 16-byte pieces of a row, so a warp-wide copy touches 8
+    //                      rows, not 32), the per-visibility scalars (a, sqrt w, kz, sqrt w Re V) of tile s + 2, the
+    //                      range (min a, max a) of tile s + 3.
+    // prepare(ar, ...)  -- J0 phase of tile s, for tile s + 1: thread 256 + c shifts the staged row's polynomial of column
+    //                      c to the tile centre (B); thread v < 64 forms the powers of visibility v's tile variable (P).
+    auto select = [&](const double2 ar) {
         if (col >= 0 && col < it.ncol) {
             int m = 0;
-            double cen = 0.0, jks = -0.0;
-            if (it.my_jk >= 0.0) {
-                const double xlo = __dmul_rn(ar.x, it.my_jk), xhi = __dmul_rn(ar.y, it.my_jk);
+            const double jk = lds_f64(sbase + SMB_COL + col * 16);
+            if (jk >= 0.0) {
+                const double xlo = __dmul_rn(ar.x, jk), xhi = __dmul_rn(ar.y, jk);
                 m = min(__double2loint(fma(xlo + xhi, 0.5 * FB_J0_INVH, J0_MAGIC)), last_row);
-                cen = (double)m * FB_J0_H;
-                jks = (fabs(xlo - cen) < FB_J0_ACCEPT && fabs(xhi - cen) < FB_J0_ACCEPT) ? it.my_jk : -it.my_jk;
             }
-            sts_v2f64(sbase + SMB_CEN + (buf * GCOLS + col) * 16, cen, jks);
             asm volatile("st.shared.s32 [%0], %1;" ::"r"(sbase + SMB_JK + col * 4), "r"(m) : "memory");
         }
     };
-    auto stage_copy = [&](const int buf, const long long q, const long long q2) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int col = (tid >> 2) + 128 * h, piece = tid & 3;
-            if (col < it.ncol) {
+    auto prepare = [&](const double2 ar, const int vbuf, const int buf) {
+        const double ac = 0.5 * (ar.x + ar.y);
+        if (col >= 0 && col < it.ncol) {
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
+            const double2 jr = lds_v2f64(sbase + SMB_COL + col * 16);                  // (j_k | -1 data column | -2 padding, j_k / j_ref)
+            bool listed = jr.x == -1.0;
+            if (jr.x >= 0.0) {
                 int m;
                 asm volatile("ld.shared.s32 %0, [%1];" : "=r"(m) : "r"(sbase + SMB_JK + col * 4));
-                const double2 *src = p.tab + (size_t)m * (FB_J0_ROWLEN / 2) + piece;
-                const uint32_t dst = sbase + SMB_ROW + buf * (GCOLS * ROWB) + piece * (GCOLS * 16) + col * 16;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                const double cen = (double)m * FB_J0_H;
+                const double xlo = __dmul_rn(ar.x, jr.x), xhi = __dmul_rn(ar.y, jr.x);
+                const bool ok = fabs(xlo - cen) < FB_J0_ACCEPT && fabs(xhi - cen) < FB_J0_ACCEPT;
+                listed = !ok;
+                if (ok) {
+                    const uint32_t rw = sbase + SMB_ROW + col * 16;
+                    const double2 r01 = lds_v2f64(rw), r23 = lds_v2f64(rw + GCOLS * 16), r45 = lds_v2f64(rw + 2 * GCOLS * 16),
+                                  r67 = lds_v2f64(rw + 3 * GCOLS * 16);
+                    c0 = r01.x; c1 = r01.y; c2 = r23.x; c3 = r23.y; c4 = r45.x; c5 = r45.y; c6 = r67.x; c7 = r67.y;
+                    // a j_k - cen = s r + e: shift the polynomial by e (repeated synthetic division) ...
+                    const double e = fma(ac, jr.x, -cen);
+#define FB_SHIFT_PASS(lo)                                          \
+                    c6 = fma(e, c7, c6);                           \
+                    if (lo <= 5) c5 = fma(e, c6, c5);              \
+                    if (lo <= 4) c4 = fma(e, c5, c4);              \
+                    if (lo <= 3) c3 = fma(e, c4, c3);              \
+                    if (lo <= 2) c2 = fma(e, c3, c2);              \
+                    if (lo <= 1) c1 = fma(e, c2, c1);              \
+                    if (lo <= 0) c0 = fma(e, c1, c0);
+                    FB_SHIFT_PASS(0) FB_SHIFT_PASS(1) FB_SHIFT_PASS(2) FB_SHIFT_PASS(3) FB_SHIFT_PASS(4) FB_SHIFT_PASS(5) FB_SHIFT_PASS(6)
+#undef FB_SHIFT_PASS
+                    // ... and rescale to the tile variable: b_d = c_d r^d
+                    const double r = jr.y, r2 = r * r, r4 = r2 * r2;
+                    c1 *= r; c2 *= r2; c3 *= r2 * r; c4 *= r4; c5 *= r4 * r; c6 *= r4 * r2; c7 *= r4 * (r2 * r);
+                }
             }
+            if (listed) {                                                   // not served by the tile's DMMAs: NaN marks the column (j0_gemm)
+                c0 = __longlong_as_double(0x7ff8000000000000LL);
+                int idx;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(idx) : "r"(sbase + SMB_NLIST + buf * 4) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(sbase + SMB_LIST + (buf * GCOLS + idx) * 2), "h"((unsigned short)col) : "memory");
+            }
+            const uint32_t cm = sbase + SMB_CM + buf * (2 * GCOLS * 32) + col * 32;
+            sts_v2f64(cm, c0, c1); sts_v2f64(cm + 16, c2, c3);
+            sts_v2f64(cm + GCOLS * 32, c4, c5); sts_v2f64(cm + GCOLS * 32 + 16, c6, c7);
         }
         if (tid < GS) {
-            const size_t v = (size_t)q * GS + tid;
-            const uint32_t d = sbase + SMB_VIS + buf * (GS * 32) + tid * 32;
+            const double2 aw = lds_v2f64(sbase + SMB_VIS + vbuf * (GS * 32) + tid * 32);
+            const double sv = aw.y != 0.0 ? (aw.x - ac) * lds_f64(sbase + SMB_JREF) : 0.0;            // padding slots: a = 0, w = 0
+            const double s2 = sv * sv, s4 = s2 * s2;
+            const double p0 = aw.y, p1 = p0 * sv, p2 = p0 * s2, p3 = p1 * s2;
+            const uint32_t pp = sbase + SMB_P + buf * (2 * GS * 32) + tid * 32;
+            sts_v2f64(pp, p0, p1); sts_v2f64(pp + 16, p2, p3);
+            sts_v2f64(pp + GS * 32, p0 * s4, p1 * s4); sts_v2f64(pp + GS * 32 + 16, p2 * s4, p3 * s4);
+        }
+    };
+    // rows: copy the rows chosen by select(); qv >= 0: scalars of tile qv into buffer vbuf; qa >= 0: range of tile qa into ring slot
+    auto stage_copy = [&](const bool rows, const long long qv, const int vbuf, const long long qa, const int slot) {
+        if (rows) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int c = (tid >> 2) + 128 * h, piece = tid & 3;
+                if (c < it.ncol) {
+                    int m;
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(m) : "r"(sbase + SMB_JK + c * 4));
+                    const double2 *src = p.tab + (size_t)m * (FB_J0_ROWLEN / 2) + piece;
+                    const uint32_t dst = sbase + SMB_ROW + piece * (GCOLS * 16) + c * 16;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                }
+            }
+        }
+        if (qv >= 0 && tid < GS) {
+            const size_t v = (size_t)qv * GS + tid;
+            const uint32_t d = sbase + SMB_VIS + vbuf * (GS * 32) + tid * 32;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(p.a + v) : "memory");
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8), "l"(p.sw + v) : "memory");
-#ifdef FB_J0_HALFWARP
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + SMB_SW + (buf * GS + tid) * 8), "l"(p.sw + v) : "memory");
-#endif
             if (DEBRIS) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 16), "l"(p.kz + v) : "memory");
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 24), "l"(p.swV + v) : "memory");
         }
-        if (tid == GS && q2 >= 0)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sbase + SMB_AR + (buf ^ 1) * 16), "l"(p.arange + q2) : "memory");
+        if (qa >= 0 && tid == GS)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sbase + SMB_AR + slot * 16), "l"(p.arange + qa) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // J0 phase of this warp
-    auto produce = [&](const int buf) {
-        if (it.dcol >= 0 && tid >= FB_GRAM_THREADS - GS) {       // data column: G[N][v] = sqrt(w_v) Re V_v
-            const int vv = tid - (FB_GRAM_THREADS - GS);
-            sts_f64(sbase + SMB_G + (it.dcol * GLD + vv) * 8, lds_f64(sbase + SMB_VIS + buf * (GS * 32) + vv * 32 + 24));
-        }
-#ifdef FB_J0_HALFWARP
-        j0_columns4<DEBRIS>(p, sbase, buf, it.ncol, tid >> 5, lane, last_row);
-#else
-        j0_columns<DEBRIS>(p, sbase, buf, it.ncol, tid >> 5, lane, last_row);
-#endif
-    };
+    auto ring = [&](const int s) { return lds_v2f64(sbase + SMB_AR + (s & 3) * 16); };
 
     const long long q0 = it.q0, qs = it.qs;
     const int nst = it.nst;
-    // ---- prologue: rows and scalars of the first tile, range of the second --------------------------------------
-    stage_math(p.arange[q0], 0);
-    __syncthreads();
-    stage_copy(0, q0, nst > 1 ? q0 + qs : -1);
+    auto tile = [&](const int s) { return s < nst ? q0 + s * qs : -1LL; };
+    // ---- prologue: tile 0 prepared, rows of tile 1 chosen and on their way -----------------------------------------
+    {
+        const double2 ar0 = p.arange[q0];
+        select(ar0);
+        if (tid == 0) asm volatile("st.shared.v2.s32 [%0], {%1, %1};" ::"r"(sbase + SMB_NLIST), "r"(0) : "memory");
+        __syncthreads();
+        stage_copy(true, tile(0), 0, tile(1), 1);
+        stage_copy(false, tile(1), 1, tile(2), 2);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        prepare(ar0, 0, 0);
+        if (nst > 1) select(ring(1));
+        __syncthreads();
+        stage_copy(nst > 1, -1, 0, -1, 0);
+    }
     // ---- main loop: J0 phase, DMMA phase ------------------------------------------------------------------------
-    long long t_j0 = 0, t_mma = 0, t_last = clock64();
+#ifdef FB_GRAM_CLOCKS
+    long long t_j0 = 0, t_mma = 0, t_g0 = 0, t_last = clock64();
+#endif
     for (int s = 0; s < nst; s++) {
         const int b = s & 1;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                     // tile s staged; DMMAs of tile s - 1 done
+        __syncthreads();                                     // rows of tile s + 1 and scalars of tile s + 2 staged; DMMAs of tile s - 1 done
+#ifdef FB_GRAM_CLOCKS
         if (p.prof && tid == 0) { const long long t = clock64(); t_mma += t - t_last; t_last = t; }
-        produce(b);
-        if (s + 1 < nst) stage_math(lds_v2f64(sbase + SMB_AR + (b ^ 1) * 16), b ^ 1);
+#endif
+        // the tile's DMMAs first: the per-column DFMA chains of prepare() crawl while other warps stream DMMAs (one FP64
+        // pipe serves both: run first, they stretched the phase by a third), so they go last, on an idle pipe
+        j0_gemm<DEBRIS>(p, sbase, b, it.ncol / 8, tid >> 5, lane, last_row);
+#ifdef FB_GRAM_CLOCKS
+        if (p.prof && tid == 0) t_g0 += clock64() - t_last;
+#endif
+        if (s + 1 < nst) {
+            prepare(ring(s + 1), b ^ 1, b ^ 1);
+            if (s + 2 < nst) select(ring(s + 2));
+        }
         __syncthreads();
+#ifdef FB_GRAM_CLOCKS
         if (p.prof && tid == 0) { const long long t = clock64(); t_j0 += t - t_last; t_last = t; }
-        if (s + 1 < nst) stage_copy(b ^ 1, q0 + (s + 1) * qs, s + 2 < nst ? q0 + (s + 2) * qs : -1);     // flies during the DMMAs
-        stage_dmma<KIND, NR, NC>(acc, it.G, fr0, fr1, ta, tb, cbase, it.nmod);
+#endif
+        if (tid == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(sbase + SMB_NLIST + b * 4), "r"(0) : "memory");   // refilled by the next phase's prepare()
+        stage_copy(s + 2 < nst, tile(s + 2), b, tile(s + 3), (s + 3) & 3);     // flies during the DMMAs
+        stage_dmma<KIND, NR, NC>(acc, it.G, fr, ta, tb, cbase, it.nmod);
     }
+#ifdef FB_GRAM_CLOCKS
     if (p.prof && tid == 0) {
         t_mma += clock64() - t_last;
         atomicAdd((unsigned long long *)&p.prof[2 * blockIdx.x], (unsigned long long)t_j0);
         atomicAdd((unsigned long long *)&p.prof[2 * blockIdx.x + 1], (unsigned long long)t_mma);
-
+        atomicAdd((unsigned long long *)&p.prof[2 * gridDim.x], (unsigned long long)t_g0);
     }
+#endif
     // ---- write the partial block ------------------------------------------------------------------------------------
 #pragma unroll
     for (int r = 0; r < NR; r++)
@@ -494,24 +523,20 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
 
         // column tables of this block
         __syncthreads();                      // every warp is done with the previous item
-        it.my_jk = -2.0;
         {
-            const int col = tid < GCOLS ? tid : tid - GCOLS;          // both halves of the CTA look at column code `col`
-            double v = -2.0, h = 0.0;
-            if (col < it.ncol) {
-                const int g = col < it.ncolA ? ty.a_t0 * 8 + col : ty.b_t0 * 8 + (col - it.ncolA);
+            const int last = ty.kind == FB_KIND_OFF ? max(ty.a_t0 + ty.a_nt, ty.b_t0 + ty.b_nt) : ty.a_t0 + ty.a_nt;
+            const double jref = p.jk[min(p.N, last * 8) - 1];
+            if (tid == 0) sts_f64(sbase + SMB_JREF, jref);
+            if (tid < it.ncol) {
+                const int g = tid < it.ncolA ? ty.a_t0 * 8 + tid : ty.b_t0 * 8 + (tid - it.ncolA);
+                double v = -2.0, h = 0.0;
                 if (g < p.N) { v = p.jk[g]; if (DEBRIS) h = p.H2[g]; }
                 else if (g == p.N) v = -1.0;
-            }
-            if (tid >= GCOLS) {
-                it.my_jk = v;                                          // staging duty (stage_math)
-            } else {
-                if (DEBRIS) sts_f64(sbase + SMB_H2 + col * 8, h);
-                if (v == -2.0 && col < it.ncol) {                      // zero padding columns stay zero for the whole item
-                    for (int x = 0; x < GS; x++) sts_f64(sbase + SMB_G + (col * GLD + x) * 8, 0.0);
-                }
+                sts_v2f64(sbase + SMB_COL + tid * 16, v, v >= 0.0 ? v / jref : 0.0);
+                if (DEBRIS) sts_f64(sbase + SMB_H2 + tid * 8, h);
             }
         }
+        __syncthreads();                      // the column tables are read by other threads (select / prepare)
         {
             const int gA = p.N - ty.a_t0 * 8, gB = p.N - ty.b_t0 * 8;
             it.dcol = (gA >= 0 && gA < it.ncolA) ? gA : ((gB >= 0 && gB < it.ncol - it.ncolA) ? it.ncolA + gB : -1);
@@ -930,10 +955,14 @@ int fb_enqueue_gram(fb_ctx *ctx, FbLane &ln, int chan, int vis_model)
     args.cta_off = ctx->d_work; args.items = ctx->d_work + grid + 1; args.type_tab = ctx->d_work + grid + 1 + 3 * (size_t)n_items;
     args.H2 = ctx->d_H2; args.partial = ln.d_partial + (size_t)chan * n_items * FB_PSZ;
     args.prof = nullptr;
+#ifdef FB_GRAM_CLOCKS
     static const bool prof = getenv("FB_GRAM_PROF") != nullptr;
+#else
+    const bool prof = false;
+#endif
     if (prof) {
-        FB_CUDA(cudaMalloc(&args.prof, sizeof(long long) * 2 * grid));
-        FB_CUDA(cudaMemsetAsync(args.prof, 0, sizeof(long long) * 2 * grid, ln.stream));
+        FB_CUDA(cudaMalloc(&args.prof, sizeof(long long) * (2 * grid + 1)));
+        FB_CUDA(cudaMemsetAsync(args.prof, 0, sizeof(long long) * (2 * grid + 1), ln.stream));
     }
     if (vis_model == FB_MODEL_DEBRIS) {
         static bool attr = false;
@@ -946,9 +975,9 @@ int fb_enqueue_gram(fb_ctx *ctx, FbLane &ln, int chan, int vis_model)
     }
     FB_CUDA(cudaGetLastError());
     if (args.prof) {
-        std::vector<long long> h(2 * grid);
+        std::vector<long long> h(2 * grid + 1);
         FB_CUDA(cudaStreamSynchronize(ln.stream));
-        FB_CUDA(cudaMemcpy(h.data(), args.prof, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
+        FB_CUDA(cudaMemcpy(h.data(), args.prof, sizeof(long long) * (2 * grid + 1), cudaMemcpyDeviceToHost));
         long long j0_sum = 0, mma_sum = 0, j0_max = 0, mma_max = 0, tot_max = 0, tot_min = -1;
         for (int b = 0; b < grid; b++) {
             j0_sum += h[2 * b]; mma_sum += h[2 * b + 1];
@@ -956,8 +985,8 @@ int fb_enqueue_gram(fb_ctx *ctx, FbLane &ln, int chan, int vis_model)
             tot_max = std::max(tot_max, h[2 * b] + h[2 * b + 1]);
             tot_min = tot_min < 0 ? h[2 * b] + h[2 * b + 1] : std::min(tot_min, h[2 * b] + h[2 * b + 1]);
         }
-        fprintf(stderr, "[fb_gram prof] chan=%d  per-CTA clocks: J0 avg %.0f max %lld | DMMA avg %.0f max %lld | total min %lld max %lld\n",
-                chan, (double)j0_sum / grid, j0_max, (double)mma_sum / grid, mma_max, tot_min, tot_max);
+        fprintf(stderr, "[fb_gram prof] chan=%d  per-CTA clocks: J0 avg %.0f max %lld (warp 0's own J0 DMMAs %.0f) | DMMA avg %.0f max %lld | total min %lld max %lld\n",
+                chan, (double)j0_sum / grid, j0_max, (double)h[2 * grid] / grid, (double)mma_sum / grid, mma_max, tot_min, tot_max);
         cudaFree(args.prof);
     }
     return 0;
