@@ -1,4 +1,4 @@
-"""A/B timing of the Gram kernel for the library named by FRANK_B200_LIB (dev tool): python scripts/ab_gram.py [N ...]"""
+"""A/B timing of the Gram kernel for the library named by FRANK_B200_LIB (dev tool): python scripts/ab_gram.py [N[:n_vis] ...]"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -20,8 +20,9 @@ m = vm.map_visibilities(u, v, V, w)
 o = fo.map_visibilities(odht, u, v, V, w, *bench.GEOM)
 d = np.sqrt(np.diag(o['M']))
 res['parity_cs'] = float(np.max(np.abs(m['M'] - o['M']) / np.outer(d, d)))
-for N in [int(x) for x in sys.argv[1:]] or [300]:
-    n = 10_000_000
+# arguments: N or N:n_vis (default 1e7 visibilities)
+for arg in sys.argv[1:] or ['300']:
+    N, n = (int(float(x)) for x in (arg.split(':') + ['1e7'])[:2])
     dht = DiscreteHankelTransform(1.6 / rad_to_arcsec, N)
     vm = VisibilityMapping(dht, g, verbose=False)
     ud, vd, Vd, wd = bench.synthetic_visibilities_device(n, dht, seed=1)
@@ -29,5 +30,5 @@ for N in [int(x) for x in sys.argv[1:]] or [300]:
     for _ in range(5):
         vm.map_visibilities(ud, vd, Vd, wd)
         t.append(vm.last_timing['gram_ms'])
-    res[f'gram_ms_N{N}'] = [round(float(x), 3) for x in t]
+    res[f'gram_ms_N{N}_n{n}'] = [round(float(x), 3) for x in t]
 print(json.dumps(res))
