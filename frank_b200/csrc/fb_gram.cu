@@ -255,7 +255,6 @@ struct ItemCtx {
     int nst;
     int ld;
     double *out;
-    int dcol;              // local index of the data column in this block, -1 if absent
 };
 
 // DMMAs of one tile for one warp.  G: generic pointer to the tile; fr: this lane's fragment offset inside a tile row;
@@ -537,10 +536,6 @@ __global__ void __launch_bounds__(FB_GRAM_THREADS, 1) k_gram(const GramArgs p)
             }
         }
         __syncthreads();                      // the column tables are read by other threads (select / prepare)
-        {
-            const int gA = p.N - ty.a_t0 * 8, gB = p.N - ty.b_t0 * 8;
-            it.dcol = (gA >= 0 && gA < it.ncolA) ? gA : ((gB >= 0 && gB < it.ncol - it.ncolA) ? it.ncolA + gB : -1);
-        }
 
         // this warp's register block (warp-uniform).  Latin-square assignment of (row group, column group) to
         // (slot, sub-partition) balances the DMMA count of the four SM sub-partitions.
