@@ -750,8 +750,10 @@ int cdiv4(int n) { return (n + 3) / 4; }
 bool off_fits(int a, int b) { return cdiv4(a) * cdiv4(b) <= FB_ACC && cdiv4(a) <= 5 && cdiv4(b) <= 5 && (a + b) * 8 <= FB_GCOLS; }
 bool diag_fits(int n) { return cdiv4(n) * cdiv4(n / 2 + 1) <= FB_ACC && cdiv4(n) <= 5 && n * 8 <= FB_GCOLS; }
 
-// Cost of a block per tile of FB_TV visibilities, in FP64-pipe clocks of the busiest SM sub-partition:
-// a DMMA holds the pipe for 16 clocks, a J0 evaluation is ~10 FP64 instructions of 2 clocks for 32 lanes.
+// Cost of a block per tile of FB_TV visibilities, in FP64-pipe clocks of the busiest SM sub-partition: a DMMA holds the
+// pipe for 16 clocks; a column of the design-matrix tile costs 8 (two DMMAs per 8 x 8 block, a quarter of the tile's
+// visibilities per sub-partition); re-centring the polynomials, the barriers and the ramps cost about 1500 per tile
+// (measured with the in-kernel clocks; the split between the block types is flat within 0.5 % around these values).
 double block_cost(const FbGramType &ty)
 {
     const int nrows = ty.a_nt, ncols = ty.kind == FB_KIND_OFF ? ty.b_nt : ty.a_nt / 2 + 1;
@@ -762,8 +764,9 @@ double block_cost(const FbGramType &ty)
         worst = std::max(worst, t);
     }
     const int cols = 8 * (ty.kind == FB_KIND_OFF ? ty.a_nt + ty.b_nt : ty.a_nt);
-    static const double j0w = getenv("FB_J0_COST") ? atof(getenv("FB_J0_COST")) : 12.0;
-    return 16.0 * (FB_TV / 4) * worst + j0w * cols;
+    static const double j0w = getenv("FB_J0_COST") ? atof(getenv("FB_J0_COST")) : 8.0;
+    static const double j0f = getenv("FB_J0_FIXED") ? atof(getenv("FB_J0_FIXED")) : 1500.0;
+    return 16.0 * (FB_TV / 4) * worst + j0w * cols + j0f;
 }
 
 struct GramPlan {
