@@ -252,9 +252,21 @@ def main():
         distributed.init_library_comm(ctx)          # the library all-reduces (M, j, H0) in-call, on its own stream
     u, v, V, w = synthetic_visibilities_device(n, dht, seed=12345 + rank)
     chan = None
+    chan_sharding = None
     if nchan > 1:
+        # channel-major sharding (frank_b200.distributed.channel_major_order): a rank holds as few channels as possible, so
+        # its tiles of 64 baseline-sorted visibilities stay narrow in baseline (sparse regime)
         gen = torch.Generator(device='cuda').manual_seed(777 + rank)
-        chan = torch.randint(0, nchan, (n,), device='cuda', dtype=torch.int32, generator=gen)
+        if world % nchan == 0:
+            chan = torch.full((n,), rank // (world // nchan), device='cuda', dtype=torch.int32)
+            chan_sharding = 'channel-major: one channel per rank'
+        elif nchan % world == 0:
+            k = nchan // world
+            chan = rank * k + torch.randint(0, k, (n,), device='cuda', dtype=torch.int32, generator=gen)
+            chan_sharding = f'channel-major: {k} channels per rank' if world > 1 else None
+        else:
+            chan = torch.randint(0, nchan, (n,), device='cuda', dtype=torch.int32, generator=gen)
+            chan_sharding = 'every rank holds a share of every channel'
     gdev = geom.device_scalars()
     nM, nj = nchan * N * N, nchan * N
     out = torch.zeros(nM + nj + 1, dtype=torch.float64, device='cuda')
@@ -390,6 +402,7 @@ def main():
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': wl['scaling'], 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': wl['name'].format(n=float(n)), 'n_vis_per_gpu': n, 'n_vis_total': n_total, 'N': N, 'channels': nchan,
+                       'channel_sharding': chan_sharding,
                        'vis_model': wl['model'], 'Rmax_arcsec': RMAX, 'geometry': GEOM,
                        'l2': f'inputs ({40 * n / 1e6:.0f} MB per step) exceed the 126 MB L2',
                        'multi_gpu': 'visibility shards; the library all-reduces (M, j, H0) over its NCCL communicator inside the call, on its own stream'},

@@ -148,7 +148,7 @@ class VisibilityMapping(object):
             weights = f64(weights, 'weights')
         return u, v, Vr, weights, w_stride
 
-    def map_visibilities(self, u, v, V, weights, frequencies=None, geometry=None):
+    def map_visibilities(self, u, v, V, weights, frequencies=None, geometry=None, channels=None):
         r"""Compute M = H^T w H, j = H^T w V and the null likelihood H0 from the visibilities
         (frank/statistical_models.py:109-237).
 
@@ -158,6 +158,8 @@ class VisibilityMapping(object):
 
         With `frequencies` the Gram matrices of all channels come out of ONE device call (the channel index is the
         high part of the kernel's sort key, statistical_models.py:175-214); nothing is split on the host.
+        `channels` (not in the reference; sorted, unique) fixes the channel list instead of np.unique(frequencies): a rank
+        of a sharded call must use the GLOBAL list even if its slice misses a channel (that channel's M, j are zero).
 
         As in the reference the deprojection always uses the geometry given at construction;
         a `geometry` argument only lands in the returned hash (statistical_models.py:158-165, 227).
@@ -194,13 +196,30 @@ class VisibilityMapping(object):
                     'hash': [False, self._DHT, geometry, self._vis_model, self._scale_height]}
 
         # multi-frequency: channel index = position in np.unique(frequencies) (statistical_models.py:180-189)
+        if channels is not None:
+            channels = np.asarray(channels, dtype=np.float64).reshape(-1)
+            if channels.size == 0 or np.any(np.diff(channels) <= 0):
+                raise ValueError("map_visibilities: channels must be sorted and unique")
         if on_device:
             import torch
-            channels, chan = torch.unique(frequencies.reshape(-1), return_inverse=True)
+            f = frequencies.reshape(-1)
+            if channels is None:
+                channels, chan = torch.unique(f, return_inverse=True)
+                channels = channels.cpu().numpy()
+            else:
+                ch = torch.as_tensor(channels, dtype=f.dtype, device=f.device)
+                chan = torch.searchsorted(ch, f.contiguous()).clamp_(max=len(channels) - 1)
+                if f.numel() and not bool(torch.all(ch[chan] == f)):
+                    raise ValueError("map_visibilities: a frequency is not in `channels`")
             chan = chan.to(torch.int32).contiguous()
-            channels = channels.cpu().numpy()
         else:
-            channels, chan = np.unique(np.asarray(frequencies).reshape(-1), return_inverse=True)
+            f = np.asarray(frequencies).reshape(-1)
+            if channels is None:
+                channels, chan = np.unique(f, return_inverse=True)
+            else:
+                chan = np.minimum(np.searchsorted(channels, f), len(channels) - 1)
+                if f.size and not np.array_equal(channels[chan], f):
+                    raise ValueError("map_visibilities: a frequency is not in `channels`")
             chan = np.ascontiguousarray(chan, dtype=np.int32)
         if chan.shape[0] != u.shape[0]:
             raise ValueError("map_visibilities: frequencies must have the length of u")

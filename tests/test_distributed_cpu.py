@@ -65,6 +65,55 @@ def test_sharded_mapping_range_error_is_global(tmp_path):
     assert 'raised' in np.load(tmp_path / 'r0.npz').files and 'raised' in np.load(tmp_path / 'r1.npz').files
 
 
+class _OracleChannelMapper(_OracleMapper):
+    """Multi-frequency stand-in with the product's `channels` contract: one (M, j) per entry of the GLOBAL channel list."""
+
+    def map_visibilities(self, u, v, V, w, frequencies=None, channels=None):
+        assert channels is not None, "a sharded multi-frequency call must pass the global channel list"
+        N = self.dht.N if hasattr(self.dht, 'N') else len(self.dht.j_nk)
+        Ms, js, H0 = np.zeros((len(channels), N, N)), np.zeros((len(channels), N)), 0.0
+        for c, f in enumerate(channels):
+            s = frequencies == f
+            if s.any():
+                m = fo.map_visibilities(self.dht, u[s], v[s], V[s], w[s], 30., 40., 1e-3, -2e-3)
+                Ms[c], js[c] = m['M'], m['j']
+                H0 += m['null_likelihood']
+        self.seen = np.unique(frequencies)
+        return {'M': Ms, 'j': js, 'null_likelihood': H0}
+
+
+def _chan_worker(rank, world, port, out_dir, channel_major):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from frank_b200.distributed import map_visibilities_sharded
+    u, v, V, w, _ = fo.synthetic_disc(3000, 24, seed=5)
+    # frequency-sorted data: the second rank's slice has no visibility of the first channel, and the other way round
+    freqs = np.repeat([1.0e11, 2.3e11], 1500) if not channel_major else np.tile([1.0e11, 2.3e11], 1500)
+    vm = _OracleChannelMapper(24)
+    m = map_visibilities_sharded(vm, u, v, V, w, frequencies=freqs, channel_major=channel_major)
+    np.savez(os.path.join(out_dir, f'r{rank}.npz'), M=m['M'], j=m['j'], H0=m['null_likelihood'], seen=vm.seen)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('channel_major', [False, True])
+def test_sharded_multifrequency_uses_the_global_channel_list(tmp_path, channel_major):
+    """A rank whose slice misses a channel still returns that channel (zeros), so the all-reduce lines up; with
+    channel_major=True interleaved frequencies are dealt so that every rank sees ONE channel."""
+    world = 2
+    mp.spawn(_chan_worker, args=(world, _free_port(), str(tmp_path), channel_major), nprocs=world, join=True)
+    u, v, V, w, dht = fo.synthetic_disc(3000, 24, seed=5)
+    freqs = np.repeat([1.0e11, 2.3e11], 1500) if not channel_major else np.tile([1.0e11, 2.3e11], 1500)
+    r0, r1 = np.load(tmp_path / 'r0.npz'), np.load(tmp_path / 'r1.npz')
+    assert r0['M'].shape == (2, 24, 24) and np.array_equal(r0['M'], r1['M'])
+    assert len(r0['seen']) == 1 and len(r1['seen']) == 1 and r0['seen'][0] != r1['seen'][0]
+    for c, f in enumerate([1.0e11, 2.3e11]):
+        s = freqs == f
+        ref = fo.map_visibilities(dht, u[s], v[s], V[s], w[s], 30., 40., 1e-3, -2e-3)
+        assert np.max(np.abs(r0['M'][c] - ref['M'])) <= 1e-14 * np.max(np.abs(ref['M']))
+        assert np.max(np.abs(r0['j'][c] - ref['j'])) <= 1e-13 * np.max(np.abs(ref['j']))
+
+
 def test_shard_bounds_cover():
     from frank_b200.distributed import shard_bounds
     for n in [0, 1, 7, 64, 1000003]:

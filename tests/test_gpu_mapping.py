@@ -374,6 +374,31 @@ def test_multichannel_matches_per_channel_calls(fb, golden):
     assert abs(H0 - m['null_likelihood']) <= 1e-13 * abs(H0)
 
 
+def test_explicit_channel_list_with_an_empty_channel(fb, golden):
+    """`channels=` fixes the channel list (what a rank of a sharded multi-frequency call must do): a channel without
+    visibilities comes back as zeros, the others equal the call that only knows the channels present."""
+    import torch
+    g = golden('mapping.npz')
+    dht, vm = mapping_from_golden(fb, g)
+    rng = np.random.default_rng(11)
+    n = len(g['u'])
+    freqs = rng.choice(np.array([1.0, 5.0]), n, p=[0.6, 0.4])
+    ref = vm.map_visibilities(g['u'], g['v'], g['V'], g['w'], frequencies=freqs)
+    m = vm.map_visibilities(g['u'], g['v'], g['V'], g['w'], frequencies=freqs, channels=[1.0, 2.0, 5.0])
+    assert m['M'].shape == (3,) + ref['M'].shape[1:] and list(m['channels']) == [1.0, 2.0, 5.0]
+    assert not m['M'][1].any() and not m['j'][1].any()
+    for c, r in ((0, 0), (2, 1)):
+        d = np.sqrt(np.diag(ref['M'][r]))
+        assert np.max(np.abs(m['M'][c] - ref['M'][r]) / np.outer(d, d)) < 16 * EPS
+        assert np.max(np.abs(m['j'][c] - ref['j'][r])) <= 1e-14 * np.max(np.abs(ref['j'][r]))
+    assert abs(m['null_likelihood'] - ref['null_likelihood']) <= 1e-13 * abs(ref['null_likelihood'])
+    dev = [torch.as_tensor(np.ascontiguousarray(x)).cuda() for x in (g['u'], g['v'], g['V'], g['w'], freqs)]
+    md = vm.map_visibilities(dev[0], dev[1], dev[2], dev[3], frequencies=dev[4], channels=[1.0, 2.0, 5.0])
+    assert np.array_equal(md['M'], m['M']) and np.array_equal(md['j'], m['j'])
+    with pytest.raises(ValueError):
+        vm.map_visibilities(g['u'], g['v'], g['V'], g['w'], frequencies=freqs, channels=[1.0, 2.0])
+
+
 @pytest.mark.parametrize('staging', ['pinned', 'pageable'])
 def test_chunked_host_pipeline(fb, staging):
     """The K-deep copy / compute pipeline of the host entry point (several chunks over two lanes, growing chunk sizes,
