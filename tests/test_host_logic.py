@@ -102,3 +102,20 @@ def test_j0_table_accuracy(tmp_path):
     # (half an ulp of the value itself is 1.1e-16 / 5.6e-17 / 2.8e-17 / 1.4e-17 at the top of these ranges)
     assert near[0] <= 1.2e-16 and near[1] <= 7e-17 and near[2] <= 3.5e-17 and near[3] <= 1.5e-17
     assert far[0] <= 1.3e-16 and far[1] <= 7e-17 and far[2] <= 3.5e-17 and far[3] <= 1.5e-17
+
+
+def test_j0_recentred_product_accuracy(tmp_path):
+    """The J0 phase of k_gram forms a tile of the design matrix as a rank-8 product: the table row of a (column, tile) pair is
+    shifted to the tile centre and rescaled to the tile variable, the visibilities contribute sqrt(w) times its powers
+    (fb_gram.cu: select / prepare / j0_gemm).  tests/native/j0_recentre_check.cpp restates that arithmetic on the host, in the
+    kernel's operation order, and measures G / sqrt(w) against glibc's 80-bit j0l(a j_k).  The bars sit where SciPy's own J0
+    -- what the reference calls -- does: 4.4e-16 for x <= 30, 5.6e-17 above."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'j0_recentre_check')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(root, 'tests', 'native', 'j0_recentre_check.cpp')])
+    out = [float(v) for v in subprocess.check_output([exe, '6400', '40000']).decode().split()]
+    worst, rejected = out[:4], out[4]
+    # ranges: x < 5, < 30, < 200, < 6400; measured 4.0e-16 / 1.4e-16 / 6.6e-17 / 2.3e-17
+    assert worst[0] <= 4.5e-16 and worst[1] <= 2.0e-16 and worst[2] <= 1.0e-16 and worst[3] <= 4.0e-17
+    assert 0.0 < rejected < 0.2          # tiles wider than a row's validity window are rejected (per-visibility path), not mis-evaluated
